@@ -1,0 +1,51 @@
+"""Shared definitions of the golden cases (what tests/golden/make_golden.py ran the reference on)."""
+import os
+
+import numpy as np
+
+from oracle import eryn_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def corr_prec(d, seed=99):
+    A = np.random.RandomState(seed).randn(d, d)
+    cov = A @ A.T / d + np.eye(d)
+    return np.linalg.inv(cov)
+
+
+COV3 = np.array([[0.04, 0.01, 0.0], [0.01, 0.09, -0.02], [0.0, -0.02, 0.01]])
+
+# name -> (likelihood factory(ndim), moves, weights, tempering extras)
+CASES = {
+    "c1_kat1": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), moves=[dict(kind="stretch", a=2.0)]),
+    "pt_kat2": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), moves=[dict(kind="stretch", a=2.0)]),
+    "c2_small": dict(like=lambda d: orc.GaussianLike(np.zeros(d), corr_prec(d)), moves=[dict(kind="stretch", a=2.0)]),
+    "c2_tightprior": dict(like=lambda d: orc.GaussianLike(np.zeros(d), corr_prec(d)),
+                          moves=[dict(kind="stretch", a=2.0)]),
+    "c3_small": dict(like=lambda d: orc.RosenbrockLike(),
+                     moves=[dict(kind="stretch", a=2.0),
+                            dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.01)))],
+                     weights=[0.5, 0.5]),
+    "gauss_matrix": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                         moves=[dict(kind="gaussian", proposal=dict(kind="matrix", cov=COV3))]),
+    "odd_walkers": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), moves=[dict(kind="stretch", a=1.5)]),
+    "noadapt_noperm": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                           moves=[dict(kind="stretch", a=2.0)], adaptive=False, permute=False),
+}
+
+
+def load(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    T, W = int(g["ntemps"]), int(g["nwalkers"])
+    g["accepted"] = np.unpackbits(g["accepted"], axis=-1)[..., :W].astype(bool)
+    return g
+
+
+def seeded_streams(seed):
+    """The reference's two streams after `np.random.seed(seed)` + sampler construction
+    (ensemble.py:604,651-652: the private stream is a copy of the global state)."""
+    glob = np.random.RandomState(seed)
+    private = np.random.RandomState()
+    private.set_state(glob.get_state())
+    return private, glob
