@@ -1,0 +1,139 @@
+"""ctypes binding of `liberyn_b200.so` (C ABI declared in include/eryn_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is present, every compute
+entry point raises.  Importing this module only loads the shared object (no CUDA call)."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "liberyn_b200.so")
+
+EB_MAX_TEMPS = 256
+EB_MAX_ROW = 32
+EB_RNG_REPLAY, EB_RNG_PHILOX = 0, 1
+EB_LIKE_GAUSSIAN, EB_LIKE_ROSENBROCK, EB_LIKE_GMIX = 0, 1, 2
+
+_STATUS = {1: "EB_ERR_INVALID", 2: "EB_ERR_UNSUPPORTED", 3: "EB_ERR_CUDA", 4: "EB_ERR_NODEVICE"}
+
+vp = C.c_void_p
+
+
+class eb_state(C.Structure):
+    _fields_ = [("ntemps", C.c_int32), ("nwalkers", C.c_int32), ("nleaves", C.c_int32), ("ndim", C.c_int32),
+                ("coords", vp), ("logl", vp), ("logp", vp), ("inds", vp), ("betas", vp)]
+
+
+class eb_prior(C.Structure):
+    _fields_ = [("lo", vp), ("hi", vp), ("logpdf", vp)]
+
+
+class eb_like(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ncomp", C.c_int32), ("nparams", C.c_int32), ("_pad", C.c_int32),
+                ("params", vp)]
+
+
+class eb_stretch_rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("randomize_split", C.c_int32), ("sub_idx", vp), ("comp_idx", vp),
+                ("rint", vp), ("u_z", vp), ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp),
+                ("iter", C.c_uint64)]
+
+
+class eb_gauss_rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("cov_kind", C.c_int32), ("scale", C.c_double), ("chol", vp), ("delta", vp),
+                ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+
+
+class eb_swap_rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("permute", C.c_int32), ("iperm", vp), ("i1perm", vp), ("u", vp),
+                ("next_pos", vp), ("u_at", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+
+
+class eb_ctrl(C.Structure):
+    _fields_ = [("iter", C.c_uint64), ("time", C.c_int64), ("ticket", C.c_uint32), ("_pad", C.c_uint32),
+                ("swaps_work", C.c_int32 * EB_MAX_TEMPS), ("swaps_accepted", C.c_int32 * EB_MAX_TEMPS),
+                ("swaps_total", C.c_uint64 * EB_MAX_TEMPS)]
+
+
+class eb_adapt(C.Structure):
+    _fields_ = [("adaptive", C.c_int32), ("stop_adaptation", C.c_int32), ("adaptation_lag", C.c_double),
+                ("adaptation_time", C.c_double)]
+
+
+class eb_host_job(C.Structure):
+    _fields_ = [("ntemps", C.c_int32), ("nwalkers", C.c_int32), ("nleaves", C.c_int32), ("ndim", C.c_int32),
+                ("coords_host", vp), ("logl_host", vp), ("logp_host", vp), ("betas_host", vp),
+                ("prior_lo_host", vp), ("prior_hi_host", vp),
+                ("like_kind", C.c_int32), ("like_ncomp", C.c_int32), ("like_nparams", C.c_int32), ("_pad", C.c_int32),
+                ("like_params_host", vp), ("stretch_a", C.c_double), ("gauss_scale", C.c_double),
+                ("seed", C.c_uint64), ("iter0", C.c_uint64), ("adapt", eb_adapt), ("adapt_time0", C.c_int64),
+                ("permute", C.c_int32), ("randomize_split", C.c_int32), ("move_schedule_host", vp),
+                ("swaps_accepted_host", vp), ("accepted_count_host", vp)]
+
+
+# every symbol include/eryn_b200.h declares: name -> (restype, argtypes)
+P = C.POINTER
+SYMBOLS = {
+    "eb_abi_version": (C.c_int, []),
+    "eb_last_error": (C.c_char_p, []),
+    "eb_device_count": (C.c_int, []),
+    "eb_ctrl_size": (C.c_size_t, []),
+    "eb_struct_size": (C.c_size_t, [C.c_int]),
+    "eb_eval_state": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), vp]),
+    "eb_stretch_half_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), C.c_double, C.c_int32,
+                                       P(eb_stretch_rng), vp, vp, vp]),
+    "eb_gaussian_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), P(eb_gauss_rng), vp, vp, vp]),
+    "eb_pt_swap": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
+    "eb_advance_iter": (C.c_int, [vp, vp]),
+    "eb_stretch_propose": (C.c_int, [P(eb_state), C.c_double, C.c_int32, P(eb_stretch_rng), vp, vp, vp, vp]),
+    "eb_accept_update": (C.c_int, [P(eb_state), vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int32, P(eb_stretch_rng),
+                                   vp, vp, vp]),
+    "eb_box_log_prior": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, P(eb_prior), vp, vp]),
+    "eb_run_host": (C.c_int, [P(eb_host_job), C.c_int32]),
+}
+
+STRUCTS = [eb_state, eb_prior, eb_like, eb_stretch_rng, eb_gauss_rng, eb_swap_rng, eb_ctrl, eb_adapt, eb_host_job]
+
+_lib = None
+
+
+class ErynB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building it is `python -m eryn_b200.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ErynB200Error(
+            f"{LIB_PATH} not found. eryn_b200 has no CPU fallback; build the CUDA library with "
+            "`python -m eryn_b200.build`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here = ABI mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.eb_abi_version() != 1:
+        raise ErynB200Error("liberyn_b200.so ABI version mismatch; rebuild")
+    for i, st in enumerate(STRUCTS):
+        if lib.eb_struct_size(i) != C.sizeof(st):
+            raise ErynB200Error(f"ABI layout mismatch for {st.__name__}: C {lib.eb_struct_size(i)} vs ctypes {C.sizeof(st)}")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().eb_last_error().decode(errors="replace")
+        kind = _STATUS.get(rc, str(rc))
+        if rc == 1:
+            raise ValueError(f"{what}: {msg}")
+        raise ErynB200Error(f"{what}: {kind}: {msg}")
+
+
+def require_device():
+    lib = load()
+    if lib.eb_device_count() < 1:
+        raise ErynB200Error("no CUDA device visible: eryn_b200 runs only on the GPU (no CPU fallback)")
+    return lib

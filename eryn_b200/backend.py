@@ -1,0 +1,105 @@
+"""In-memory chain store with the getters of eryn.backends.Backend that the hot path's callers use
+(backend.py:616-1091).  HDF5 storage is host I/O outside this build's scope."""
+import numpy as np
+
+from .state import State
+
+__all__ = ["Backend"]
+
+
+class Backend(object):
+    def __init__(self, store_missing_leaves=np.nan):
+        self.initialized = False
+        self.store_missing_leaves = store_missing_leaves
+
+    def reset(self, nwalkers, ndims, nleaves_max=1, ntemps=1, branch_names=None, nbranches=1, rj=False,
+              moves=None, key_order=None, **info):
+        self.nwalkers, self.ntemps = int(nwalkers), int(ntemps)
+        self.branch_names = list(branch_names) if branch_names is not None else ["model_0"]
+        self.ndims = ndims if isinstance(ndims, dict) else {n: ndims for n in self.branch_names}
+        self.nleaves_max = nleaves_max if isinstance(nleaves_max, dict) else {n: nleaves_max for n in self.branch_names}
+        self.rj = rj
+        self.move_keys = list(moves) if moves is not None else None
+        self.key_order = key_order
+        self.iteration = 0
+        self.accepted = np.zeros((self.ntemps, self.nwalkers), dtype=int)
+        self.swaps_accepted = np.zeros((self.ntemps - 1,), dtype=int)
+        self.chain = {n: np.empty((0, self.ntemps, self.nwalkers, self.nleaves_max[n], self.ndims[n]))
+                      for n in self.branch_names}
+        self.inds = {n: np.empty((0, self.ntemps, self.nwalkers, self.nleaves_max[n]), dtype=bool)
+                     for n in self.branch_names}
+        self.log_like = np.empty((0, self.ntemps, self.nwalkers))
+        self.log_prior = np.empty((0, self.ntemps, self.nwalkers))
+        self.betas = np.empty((0, self.ntemps))
+        self.move_info = {k: dict(acceptance_fraction=np.zeros((self.ntemps, self.nwalkers)))
+                          for k in (self.move_keys or [])}
+        self.random_state = None
+        self.initialized = True
+
+    @property
+    def shape(self):
+        return {n: (self.ntemps, self.nwalkers, self.nleaves_max[n], self.ndims[n]) for n in self.branch_names}
+
+    def grow(self, ngrow, blobs=None):
+        i = ngrow - (len(self.log_like) - self.iteration)
+        if i <= 0:
+            return
+        for n in self.branch_names:
+            self.chain[n] = np.concatenate([self.chain[n], np.empty((i,) + self.chain[n].shape[1:])], axis=0)
+            self.inds[n] = np.concatenate([self.inds[n], np.empty((i,) + self.inds[n].shape[1:], dtype=bool)], axis=0)
+        self.log_like = np.concatenate([self.log_like, np.empty((i, self.ntemps, self.nwalkers))], axis=0)
+        self.log_prior = np.concatenate([self.log_prior, np.empty((i, self.ntemps, self.nwalkers))], axis=0)
+        self.betas = np.concatenate([self.betas, np.empty((i, self.ntemps))], axis=0)
+
+    def save_step(self, state, accepted, rj_accepted=None, swaps_accepted=None, moves_accepted_fraction=None):
+        it = self.iteration
+        if it >= len(self.log_like):
+            raise ValueError("backend is full: call grow() first")
+        for n, br in state.branches.items():
+            self.inds[n][it] = br.inds
+            c = br.coords.copy()
+            c[~br.inds] = self.store_missing_leaves  # backend.py:1053-1059
+            self.chain[n][it] = c
+        self.log_like[it] = state.log_like
+        self.log_prior[it] = state.log_prior
+        if state.betas is not None:
+            self.betas[it] = state.betas
+        self.accepted += np.asarray(accepted).astype(int)
+        if swaps_accepted is not None:
+            self.swaps_accepted += np.asarray(swaps_accepted).astype(int)
+        if moves_accepted_fraction is not None:
+            for k, v in moves_accepted_fraction.items():
+                self.move_info[k]["acceptance_fraction"][:] = v
+        self.random_state = state.random_state
+        self.iteration += 1
+
+    def _get(self, arr, thin=1, discard=0):
+        return arr[discard + thin - 1:self.iteration:thin]
+
+    def get_chain(self, thin=1, discard=0):
+        return {n: self._get(self.chain[n], thin, discard) for n in self.branch_names}
+
+    def get_inds(self, thin=1, discard=0):
+        return {n: self._get(self.inds[n], thin, discard) for n in self.branch_names}
+
+    def get_log_like(self, thin=1, discard=0):
+        return self._get(self.log_like, thin, discard)
+
+    def get_log_prior(self, thin=1, discard=0):
+        return self._get(self.log_prior, thin, discard)
+
+    def get_betas(self, thin=1, discard=0):
+        return self._get(self.betas, thin, discard)
+
+    def get_last_sample(self):
+        if (not self.initialized) or self.iteration <= 0:
+            raise AttributeError("you must run the sampler with 'store == True' before accessing the results")
+        it = self.iteration - 1
+        coords = {n: self.chain[n][it].copy() for n in self.branch_names}
+        inds = {n: self.inds[n][it].copy() for n in self.branch_names}
+        return State(coords, inds=inds, log_like=self.log_like[it].copy(), log_prior=self.log_prior[it].copy(),
+                     betas=self.betas[it].copy(), random_state=self.random_state)
+
+    @property
+    def acceptance_fraction(self):
+        return self.accepted / float(max(self.iteration, 1))

@@ -1,0 +1,153 @@
+// Part of eryn_b200 (kernel overview in common.cuh). Built with --fmad=false.
+#include "common.cuh"
+
+namespace eb {
+
+// ================================================================================================
+// K2: fused Gaussian Metropolis step (all walkers at once, mh.py:56-193)
+// ================================================================================================
+struct GaussArgs {
+  Common c;
+  int cov_kind; double scale; const double* chol; const double* delta; const double* u_acc;
+  int philox;
+  uint32_t seed_lo, seed_hi; const unsigned long long* iter_dev; unsigned long long iter;
+  uint8_t* accepted; uint32_t* accepted_count;
+};
+
+template <int DMAX, int LIKE, bool PHILOX>
+__global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p) {
+  extern __shared__ double sm[];
+  const Common& c = p.c;
+  stage_params(c, sm);
+  const int D = c.D;
+  double* s_chol = sm + 3 * D + c.like_nparams;
+  if (PHILOX && p.cov_kind == 1) {
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) s_chol[i] = p.chol[i];
+    __syncthreads();
+  }
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= c.T * c.W) return;
+  const int t = tid / c.W;
+  double q[DMAX];
+  load_row<DMAX>(c.coords + (size_t)tid * c.LD, c.LD, q);
+  const bool active = c.inds ? (c.inds[tid] != 0) : true;
+  double u_acc;
+  if (PHILOX) {
+    const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
+    const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
+    double z[DMAX];
+#pragma unroll
+    for (int j = 0; j < DMAX; j += 2) {
+      if (j < D) {
+        const uint4 r = stream(key, TAG_GAUSS, (uint32_t)tid, (uint32_t)(j >> 1));
+        const double rad = sqrt(-2.0 * log(u01_52(r.x, r.y)));
+        double sn, cs;
+        sincos(6.283185307179586 * u01_52(r.z, r.w), &sn, &cs);
+        z[j] = rad * cs;
+        z[j + 1] = rad * sn;
+      } else {
+        z[j] = 0.0; z[j + 1] = 0.0;
+      }
+    }
+    if (active) {
+      if (p.cov_kind == 0) {
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (j < D) q[j] = q[j] + p.scale * z[j];                          // gaussian.py:166-167
+      } else {
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i)
+          if (i < D) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < DMAX; ++j)
+              if (j <= i && j < D) acc += s_chol[i * D + j] * z[j];
+            q[i] = q[i] + acc;                                               // gaussian.py:192-195
+          }
+      }
+    }
+    const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)tid, 0u);
+    u_acc = u01_52(ra.x, ra.y);
+  } else {
+    const double* dl = p.delta + (size_t)tid * c.LD;
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < DMAX; ++j)
+        if (j < D) q[j] = q[j] + dl[j];
+    }
+    u_acc = p.u_acc[tid];
+  }
+  const double ll0 = c.logl[tid], lp0 = c.logp[tid];
+  const bool tempered = c.betas != nullptr;
+  const double beta = tempered ? c.betas[t] : 1.0;
+  double lp, ll;
+  eval_point<DMAX, LIKE>(q, c, sm, active, lp, ll);                          // mh.py:134-148
+  const double logP = log_posterior(ll, lp, beta, tempered);
+  const double prevP = log_posterior(ll0, lp0, beta, tempered);
+  const bool keep = (0.0 + logP - prevP) > log(u_acc);                       // mh.py:168-171
+  if (keep) {
+    store_row<DMAX>(c.coords + (size_t)tid * c.LD, c.LD, q);
+    c.logl[tid] = ll;
+    c.logp[tid] = isinf(lp) ? 0.0 : lp;
+  }
+  p.accepted[tid] = keep ? 1 : 0;
+  if (p.accepted_count && keep) p.accepted_count[tid] += 1u;
+}
+
+template <int DMAX, int LIKE>
+static int launch_gauss(const GaussArgs& a, cudaStream_t s) {
+  const int n = a.c.T * a.c.W;
+  const size_t sb = smem_bytes(a.c, a.c.D * a.c.D);
+  if (a.philox) {
+    int rc = set_smem(gaussian_step_kernel<DMAX, LIKE, true>, sb);
+    if (rc) return rc;
+    gaussian_step_kernel<DMAX, LIKE, true><<<(n + BLOCK - 1) / BLOCK, BLOCK, sb, s>>>(a);
+  } else {
+    int rc = set_smem(gaussian_step_kernel<DMAX, LIKE, false>, sb);
+    if (rc) return rc;
+    gaussian_step_kernel<DMAX, LIKE, false><<<(n + BLOCK - 1) / BLOCK, BLOCK, sb, s>>>(a);
+  }
+  return EB_OK;
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" {
+
+int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* like, const eb_gauss_rng* rng,
+                     uint8_t* accepted, uint32_t* accepted_count, void* stream) {
+  GaussArgs args;
+  int rc = fill_common(args.c, st, prior, like, true);
+  if (rc) return rc;
+  if (!rng) return fail(EB_ERR_INVALID, "rng is NULL");
+  if (!accepted) return fail(EB_ERR_INVALID, "accepted is NULL");
+  args.cov_kind = rng->cov_kind; args.scale = rng->scale; args.chol = rng->chol; args.delta = rng->delta;
+  args.u_acc = rng->u_acc; args.philox = rng->mode == EB_RNG_PHILOX;
+  args.seed_lo = (uint32_t)(rng->seed & 0xFFFFFFFFull); args.seed_hi = (uint32_t)(rng->seed >> 32);
+  args.iter_dev = (const unsigned long long*)rng->iter_dev; args.iter = rng->iter;
+  args.accepted = accepted; args.accepted_count = accepted_count;
+  if (args.philox) {
+    if (rng->cov_kind == 1 && !rng->chol) return fail(EB_ERR_INVALID, "matrix proposal needs the Cholesky factor");
+    if (rng->cov_kind != 0 && rng->cov_kind != 1) return fail(EB_ERR_INVALID, "Invalid proposal scale dimensions");
+  } else if (rng->mode == EB_RNG_REPLAY) {
+    if (!rng->delta || !rng->u_acc) return fail(EB_ERR_INVALID, "replay mode needs delta and u_acc");
+  } else {
+    return fail(EB_ERR_INVALID, "unknown rng mode %d", rng->mode);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+#define L2_(K) rc = launch_gauss<DM_, K>(args, s)
+#define L1_(DM)                              \
+  {                                          \
+    constexpr int DM_ = DM;                  \
+    EB_DISPATCH_LIKE(like->kind, L2_)        \
+  }
+  EB_DISPATCH_DMAX(args.c.LD, L1_)
+#undef L1_
+#undef L2_
+  if (rc) return rc;
+  return check_launch("gaussian_step");
+}
+
+}  // extern "C"

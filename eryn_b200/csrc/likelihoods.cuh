@@ -1,0 +1,169 @@
+// Device-side log-prior and log-likelihood functors.
+//
+// Reference semantics restated here (file:line into /root/reference/src/eryn):
+//   box prior        prior.py:80-88 (in range -> log(1/width), out of range -> -inf, NaN -> 0),
+//                    summed over parameters in index order (prior.py:369-385), inactive leaves
+//                    contribute 0 (ensemble.py:1207), leaves summed (ensemble.py:1210)
+//   likelihood gate  walkers with logp = -inf are not evaluated and get -1e300
+//                    (ensemble.py:1279-1282, :1486); NaN logl -> -1e300 (red_blue.py:279-281)
+//   tempered post.   beta*logl with NaN -> -inf, plus logp (tempering.py:284-349);
+//                    untempered: logl + logp (move.py:443)
+// The functor parameter block is staged in shared memory by the calling kernel.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+namespace eb {
+
+constexpr double FILL_LOGL = -1e300;
+
+__device__ __forceinline__ double neg_inf() { return -__longlong_as_double(0x7ff0000000000000LL); }
+
+// ---- 256/128-bit row access (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a) -----------------------
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+template <int DMAX>
+__device__ __forceinline__ void load_row(const double* __restrict__ row, int LD, double (&x)[DMAX]) {
+  if ((LD & 3) == 0) {
+#pragma unroll
+    for (int j = 0; j < DMAX; j += 4)
+      if (j < LD) ld256(row + j, x[j], x[j + 1], x[j + 2], x[j + 3]);
+  } else if ((LD & 1) == 0) {
+#pragma unroll
+    for (int j = 0; j < DMAX; j += 2)
+      if (j < LD) {
+        double2 v = *reinterpret_cast<const double2*>(row + j);
+        x[j] = v.x; x[j + 1] = v.y;
+      }
+  } else {
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if (j < LD) x[j] = row[j];
+  }
+}
+
+template <int DMAX>
+__device__ __forceinline__ void store_row(double* __restrict__ row, int LD, const double (&x)[DMAX]) {
+  if ((LD & 3) == 0) {
+#pragma unroll
+    for (int j = 0; j < DMAX; j += 4)
+      if (j < LD) st256(row + j, x[j], x[j + 1], x[j + 2], x[j + 3]);
+  } else if ((LD & 1) == 0) {
+#pragma unroll
+    for (int j = 0; j < DMAX; j += 2)
+      if (j < LD) *reinterpret_cast<double2*>(row + j) = make_double2(x[j], x[j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if (j < LD) row[j] = x[j];
+  }
+}
+
+// ---- box prior of one leaf --------------------------------------------------------------------
+template <int DMAX>
+__device__ __forceinline__ double box_logpdf_leaf(const double (&x)[DMAX], int off, int D,
+                                                  const double* __restrict__ lo,
+                                                  const double* __restrict__ hi,
+                                                  const double* __restrict__ lpdf) {
+  double out = 0.0;
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j) {
+    const int d = j - off;
+    if (d >= 0 && d < D) {
+      const double v = x[j];
+      double t = 0.0;
+      if (v >= lo[d] && v <= hi[d]) t = lpdf[d];
+      if (v < lo[d] || v > hi[d]) t = neg_inf();
+      out += t;
+    }
+  }
+  return out;
+}
+
+// ---- likelihood functors (single leaf, D = ndim) ----------------------------------------------
+template <int KIND>
+struct Like;
+
+template <>
+struct Like<0> {  // EB_LIKE_GAUSSIAN: params mu[D], P[D*D]
+  template <int DMAX>
+  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D, const double* __restrict__ sp, int) {
+    const double* mu = sp;
+    const double* P = sp + D;
+    double d[DMAX];
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i) d[i] = (i < D) ? x[i] - mu[i] : 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i) {
+      if (i < D) {
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (j < D) r += P[i * D + j] * d[j];
+        acc += d[i] * r;
+      }
+    }
+    return -0.5 * acc;
+  }
+};
+
+template <>
+struct Like<1> {  // EB_LIKE_ROSENBROCK
+  template <int DMAX>
+  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D, const double* __restrict__, int) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < DMAX - 1; ++i) {
+      if (i < D - 1) {
+        const double a = x[i + 1] - x[i] * x[i];
+        const double b = 1.0 - x[i];
+        acc += 100.0 * (a * a) + b * b;
+      }
+    }
+    return -acc;
+  }
+};
+
+template <>
+struct Like<2> {  // EB_LIKE_GMIX: params logc[K], hinv[K], mu[K*D]
+  template <int DMAX>
+  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D, const double* __restrict__ sp, int K) {
+    const double* logc = sp;
+    const double* hinv = sp + K;
+    const double* mu = sp + 2 * K;
+    double m = neg_inf(), s = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double r2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < DMAX; ++j)
+        if (j < D) {
+          const double dd = x[j] - mu[k * D + j];
+          r2 += dd * dd;
+        }
+      const double e = logc[k] - r2 * hinv[k];
+      if (e > m) {  // online log-sum-exp
+        s = s * exp(m - e) + 1.0;
+        m = e;
+      } else {
+        s += exp(e - m);
+      }
+    }
+    return m + log(s);
+  }
+};
+
+// tempered log posterior (tempering.py:284-349); beta_valid=false -> move.py:443
+__device__ __forceinline__ double log_posterior(double logl, double logp, double beta, bool tempered) {
+  if (!tempered) return logl + logp;
+  double lt = logl * beta;
+  if (lt != lt) lt = neg_inf();
+  return lt + logp;
+}
+
+}  // namespace eb

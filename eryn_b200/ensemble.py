@@ -1,0 +1,312 @@
+"""EnsembleSampler: the reference's driver surface (ensemble.py) over the device hot path.
+
+The host keeps what the reference keeps on the host — move schedule, State bookkeeping, the chain
+store — and the walkers live on the GPU between yields: `thin_by` iterations run back to back with
+no host synchronisation, and a host `State` is materialised only at yield/store points
+(ensemble.py:1013, :1045)."""
+import warnings
+from collections.abc import Iterable
+
+import numpy as np
+import torch
+
+from .backend import Backend
+from .device import DeviceContext, DeviceState
+from .model import Model
+from .moves import StretchMove, TemperatureControl
+from .prior import ProbDistContainer
+from .state import State
+
+__all__ = ["EnsembleSampler", "walkers_independent"]
+
+
+def walkers_independent(coords_in):
+    """ensemble.py:1670-1700 (emcee's linear-independence check)."""
+    assert coords_in.ndim == 4
+    ntemps, nwalkers, nleaves_max, ndim = coords_in.shape
+    coords = coords_in.reshape(ntemps * nwalkers, nleaves_max * ndim)
+    if not np.all(np.isfinite(coords)):
+        return False
+    C = coords - np.mean(coords, axis=0)[None, :]
+    C_colmax = np.amax(np.abs(C), axis=0)
+    if np.any(C_colmax == 0):
+        return False
+    C /= C_colmax
+    C /= np.sqrt(np.sum(C ** 2, axis=0))
+    return np.linalg.cond(C.astype(float)) <= 1e8
+
+
+class EnsembleSampler(object):
+    """Same call surface as eryn.ensemble.EnsembleSampler for the hot path (single branch, in-model moves
+    StretchMove / GaussianMove, parallel tempering).  Extra keyword arguments:
+
+      rng     "philox" (default; randoms generated in-kernel) or "numpy-replay" (host NumPy draws in the
+              reference's order -> chains identical to the reference under the same np.random.seed)
+      seed    Philox seed (default: taken from the NumPy global state at construction)
+      device  CUDA device (default: current)
+
+    `log_like_fn` is a device functor from eryn_b200.likelihood (fused kernels) or a callable on CUDA tensors
+    (split path).  There is no CPU fallback."""
+
+    def __init__(self, nwalkers, ndims, log_like_fn, priors, provide_groups=False, provide_supplemental=False,
+                 tempering_kwargs={}, branch_names=None, nbranches=1, nleaves_max=1, nleaves_min=0, pool=None,
+                 moves=None, rj_moves=None, args=None, kwargs=None, backend=None, vectorize=True, periodic=None,
+                 update_fn=None, update_iterations=-1, stopping_fn=None, stopping_iterations=-1,
+                 fill_zero_leaves_val=-1e300, num_repeats_in_model=1, track_moves=True, info={},
+                 rng="philox", seed=None, device=None):
+        for name, val in (("provide_groups", provide_groups), ("provide_supplemental", provide_supplemental),
+                          ("pool", pool), ("rj_moves", rj_moves), ("periodic", periodic), ("args", args),
+                          ("kwargs", kwargs)):
+            if val:
+                raise NotImplementedError(f"{name} is outside the device hot path built so far (DESIGN.md §7)")
+        if fill_zero_leaves_val != -1e300:
+            raise NotImplementedError("fill_zero_leaves_val is fixed at -1e300 on the device path")
+        if isinstance(ndims, dict):
+            branch_names = list(ndims.keys()) if branch_names is None else branch_names
+        if branch_names is None:
+            branch_names = ["model_0"]
+        if len(branch_names) != 1 or nbranches != 1:
+            raise NotImplementedError("the device hot path covers one branch per sampler in this build")
+        self.branch_names = list(branch_names)
+        name = self.branch_names[0]
+        self.ndims = ndims if isinstance(ndims, dict) else {name: int(ndims)}
+        self.nleaves_max = nleaves_max if isinstance(nleaves_max, dict) else {name: int(nleaves_max)}
+        self.nbranches = 1
+        self.has_reversible_jump = False
+        if isinstance(priors, dict) and name not in priors:
+            priors = {name: ProbDistContainer(priors)}
+        elif isinstance(priors, ProbDistContainer):
+            priors = {name: priors}
+        self.priors = priors
+        self.key_order = {name: priors[name].key_order}
+        self.nwalkers = int(nwalkers)
+        self.num_repeats_in_model = int(num_repeats_in_model)
+        self.track_moves = track_moves
+        self.update_fn, self.update_iterations = update_fn, update_iterations
+        self.stopping_fn, self.stopping_iterations = stopping_fn, stopping_iterations
+
+        # tempering (ensemble.py:321-334)
+        if tempering_kwargs == {}:
+            self.ntemps = 1
+            self.temperature_control = None
+        else:
+            total_ndim = self.nleaves_max[name] * self.ndims[name]
+            self.temperature_control = TemperatureControl(total_ndim, nwalkers, **tempering_kwargs)
+            self.ntemps = self.temperature_control.ntemps
+
+        # move schedule (ensemble.py:349-378)
+        if moves is None:
+            self.moves = [StretchMove(temperature_control=self.temperature_control, a=2.0)]
+            self.weights = [1.0]
+        elif isinstance(moves, Iterable):
+            try:
+                self.moves, self.weights = [list(tmp) for tmp in zip(*moves)]
+            except TypeError:
+                self.moves = moves
+                self.weights = np.ones(len(moves))
+        else:
+            self.moves = [moves]
+            self.weights = [1.0]
+        self.weights = np.atleast_1d(self.weights).astype(float)
+        self.weights /= np.sum(self.weights)
+
+        # random streams (ensemble.py:604, :651-652): the private stream is a copy of the global state
+        state = np.random.get_state()
+        self._random = np.random.mtrand.RandomState()
+        self._random.set_state(state)
+        if seed is None:
+            seed = int(state[1][0]) | (int(state[1][1]) << 32)
+
+        self.ctx = DeviceContext(priors[name], log_like_fn, device=device, rng=rng, seed=seed, branch_name=name)
+        self.log_like_fn = self.ctx.like
+        if self.temperature_control is not None:
+            self.temperature_control.bind(self.ctx)
+        for move in self.moves:
+            if self.temperature_control is not None and move.temperature_control is None:
+                move.temperature_control = self.temperature_control  # ensemble.py:516-525
+            move.bind(self.ctx)
+            move.accepted = np.zeros((self.ntemps, self.nwalkers))  # ensemble.py:539-540
+
+        self.backend = Backend() if backend is None else backend
+        self.all_moves = {}
+        if self.track_moves:
+            counts = {}
+            for move in self.moves:
+                mn = move.__class__.__name__
+                counts[mn] = counts.get(mn, -1) + 1
+                self.all_moves[f"{mn}_{counts[mn]}"] = move  # ensemble.py:563-583
+            self.move_keys = list(self.all_moves.keys())
+        else:
+            self.move_keys = None
+        self._previous_state = None
+        if not self.backend.initialized:
+            self.backend.reset(self.nwalkers, self.ndims, nleaves_max=self.nleaves_max, ntemps=self.ntemps,
+                               branch_names=self.branch_names, rj=False, moves=self.move_keys,
+                               key_order=self.key_order, **info)
+        self._dstate = None
+
+    # ---- small mirrors ---------------------------------------------------------------------------------
+    @property
+    def random_state(self):
+        return self._random.get_state()
+
+    @property
+    def iteration(self):
+        return self.backend.iteration
+
+    @property
+    def acceptance_fraction(self):
+        return self.backend.accepted / float(self.backend.iteration)
+
+    def get_chain(self, **kwargs):
+        return self.backend.get_chain(**kwargs)
+
+    def get_log_like(self, **kwargs):
+        return self.backend.get_log_like(**kwargs)
+
+    def get_log_prior(self, **kwargs):
+        return self.backend.get_log_prior(**kwargs)
+
+    def get_betas(self, **kwargs):
+        return self.backend.get_betas(**kwargs)
+
+    def get_last_sample(self):
+        return self.backend.get_last_sample()
+
+    def get_model(self):
+        """ensemble.py:780-806"""
+        return Model(self.log_like_fn, self.compute_log_like, self.compute_log_prior, self.temperature_control, map,
+                     self._random)
+
+    def compute_log_prior(self, coords, inds=None, supps=None, branch_supps=None):
+        """ensemble.py:1127 — evaluated on the device; returns an ndarray [ntemps, nwalkers]."""
+        name = self.branch_names[0]
+        c = coords[name] if isinstance(coords, dict) else coords
+        T, W, L, D = c.shape
+        q = self.ctx.to_dev(c, np.float64).view(T * W, L, D)
+        ii = None
+        if inds is not None:
+            ii = self.ctx.to_dev((inds[name] if isinstance(inds, dict) else inds).astype(np.uint8)).view(T * W, L)
+        out = self.ctx.box_log_prior(q, ii).cpu().numpy().reshape(T, W)
+        if np.any(np.isnan(out)):
+            raise ValueError("The prior function is returning Nan.")
+        return out
+
+    def compute_log_like(self, coords, inds=None, logp=None, supps=None, branch_supps=None):
+        """ensemble.py:1219 — evaluated on the device; returns (ndarray [ntemps, nwalkers], None)."""
+        name = self.branch_names[0]
+        c = coords[name] if isinstance(coords, dict) else coords
+        if np.any(np.isinf(c)):
+            raise ValueError("At least one parameter value was infinite")
+        if np.any(np.isnan(c)):
+            raise ValueError("At least one parameter value was NaN")
+        st = State({name: c}, inds=None if inds is None else {name: (inds[name] if isinstance(inds, dict) else inds)})
+        d = self.ctx.upload(st)
+        self.ctx.eval_state(d)
+        ll = d.logl.cpu().numpy()
+        if np.any(np.isnan(ll)):
+            raise ValueError("The likelihood function is returning Nan.")
+        return ll, None
+
+    # ---- the loop -------------------------------------------------------------------------------------
+    def sample(self, initial_state, iterations=1, tune=False, skip_initial_state_check=True, thin_by=1, store=True,
+               progress=False):
+        """Advance the chain as a generator (ensemble.py:808-1045)."""
+        if iterations is None and store:
+            raise ValueError("'store' must be False when 'iterations' is None")
+        state = State(initial_state, copy=True)
+        name = self.branch_names[0]
+        for nm, branch in state.branches.items():
+            if tuple(branch.shape) != (self.ntemps, self.nwalkers, self.nleaves_max[nm], self.ndims[nm]):
+                raise ValueError("incompatible input dimensions")
+        if (not skip_initial_state_check) and (not walkers_independent(state.branches[name].coords)):
+            raise ValueError("Initial state has a large condition number. Make sure that your walkers are "
+                             "linearly independent for the best performance")
+        tc = self.temperature_control
+        if tc is not None:
+            if state.betas is not None:
+                if state.betas.shape[0] != self.ntemps:
+                    raise ValueError("Input state has inverse temperatures (betas), but not the correct number of "
+                                     "temperatures according to sampler inputs.")
+                tc.betas = state.betas.copy()  # ensemble.py:915-921
+            else:
+                state.betas = tc.betas.copy()
+        need_eval = state.log_prior is None or state.log_like is None
+        d = self.ctx.upload(state, betas=None if tc is None else tc.betas_dev)
+        if need_eval:
+            keep_lp = None if state.log_prior is None else d.logp.clone()
+            self.ctx.eval_state(d)  # ensemble.py:898-912
+            if keep_lp is not None:
+                d.logp.copy_(keep_lp)
+        logl0, logp0 = d.logl.cpu().numpy(), d.logp.cpu().numpy()
+        if np.shape(logl0) != (self.ntemps, self.nwalkers) or np.shape(logp0) != (self.ntemps, self.nwalkers):
+            raise ValueError("incompatible input dimensions")
+        if np.any(np.isnan(logl0)):
+            raise ValueError("The initial log_like was NaN")
+        if np.any(np.isinf(logl0)):
+            raise ValueError("The initial log_like was +/- infinite")
+        if np.any(np.isnan(logp0)):
+            raise ValueError("The initial log_prior was NaN")
+        if np.any(np.isinf(logp0)):
+            raise ValueError("The initial log_prior was +/- infinite")
+        thin_by = int(thin_by)
+        if thin_by <= 0:
+            raise ValueError("Invalid thinning argument")
+        if store:
+            self.backend.grow(iterations, None)
+        model = self.get_model()
+        self._dstate = d
+        acc_total = torch.zeros((self.ntemps, self.nwalkers), dtype=torch.int32, device=self.ctx.device)
+        i = 0
+        it_range = iter(int, 1) if iterations is None else range(iterations)
+        for _ in it_range:
+            for _ in range(thin_by):
+                acc_total.zero_()  # ensemble.py:968: `accepted` restarts every inner iteration
+                for repeat in range(self.num_repeats_in_model):
+                    mi = self._random.choice(len(self.moves), p=self.weights)  # ensemble.py:971 (1 uniform)
+                    move = self.moves[mi]
+                    d, acc = move.propose(model, d)  # device resident: no host sync
+                    acc_total += acc
+                    if tune:
+                        move.tune(d, acc)
+                i += 1
+            # ---- yield point: materialise a host State (ensemble.py:1013-1045)
+            host = self.ctx.download(d, random_state=self.random_state)
+            if store:
+                maf = {k: m.acceptance_fraction for k, m in self.all_moves.items()} if self.track_moves else None
+                swaps = tc.swaps_accepted if (tc is not None and self.ntemps > 1) else None
+                self.backend.save_step(host, acc_total.cpu().numpy(), swaps_accepted=swaps,
+                                       moves_accepted_fraction=maf)
+            if self.update_iterations > 0 and self.update_fn is not None and i % self.update_iterations == 0:
+                self.update_fn(i, host, self)
+            yield host
+            if host.betas is not None and tc is not None and not np.array_equal(host.betas, tc.betas):
+                tc.betas = host.betas  # a caller may edit the yielded state's ladder
+
+    def run_mcmc(self, initial_state, nsteps, burn=None, post_burn_update=False, **kwargs):
+        """ensemble.py:1047-1125"""
+        if initial_state is None:
+            if self._previous_state is None:
+                raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")
+            initial_state = self._previous_state
+        if burn is not None and burn != 0:
+            bk = dict(kwargs)
+            bk["store"] = False
+            bk["thin_by"] = 1
+            i = 0
+            for results in self.sample(initial_state, iterations=burn, **bk):
+                i += 1
+            if post_burn_update and self.update_fn is not None:
+                self.update_fn(i, results, self)
+            initial_state = results
+        if nsteps == 0:
+            return initial_state
+        results = None
+        i = 0
+        for results in self.sample(initial_state, iterations=nsteps, **kwargs):
+            if self.stopping_iterations > 0 and self.stopping_fn is not None and (i + 1) % self.stopping_iterations == 0:
+                if self.stopping_fn(i, results, self):
+                    break
+            i += 1
+        self._previous_state = results
+        return results

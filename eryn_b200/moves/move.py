@@ -1,0 +1,98 @@
+"""Move base class: the attributes EnsembleSampler touches on a move (move.py:404-470)."""
+import numpy as np
+
+from ..device import DeviceContext, DeviceState
+
+__all__ = ["Move"]
+
+
+class Move(object):
+    def __init__(self, temperature_control=None, periodic=None, ctx=None, **kwargs):
+        if periodic is not None:
+            raise NotImplementedError("periodic parameters are a 'next' row (SURVEY.md §8f) of the device path")
+        if kwargs:
+            raise NotImplementedError(f"unsupported Move kwargs on the device path: {sorted(kwargs)}")
+        self.periodic = None
+        self._accepted = None
+        self._accepted_dev = None
+        self.num_proposals = 0
+        self.temperature_control = temperature_control
+        self.ctx = ctx
+
+    # ---- accepted counters (move.py:404-421); the device accumulator is merged lazily --------------
+    @property
+    def accepted(self):
+        if self._accepted is None:
+            raise ValueError("accepted must be inititalized with the init_accepted function if you want to use it.")
+        if self._accepted_dev is not None:
+            return self._accepted + self._accepted_dev.cpu().numpy().astype(np.float64)
+        return self._accepted
+
+    @accepted.setter
+    def accepted(self, accepted):
+        assert isinstance(accepted, np.ndarray)
+        self._accepted = accepted
+        if self._accepted_dev is not None:
+            self._accepted_dev.zero_()
+
+    @property
+    def acceptance_fraction(self):
+        return self.accepted / self.num_proposals
+
+    @property
+    def temperature_control(self):
+        return self._temperature_control
+
+    @temperature_control.setter
+    def temperature_control(self, temperature_control):
+        self._temperature_control = temperature_control
+        if temperature_control is not None:
+            self.ntemps = temperature_control.ntemps
+
+    def tune(self, state, accepted):
+        pass
+
+    # ---- helpers ----------------------------------------------------------------------------------
+    def bind(self, ctx):
+        self.ctx = ctx
+        if self.temperature_control is not None and self.temperature_control.ctx is None:
+            self.temperature_control.bind(ctx)
+
+    def _context(self):
+        if not isinstance(self.ctx, DeviceContext):
+            raise RuntimeError("move is not bound to a DeviceContext (EnsembleSampler does this; standalone use: "
+                               "pass ctx=DeviceContext(priors, log_like_fn))")
+        return self.ctx
+
+    def _count_buffer(self, ctx, T, W):
+        import torch
+        if self._accepted_dev is None or tuple(self._accepted_dev.shape) != (T, W):
+            self._accepted_dev = torch.zeros((T, W), dtype=torch.int32, device=ctx.device)
+        if self._accepted is None:
+            self._accepted = np.zeros((T, W))
+        return self._accepted_dev
+
+    def _enter(self, state):
+        """host State -> DeviceState (drop-in use with NumPy states); DeviceState passes through."""
+        ctx = self._context()
+        if isinstance(state, DeviceState):
+            return ctx, state, None
+        tc = self.temperature_control
+        betas = None
+        if tc is not None:
+            if state.betas is not None:
+                tc.betas = state.betas
+            betas = tc.betas_dev
+        return ctx, ctx.upload(state, betas=betas), state
+
+    def _exit(self, ctx, d, host_state, acc):
+        tc = self.temperature_control
+        if tc is not None:
+            d = tc.temper_comps(d)
+        else:
+            ctx.advance_iter()
+        if host_state is None:
+            return d, acc
+        accepted = acc.cpu().numpy().astype(bool)
+        state = ctx.download(d, into=host_state)
+        return state, accepted

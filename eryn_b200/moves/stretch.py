@@ -1,0 +1,53 @@
+"""StretchMove on the device (reference: moves/red_blue.py:89-333 + moves/stretch.py)."""
+import numpy as np
+
+from .move import Move
+
+__all__ = ["StretchMove"]
+
+
+class StretchMove(Move):
+    """Affine-invariant stretch move, red/blue parallelisation (Goodman & Weare 2010).
+
+    Same constructor surface as eryn.moves.StretchMove for what the device path covers:
+    a, nsplits (must be 2), randomize_split, live_dangerously, temperature_control."""
+
+    def __init__(self, a=2.0, nsplits=2, randomize_split=True, live_dangerously=False, **kwargs):
+        if int(nsplits) != 2:
+            raise NotImplementedError("the device stretch kernel implements nsplits == 2 (the reference default)")
+        self.a = a
+        self.nsplits = 2
+        self.randomize_split = randomize_split
+        self.live_dangerously = live_dangerously
+        super().__init__(**kwargs)
+
+    def propose(self, model, state):
+        """(state, accepted) — ensemble.py:974.  `state` may be a host State or a DeviceState."""
+        ctx, d, host_state = self._enter(state)
+        T, W, L, D = d.shape
+        if W < 2 * L * D and not self.live_dangerously:  # red_blue.py:103-114
+            raise RuntimeError(
+                "It is unadvisable to use a red-blue move with fewer walkers than twice the number of "
+                "dimensions. If you would like to do this, please set live_dangerously to True.")
+        cnt = self._count_buffer(ctx, T, W)
+        step = ctx.stretch_half_step if ctx.fused else ctx.stretch_half_step_split
+        if ctx.rng == "numpy-replay":
+            # same draws, same order as the reference: global shuffle (red_blue.py:124), then per split
+            # private randint / rand / rand (stretch.py:93, :131, red_blue.py:294)
+            ids = np.tile(np.arange(W), (T, 1))
+            labels = ids % self.nsplits
+            if self.randomize_split:
+                [np.random.shuffle(x) for x in labels]
+            lists = [ids[labels == s].reshape(T, -1) for s in range(2)]
+            for split in range(2):
+                sub, comp = lists[split], lists[1 - split]
+                Ns, Nc = sub.shape[1], comp.shape[1]
+                rint = model.random.randint(Nc, size=(T, Ns))
+                u_z = model.random.rand(T, Ns)
+                u_acc = model.random.rand(T, Ns)
+                acc = step(d, split, self.a, replay=(sub, comp, rint, u_z, u_acc), accepted_count=cnt)
+        else:
+            for split in range(2):
+                acc = step(d, split, self.a, randomize_split=self.randomize_split, accepted_count=cnt)
+        self.num_proposals += 1
+        return self._exit(ctx, d, host_state, acc)

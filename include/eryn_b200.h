@@ -1,0 +1,220 @@
+/* eryn_b200 — C ABI of the B200-native walker-parallel sampling hot path of Eryn.
+ *
+ * The reference (mikekatz04/Eryn, /root/reference/src/eryn) is pure Python/NumPy: there is no
+ * FFI today.  The boundary this library replaces is Eryn's Move protocol
+ * (`Move.propose(model, state)`, ensemble.py:974) and `TemperatureControl.temper_comps`
+ * (tempering.py:598).  Each entry point below names the reference routine it stands in for.
+ * INTEGRATION.md shows the ctypes binding a maintainer of Eryn would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `double*`/`uint8_t*`/`int32_t*` inside the structs
+ *     is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream); nothing here
+ *     synchronises except the `*_host` entry points;
+ *   - all floating data is IEEE float64, C-contiguous, laid out exactly like the reference's
+ *     arrays: coords[ntemps][nwalkers][nleaves][ndim], logl/logp[ntemps][nwalkers],
+ *     inds[ntemps][nwalkers][nleaves] (uint8, 0/1), betas[ntemps];
+ *   - return value 0 = EB_OK, otherwise an `eb_status`; `eb_last_error()` gives the text.
+ */
+#ifndef ERYN_B200_H
+#define ERYN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EB_API __attribute__((visibility("default")))
+#else
+#define EB_API
+#endif
+
+#define EB_ABI_VERSION 1
+#define EB_MAX_TEMPS 256
+#define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
+
+typedef enum {
+  EB_OK = 0,
+  EB_ERR_INVALID = 1,     /* bad argument (ValueError in the reference) */
+  EB_ERR_UNSUPPORTED = 2, /* shape / option outside what the fused kernels cover */
+  EB_ERR_CUDA = 3,        /* a CUDA runtime call failed */
+  EB_ERR_NODEVICE = 4     /* no CUDA device: there is NO CPU fallback */
+} eb_status;
+
+typedef enum { EB_RNG_REPLAY = 0, EB_RNG_PHILOX = 1 } eb_rng_mode;
+
+/* device-side log-likelihood functors (SURVEY.md §8d synthetic targets) */
+typedef enum {
+  EB_LIKE_GAUSSIAN = 0,   /* params: mu[D], P[D*D]           logL = -1/2 (x-mu)^T P (x-mu)          */
+  EB_LIKE_ROSENBROCK = 1, /* params: none                    logL = -sum 100(x_{i+1}-x_i^2)^2+(1-x_i)^2 */
+  EB_LIKE_GMIX = 2        /* params: logc[K], hinv[K], mu[K*D]  logL = logsumexp_k(logc_k - hinv_k |x-mu_k|^2) */
+} eb_like_kind;
+
+/* Walker state of one branch — state.py:387 (State) / :330 (Branch). */
+typedef struct {
+  int32_t ntemps, nwalkers, nleaves, ndim;
+  double* coords;      /* [T][W][L][D] */
+  double* logl;        /* [T][W]  State.log_like  */
+  double* logp;        /* [T][W]  State.log_prior */
+  uint8_t* inds;       /* [T][W][L] or NULL = all leaves active (moved by the swap pass) */
+  double* betas;       /* [T] or NULL = no TemperatureControl (move.py:443 basic posterior) */
+} eb_state;
+
+/* Independent uniform priors — prior.py:12-91 + ProbDistContainer.logpdf prior.py:337-392. */
+typedef struct {
+  const double* lo;     /* [D] */
+  const double* hi;     /* [D] */
+  const double* logpdf; /* [D] log(1/(hi-lo)) as the host computed it (prior.py:40-41) */
+} eb_prior;
+
+typedef struct {
+  int32_t kind;         /* eb_like_kind */
+  int32_t ncomp;        /* K for EB_LIKE_GMIX, else 0 */
+  int32_t nparams;      /* doubles in params */
+  int32_t _pad;
+  const double* params; /* device */
+} eb_like;
+
+/* Random inputs of one stretch half step.
+ * replay: host NumPy draws in reference order (stretch.py:93, :131, red_blue.py:294) and the
+ *         ascending walker-id lists of the split (red_blue.py:150-154).
+ * philox: everything is generated in-kernel from (seed, *iter_dev, tags). */
+typedef struct {
+  int32_t mode; /* eb_rng_mode */
+  int32_t randomize_split; /* red_blue.py:123 (philox mode; replay encodes it in sub_idx) */
+  const int32_t* sub_idx;  /* replay [T][Ns] walkers that move */
+  const int32_t* comp_idx; /* replay [T][Nc] complement walkers */
+  const int64_t* rint;     /* replay [T][Ns] */
+  const double* u_z;       /* replay [T][Ns] */
+  const double* u_acc;     /* replay [T][Ns] */
+  uint64_t seed;           /* philox */
+  const uint64_t* iter_dev; /* philox: device iteration counter (eb_ctrl.iter) or NULL */
+  uint64_t iter;           /* philox: used when iter_dev == NULL */
+} eb_stretch_rng;
+
+/* Random inputs of one Gaussian Metropolis step (gaussian.py:68-195, mh.py:171). */
+typedef struct {
+  int32_t mode;
+  int32_t cov_kind;       /* 0 scalar (gaussian.py:166), 1 full matrix via Cholesky factor (gaussian.py:192) */
+  double scale;           /* sqrt(cov) for cov_kind 0 */
+  const double* chol;     /* [D][D] lower Cholesky factor for cov_kind 1 (philox mode) */
+  const double* delta;    /* replay [T][W][L][D] proposal increment drawn on the host */
+  const double* u_acc;    /* replay [T][W] */
+  uint64_t seed;
+  const uint64_t* iter_dev;
+  uint64_t iter;
+} eb_gauss_rng;
+
+/* Random inputs of one swap pass (tempering.py:525-535). */
+typedef struct {
+  int32_t mode;
+  int32_t permute;        /* tempering.py:525 */
+  const int32_t* iperm;   /* replay [T][W], row i = permutation used at rung i (row 0 unused) */
+  const int32_t* i1perm;  /* replay [T][W] */
+  const double* u;        /* replay [T][W] uniforms (log taken on device, :535) */
+  int32_t* next_pos;      /* replay scratch [T][W] int32 */
+  double* u_at;           /* replay scratch [T][W] */
+  uint64_t seed;
+  const uint64_t* iter_dev;
+  uint64_t iter;
+} eb_swap_rng;
+
+/* Device control block: iteration counter, ladder-adaptation clock and swap statistics
+ * (TemperatureControl.time / .swaps_accepted, tempering.py:280,500,596). */
+typedef struct {
+  uint64_t iter;                        /* incremented by eb_pt_swap (or eb_advance_iter) */
+  int64_t time;                         /* TemperatureControl.time */
+  uint32_t ticket;                      /* last-block election */
+  uint32_t _pad;
+  int32_t swaps_work[EB_MAX_TEMPS];     /* scratch, zero between passes */
+  int32_t swaps_accepted[EB_MAX_TEMPS]; /* result of the last pass, entry i-1 = rung i */
+  uint64_t swaps_total[EB_MAX_TEMPS];   /* running sum */
+} eb_ctrl;
+
+typedef struct {
+  int32_t adaptive;         /* tempering.py:632 */
+  int32_t stop_adaptation;  /* tempering.py:590 */
+  double adaptation_lag;    /* tempering.py:571 */
+  double adaptation_time;   /* tempering.py:572 */
+} eb_adapt;
+
+/* ---- library ---------------------------------------------------------------------- */
+EB_API int eb_abi_version(void);
+EB_API const char* eb_last_error(void);
+EB_API int eb_device_count(void);
+EB_API size_t eb_ctrl_size(void);
+/* sizeof() of the ABI structs, for binding self-checks: 0 eb_state, 1 eb_prior, 2 eb_like,
+ * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job */
+EB_API size_t eb_struct_size(int which);
+
+/* ---- probability evaluation:  EnsembleSampler.compute_log_prior (ensemble.py:1127) and
+ *      compute_log_like (ensemble.py:1219) on the whole state; fills st->logp, st->logl.
+ *      Walkers with logp = -inf are not evaluated and get -1e300 (ensemble.py:1279-1282,1486). */
+EB_API int eb_eval_state(const eb_state* st, const eb_prior* prior, const eb_like* like, void* stream);
+
+/* ---- StretchMove: one red/blue half step = red_blue.py:148-323 + stretch.py:74-231 +
+ *      Move.update (move.py:472-703), fused.  `split` is 0 or 1.  `accepted` [T][W] uint8 gets
+ *      the flags of the walkers that moved this half step; `accepted_count` (nullable,
+ *      [T][W] uint32) is incremented (Move.accepted, move.py:404). */
+EB_API int eb_stretch_half_step(const eb_state* st, const eb_prior* prior, const eb_like* like, double a,
+                         int32_t split, const eb_stretch_rng* rng, uint8_t* accepted,
+                         uint32_t* accepted_count, void* stream);
+
+/* ---- GaussianMove: one Metropolis step over all walkers = mh.py:56-193 + gaussian.py:68-195. */
+EB_API int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* like,
+                     const eb_gauss_rng* rng, uint8_t* accepted, uint32_t* accepted_count,
+                     void* stream);
+
+/* ---- TemperatureControl.temper_comps (tempering.py:598-649): swap ladder
+ *      (temperature_swaps :484-561, do_swaps_indexing :351-482) + adapt_temps (:585-596).
+ *      Resolved chain-parallel; results identical to the sequential ladder.
+ *      Increments ctrl->iter.  `adapt` may be NULL (no adaptation, rj.py:381-382). */
+EB_API int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl,
+               void* stream);
+
+/* iteration counter tick for untempered runs (no swap pass) */
+EB_API int eb_advance_iter(eb_ctrl* ctrl, void* stream);
+
+/* ---- split path for likelihoods that are not device functors (user callables on device
+ *      tensors): proposal only (stretch.py:160-231) and accept+update only
+ *      (red_blue.py:283-323, move.py:472).  q [T][Ns][L][D], factors [T][Ns],
+ *      sub_out [T][Ns] int32 = walker ids the rows of q belong to. */
+EB_API int eb_stretch_propose(const eb_state* st, double a, int32_t split, const eb_stretch_rng* rng,
+                       double* q, double* factors, int32_t* sub_out, void* stream);
+EB_API int eb_accept_update(const eb_state* st, const int32_t* sub, int32_t nsub, const double* q,
+                     const double* factors, const double* logl_new, const double* logp_new,
+                     const double* u_acc, int32_t slot, const eb_stretch_rng* rng,
+                     uint8_t* accepted, uint32_t* accepted_count, void* stream);
+/* box prior of proposed points q [T][Ns][L][D] -> logp_out [T][Ns] (ensemble.py:1192-1212) */
+EB_API int eb_box_log_prior(const double* q, const uint8_t* inds_sub, int32_t nrows, int32_t nleaves,
+                     int32_t ndim, const eb_prior* prior, double* logp_out, void* stream);
+
+/* ---- reference-facing entry with HOST buffers: uploads the state, runs `niter` full
+ *      iterations (move + swap pass) in philox mode, downloads the state.  This is the call
+ *      bench.py's `e2e` leg times.  move_schedule_host[niter]: 0 = stretch, 1 = gaussian
+ *      (the reference's per-iteration `random.choice(moves)`, ensemble.py:971); NULL = stretch. */
+typedef struct {
+  int32_t ntemps, nwalkers, nleaves, ndim;
+  double* coords_host; double* logl_host; double* logp_host; double* betas_host; /* betas NULL = untempered */
+  const double* prior_lo_host; const double* prior_hi_host;
+  int32_t like_kind, like_ncomp, like_nparams, _pad;
+  const double* like_params_host;
+  double stretch_a;
+  double gauss_scale;
+  uint64_t seed, iter0;
+  eb_adapt adapt;
+  int64_t adapt_time0;
+  int32_t permute, randomize_split;
+  const uint8_t* move_schedule_host;
+  int32_t* swaps_accepted_host;   /* [T-1] of the last iteration, nullable */
+  uint32_t* accepted_count_host;  /* [T][W] accumulated over niter, nullable */
+} eb_host_job;
+EB_API int eb_run_host(eb_host_job* job, int32_t niter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERYN_B200_H */

@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference interface (no GPU needed)."""
+import numpy as np
+import pytest
+
+from oracle import eryn_oracle as orc
+from oracle import philox_np as px
+from tests import cases
+
+
+def test_make_ladder_matches_oracle_and_reference_values():
+    from eryn_b200.moves import make_ladder
+    for nd, nt in [(3, 4), (8, 16), (20, 32), (150, 5)]:
+        np.testing.assert_array_equal(make_ladder(nd, ntemps=nt), orc.make_ladder_default(nd, nt))
+    # golden: the reference's ladder after 0 adaptations is betas[0] of the first iteration's parent
+    b = make_ladder(3, ntemps=4, Tmax=np.inf)
+    assert b[-1] == 0 and len(b) == 4
+    with pytest.raises(ValueError):
+        make_ladder(0, ntemps=3)
+    with pytest.raises(ValueError):
+        make_ladder(3)
+    with pytest.raises(ValueError):
+        make_ladder(3, ntemps=3, Tmax=0.5)
+
+
+def test_prior_rvs_consumes_global_stream_like_reference():
+    from eryn_b200.prior import ProbDistContainer, uniform_dist
+    g = cases.load("c2_small")
+    np.random.seed(int(g["seed"]))
+    pri = ProbDistContainer({i: uniform_dist(float(g["lo"]), float(g["hi"])) for i in range(int(g["ndim"]))})
+    x0 = pri.rvs(size=(int(g["ntemps"]), int(g["nwalkers"])))
+    np.testing.assert_array_equal(x0, g["x0"])
+    lo, hi, lp = pri.arrays()
+    np.testing.assert_array_equal(lp, orc.BoxPrior(lo, hi).logpdf_val)
+    with pytest.raises(ValueError):
+        uniform_dist(1.0, 1.0)
+    assert uniform_dist(2.0, -2.0).min_val == -2.0  # swapped like prior.py:29-32
+
+
+def test_state_shapes():
+    from eryn_b200.state import State
+    s = State(np.zeros((6, 3)))
+    assert s.branches["model_0"].shape == (1, 6, 1, 3)
+    s = State(np.zeros((2, 6, 3)))
+    assert s.branches["model_0"].shape == (2, 6, 1, 3) and s.branches_inds["model_0"].all()
+    with pytest.raises(ValueError):
+        State(np.zeros(3))
+    s2 = State(s, copy=True)
+    s2.branches["model_0"].coords[0, 0, 0, 0] = 1.0
+    assert s.branches["model_0"].coords[0, 0, 0, 0] == 0.0
+
+
+def test_backend_roundtrip():
+    from eryn_b200.backend import Backend
+    from eryn_b200.state import State
+    b = Backend()
+    b.reset(4, 2, ntemps=3, branch_names=["model_0"], moves=["StretchMove_0"])
+    b.grow(2)
+    st = State(np.arange(24.0).reshape(3, 4, 1, 2), log_like=np.ones((3, 4)), log_prior=np.zeros((3, 4)),
+               betas=np.array([1.0, 0.5, 0.1]))
+    b.save_step(st, np.ones((3, 4)), swaps_accepted=np.array([1.0, 2.0]))
+    b.save_step(st, np.ones((3, 4)), swaps_accepted=np.array([1.0, 2.0]))
+    assert b.iteration == 2 and b.get_chain()["model_0"].shape == (2, 3, 4, 1, 2)
+    assert b.accepted.sum() == 24 and list(b.swaps_accepted) == [2, 4]
+    last = b.get_last_sample()
+    np.testing.assert_array_equal(last.branches["model_0"].coords, st.branches["model_0"].coords)
+
+
+def test_philox_oracle_streams():
+    # Random123 known-answer vectors for Philox4x32-10
+    def h(v):
+        return [int(x) for x in v]
+    assert h(px.philox4x32_10(0, 0, 0, 0, 0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    m = 0xFFFFFFFF
+    assert h(px.philox4x32_10(m, m, m, m, m, m)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert h(px.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    for n in (1, 2, 3, 7, 32, 99, 4096, 5000):
+        p = px.split_perm(5, 77, 2, n)
+        assert sorted(p.tolist()) == list(range(n))
+    u = px.swap_uniforms(3, 9, 2, 1000)
+    assert u.min() > 0.0 and u.max() < 1.0
+    z = px.gauss_draws(0, 1, np.arange(20000), 3)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+
+
+def test_oracle_philox_sampler_is_a_valid_sampler():
+    """Production-mode streams through the oracle: a unit Gaussian is recovered (mean 0, var 1)."""
+    d, W = 2, 64
+    prior = orc.BoxPrior(np.full(d, -10.0), np.full(d, 10.0))
+    smp = orc.OracleSampler(prior, orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0],
+                            orc.PhiloxStreams(123), betas=orc.make_ladder_default(d, 3))
+    st = smp.initialise(orc.OState(np.random.RandomState(0).uniform(-1, 1, size=(3, W, d))))
+    xs = []
+    for it in range(600):
+        smp.iterate(st)
+        if it >= 100:
+            xs.append(st.coords[0, :, 0, :].copy())
+    xs = np.concatenate(xs)
+    assert np.all(np.abs(xs.mean(0)) < 0.15)
+    assert np.all(np.abs(xs.var(0) - 1.0) < 0.2)
+    assert smp.swaps_accepted.sum() > 0
