@@ -8,7 +8,7 @@ Metropolis test) + one parallel-tempering swap pass + ladder adaptation.  N=1 ru
 (16 temps x 4096 walkers x 8-d correlated Gaussian, StretchMove + PT).  Prints ONE JSON line on rank 0.
 
   value     device-resident throughput (state already in HBM), production (philox) mode, each step a
-            replay of the captured 3-kernel iteration graph, timed by its own CUDA-event pair with an
+            replay of the captured 2-kernel iteration graph, timed by its own CUDA-event pair with an
             L2 flush between steps (outside the pairs);
   e2e       the same step through the C-ABI entry with HOST buffers (eb_run_host): pinned host state ->
             H2D -> kernels -> D2H -> host state, every step;
@@ -272,7 +272,7 @@ def run_gpu(args):
     with torch.cuda.stream(stream):
         with torch.cuda.graph(gk, stream=stream):
             for r in range(nrep):
-                ctx.stretch_half_step(ds, r & 1, 2.0, accepted_count=cnt)
+                ctx.stretch_step(ds, 2.0, accepted_count=cnt)
         gk.replay()
         torch.cuda.synchronize()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -282,10 +282,10 @@ def run_gpu(args):
         torch.cuda.synchronize()
     k_us = k0.elapsed_time(k1) * 1e3 / nrep
     D = d
-    alg_bytes = (24 * D + 41) * T * (W // 2)  # 24*D+41 B per walker per half step
+    alg_bytes = (24 * D + 41) * T * W  # 24*D+41 B per walker-update; one launch updates all T*W walkers
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (k_us * 1e-6) / 1e9
-    roofline = dict(bound="hbm", kernel="stretch_half_step_kernel", achieved=round(achieved, 1), peak=peak, unit="GB/s",
+    roofline = dict(bound="hbm", kernel="stretch_step_kernel", achieved=round(achieved, 1), peak=peak, unit="GB/s",
                     frac=round(achieved / peak, 4), traffic=None, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes, avg_launch_us=round(k_us, 3),
                     note="state (4.3 MB at C2) is L2-resident across launches; back-to-back launches in one graph")
@@ -320,10 +320,10 @@ def run_gpu(args):
     state_bytes = h_coords.numel() * 8 + h_logl.numel() * 8 + h_logp.numel() * 8 + h_betas.numel() * 8
     e2e = dict(value=T * W / e2e_s, unit=UNIT, h2d_bytes_per_step=int(state_bytes + par.size * 8 + 3 * d * 8 + 4120),
                d2h_bytes_per_step=int(state_bytes + 4120), ms_per_step=e2e_s * 1e3,
-               api="eb_run_host(job, niter=1): pinned host State -> H2D -> 3 kernels -> D2H, every step")
+               api="eb_run_host(job, niter=1): pinned host State -> H2D -> 2 kernels -> D2H, every step")
 
     # ---- CPU baseline (oracle port), bounded sample -------------------------------------------------------------
-    cpu_v, cpu_s, cpu_n = run_cpu(wl, steps=10 ** 6, warmup=1, budget_s=12.0)
+    cpu_v, cpu_s, cpu_n = run_cpu(wl, steps=10 ** 6, warmup=1, budget_s=0.5 if args.profile else 12.0)
     cpu = dict(value=cpu_v, unit=UNIT, cores=cpu_threads(), kind="port",
                sample=f"{cpu_n} iterations of the same workload ({cpu_s * 1e3:.1f} ms/iteration), NumPy oracle port, "
                       f"os.cpu_count()={os.cpu_count()}")
@@ -333,7 +333,7 @@ def run_gpu(args):
                dtype="f64", data="synthetic",
                config=dict(workload=wl["label"], ntemps=T, nwalkers=W, ndim=d, rng="philox",
                            l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
-                           step="one iteration = 2 stretch half-step kernels + 1 swap/adapt kernel (CUDA graph replay)"),
+                           step="one iteration = 1 fused stretch kernel (both red/blue halves) + 1 swap/adapt kernel (CUDA graph replay)"),
                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                extra=dict(ms_per_step_resident_no_flush=resident_ms,
                           value_resident_no_flush=T * W / (resident_ms * 1e-3),
@@ -367,6 +367,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--profile", action="store_true", help="shorten the CPU-baseline leg (for runs under ncu)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3

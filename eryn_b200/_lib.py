@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "lib", "liberyn_b200.so")
 
 EB_MAX_TEMPS = 256
 EB_MAX_ROW = 32
+EB_MAX_RANKS = 16
 EB_RNG_REPLAY, EB_RNG_PHILOX = 0, 1
 EB_LIKE_GAUSSIAN, EB_LIKE_ROSENBROCK, EB_LIKE_GMIX = 0, 1, 2
 
@@ -20,6 +21,7 @@ vp = C.c_void_p
 
 class eb_state(C.Structure):
     _fields_ = [("ntemps", C.c_int32), ("nwalkers", C.c_int32), ("nleaves", C.c_int32), ("ndim", C.c_int32),
+                ("temp_offset", C.c_int32), ("_pad", C.c_int32),
                 ("coords", vp), ("logl", vp), ("logp", vp), ("inds", vp), ("betas", vp)]
 
 
@@ -33,9 +35,9 @@ class eb_like(C.Structure):
 
 
 class eb_stretch_rng(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("randomize_split", C.c_int32), ("sub_idx", vp), ("comp_idx", vp),
-                ("rint", vp), ("u_z", vp), ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp),
-                ("iter", C.c_uint64)]
+    _fields_ = [("mode", C.c_int32), ("randomize_split", C.c_int32),
+                ("list", vp * 2), ("rint", vp * 2), ("u_z", vp * 2), ("u_acc", vp * 2),
+                ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
 
 
 class eb_gauss_rng(C.Structure):
@@ -70,6 +72,13 @@ class eb_host_job(C.Structure):
                 ("swaps_accepted_host", vp), ("accepted_count_host", vp)]
 
 
+class eb_shard(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ntemps_total", C.c_int32),
+                ("temp_begin", C.c_int32 * (EB_MAX_RANKS + 1)),
+                ("coords_src", vp * EB_MAX_RANKS), ("logp_src", vp * EB_MAX_RANKS), ("inds_src", vp * EB_MAX_RANKS),
+                ("logl_all", vp), ("betas_all", vp)]
+
+
 # every symbol include/eryn_b200.h declares: name -> (restype, argtypes)
 P = C.POINTER
 SYMBOLS = {
@@ -79,19 +88,20 @@ SYMBOLS = {
     "eb_ctrl_size": (C.c_size_t, []),
     "eb_struct_size": (C.c_size_t, [C.c_int]),
     "eb_eval_state": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), vp]),
-    "eb_stretch_half_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), C.c_double, C.c_int32,
-                                       P(eb_stretch_rng), vp, vp, vp]),
+    "eb_stretch_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), C.c_double, P(eb_stretch_rng), vp, vp, vp]),
     "eb_gaussian_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), P(eb_gauss_rng), vp, vp, vp]),
     "eb_pt_swap": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
+    "eb_pt_swap_sharded": (C.c_int, [P(eb_shard), P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_advance_iter": (C.c_int, [vp, vp]),
     "eb_stretch_propose": (C.c_int, [P(eb_state), C.c_double, C.c_int32, P(eb_stretch_rng), vp, vp, vp, vp]),
-    "eb_accept_update": (C.c_int, [P(eb_state), vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int32, P(eb_stretch_rng),
+    "eb_accept_update": (C.c_int, [P(eb_state), vp, C.c_int32, vp, vp, vp, vp, C.c_int32, P(eb_stretch_rng),
                                    vp, vp, vp]),
     "eb_box_log_prior": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, P(eb_prior), vp, vp]),
     "eb_run_host": (C.c_int, [P(eb_host_job), C.c_int32]),
 }
 
-STRUCTS = [eb_state, eb_prior, eb_like, eb_stretch_rng, eb_gauss_rng, eb_swap_rng, eb_ctrl, eb_adapt, eb_host_job]
+STRUCTS = [eb_state, eb_prior, eb_like, eb_stretch_rng, eb_gauss_rng, eb_swap_rng, eb_ctrl, eb_adapt, eb_host_job,
+           eb_shard]
 
 _lib = None
 

@@ -73,6 +73,7 @@ int fill_common(Common& c, const eb_state* st, const eb_prior* prior, const eb_l
   c.coords = st->coords; c.logl = st->logl; c.logp = st->logp;
   c.inds = const_cast<uint8_t*>(st->inds); c.betas = st->betas;
   c.T = st->ntemps; c.W = st->nwalkers; c.L = st->nleaves; c.D = st->ndim; c.LD = st->nleaves * st->ndim;
+  c.t0 = st->temp_offset;
   c.lo = c.hi = c.lpdf = nullptr; c.like_params = nullptr; c.like_nparams = 0; c.like_ncomp = 0;
   if (prior) { c.lo = prior->lo; c.hi = prior->hi; c.lpdf = prior->logpdf; }
   if (like) { c.like_params = like->params; c.like_nparams = like->nparams; c.like_ncomp = like->ncomp; }
@@ -131,6 +132,7 @@ size_t eb_struct_size(int which) {
     case 6: return sizeof(eb_ctrl);
     case 7: return sizeof(eb_adapt);
     case 8: return sizeof(eb_host_job);
+    case 9: return sizeof(eb_shard);
     default: return 0;
   }
 }

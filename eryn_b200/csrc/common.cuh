@@ -2,11 +2,12 @@
 //
 // Kernels:
 //   K0  eval_state_kernel         log-prior + log-like of the whole state            (abi_core.cu)
-//   K1  stretch_half_step_kernel  fused: draw -> gather complement -> stretch -> prior/like ->
+//   K1  stretch_step_kernel       fused, both red/blue halves per launch (cluster per temperature):
+//                                 draw -> gather complement -> stretch -> prior/like ->
 //                                 tempered Metropolis test -> in-place update        (k_stretch.cu, hot kernel)
 //   K2  gaussian_step_kernel      fused Gaussian Metropolis step over all walkers    (k_gauss.cu)
-//   K3  pt_swap_kernel            chain-parallel swap ladder + in-place walker exchange +
-//                                 last-block ladder adaptation                       (k_swap.cu)
+//   K3  pt_swap_kernel            chain-parallel swap ladder (decide on logl, then move only the rows
+//                                 that changed rung, in place) + last-block ladder adaptation (k_swap.cu)
 //   K3r pt_pairmap_kernel         replay mode: host permutations -> per-position pair map
 //   K4  stretch_propose_kernel / accept_update_kernel / box_prior_kernel   (split path)
 //
@@ -40,6 +41,7 @@ constexpr int BLOCK = 128;
 struct Common {
   double* coords; double* logl; double* logp; uint8_t* inds; double* betas;
   int T, W, L, D, LD;
+  int t0;  // global index of local temperature 0 (random-stream keying)
   const double* lo; const double* hi; const double* lpdf;
   const double* like_params; int like_nparams, like_ncomp;
 };

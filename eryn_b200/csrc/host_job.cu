@@ -92,7 +92,7 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
 
   // ---- iterations -----------------------------------------------------------------------------
   eb_state st;
-  st.ntemps = T; st.nwalkers = W; st.nleaves = L; st.ndim = D;
+  st.ntemps = T; st.nwalkers = W; st.nleaves = L; st.ndim = D; st.temp_offset = 0; st._pad = 0;
   st.coords = (double*)cx.coords.p; st.logl = (double*)cx.logl.p; st.logp = (double*)cx.logp.p;
   st.inds = nullptr; st.betas = job->betas_host ? (double*)cx.betas.p : nullptr;
   eb_prior prior{(const double*)cx.prior.p, (const double*)cx.prior.p + D, (const double*)cx.prior.p + 2 * D};
@@ -113,11 +113,7 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
     const int mv = job->move_schedule_host ? job->move_schedule_host[it] : 0;
     int rc;
     if (mv == 0) {
-      rc = eb_stretch_half_step(&st, &prior, &like, job->stretch_a, 0, &srng, (uint8_t*)cx.acc.p,
-                                (uint32_t*)cx.acc_cnt.p, s);
-      if (rc) return rc;
-      rc = eb_stretch_half_step(&st, &prior, &like, job->stretch_a, 1, &srng, (uint8_t*)cx.acc.p,
-                                (uint32_t*)cx.acc_cnt.p, s);
+      rc = eb_stretch_step(&st, &prior, &like, job->stretch_a, &srng, (uint8_t*)cx.acc.p, (uint32_t*)cx.acc_cnt.p, s);
     } else {
       rc = eb_gaussian_step(&st, &prior, &like, &grng, (uint8_t*)cx.acc.p, (uint32_t*)cx.acc_cnt.p, s);
     }

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
 #pragma unroll
     for (int j = 0; j < DMAX; j += 2) {
       if (j < D) {
-        const uint4 r = stream(key, TAG_GAUSS, (uint32_t)tid, (uint32_t)(j >> 1));
+        const uint4 r = stream(key, TAG_GAUSS, (uint32_t)(tid + c.t0 * c.W), (uint32_t)(j >> 1));
         const double rad = sqrt(-2.0 * log(u01_52(r.x, r.y)));
         double sn, cs;
         sincos(6.283185307179586 * u01_52(r.z, r.w), &sn, &cs);
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
           }
       }
     }
-    const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)tid, 0u);
+    const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)(tid + c.t0 * c.W), 0u);
     u_acc = u01_52(ra.x, ra.y);
   } else {
     const double* dl = p.delta + (size_t)tid * c.LD;

@@ -8,187 +8,284 @@ namespace eb {
 // ================================================================================================
 // The reference walks the ladder hot -> cold; at rung i it pairs (i, iperm[k]) with
 // (i-1, i1perm[k]) (tempering.py:515-559).  Both permutations are bijections, so the slots touched
-// by successive rungs form W disjoint chains  p_{T-1} -> p_{T-2} -> ... -> p_0  with
-// p_{i-1} = i1perm_i[iperm_i^{-1}[p_i]], and every exchange stays inside one chain.  One group
-// of 8 lanes owns a chain: it carries the walker that is bubbling down in registers, decides each
-// rung from logl alone (:538) and rewrites only the slots whose content changed, in place.
+// by successive rungs form W disjoint chains  p_{T-1} -> p_{T-2} -> ... -> p_0  and every exchange
+// stays inside one chain.  The accept test needs logl only (:538), so a chain is resolved in three
+// phases by a group of 8 lanes, all staging in shared memory:
+//   1. positions p_r of the chain on every rung, logl[r][p_r] and log(u) of every rung — independent
+//      across rungs, lanes work on different rungs (philox mode: p_r = sigma_r(chain) with one keyed
+//      bijection per rung, so the pairing of rung i is sigma_{i-1} o sigma_i^{-1}, a uniform random
+//      bijection exactly like i1perm o iperm^{-1}; replay mode: lane 0 follows the host pair map);
+//   2. the hot -> cold cascade on those T numbers (one lane, registers + shared memory) giving
+//      src[r] = rung whose walker ends on rung r;
+//   3. only the rows with src[r] != r move: cp.async global -> shared for all of them at once, one
+//      warp-level sync, then shared -> global.  In place, no second state buffer.
+// The last block to finish folds the per-rung swap counts and adapts the ladder (tempering.py:563-596).
 struct SwapArgs {
-  Common c;
-  int philox, permute;
+  Common c;                                       // local state (sharded: the DESTINATION buffers of this rank)
+  int T;                                          // rungs of the full ladder
+  const double* logl_in;                          // [T][W] log-likelihoods the cascade reads
+  double* betas;                                  // [T] full ladder (adapted in place)
+  // temperature-sharded run (eb_pt_swap_sharded): this rank writes rungs [t_lo, t_hi) into c.*, reading
+  // the source rows from the rank that owns them (peer-mapped pointers)
+  int sharded, world, t_lo, t_hi;
+  int temp_begin[EB_MAX_RANKS + 1];
+  const double* coords_src[EB_MAX_RANKS]; const double* logp_src[EB_MAX_RANKS]; const uint8_t* inds_src[EB_MAX_RANKS];
+  int philox, permute, cpb;                       // cpb = chains per block
   const int32_t* next_pos; const double* u_at;  // replay pair map [T][W]
   uint32_t seed_lo, seed_hi; const unsigned long long* iter_dev; unsigned long long iter;
   eb_ctrl* ctrl;
   int adapt_on, adaptive, stop_adaptation; double lag, t0;
 };
 
-struct PairSrc {  // per-rung description of "who is my partner one rung colder"
-  const SwapArgs* p;
-  RngKey key;
-};
-
-template <bool PHILOX>
-__device__ __forceinline__ void pair_lookup(const SwapArgs& p, const RngKey& key, int rung, int pos, int& pos_next,
-                                            double& u) {
-  if (PHILOX) {
-    if (p.permute) {
-      Feistel sig;
-      sig.init(key, TAG_SWAP_KEY, (uint32_t)rung, (uint32_t)p.c.W);
-      pos_next = (int)sig((uint32_t)pos);
-    } else {
-      pos_next = pos;
-    }
-    const uint4 r = stream(key, TAG_SWAP_U, (uint32_t)pos, (uint32_t)rung);
-    u = u01_52(r.x, r.y);
-  } else {
-    const size_t i = (size_t)rung * p.c.W + pos;
-    pos_next = p.next_pos[i];
-    u = p.u_at[i];
-  }
-}
-
 constexpr int CHAIN_LANES = 8;
 
-template <int NPL>
-struct WalkerRegs {
-  double x[NPL];
-  double ll, lp;
-  uint32_t inds;  // this lane's leaf flags (bit j = leaf lane + 8 j)
+struct SwapLayout {  // byte offsets into dynamic shared memory
+  size_t betas, dts, ll, lu, rows, keys, pos, src, cnt, inds, total;
 };
-
-template <int NPL>
-__device__ __forceinline__ void load_walker(const Common& c, int rung, int pos, int lane, WalkerRegs<NPL>& r) {
-  const size_t slot = (size_t)rung * c.W + pos;
-  const double* row = c.coords + slot * c.LD;
-#pragma unroll
-  for (int j = 0; j < NPL; ++j) {
-    const int e = lane + CHAIN_LANES * j;
-    r.x[j] = (e < c.LD) ? row[e] : 0.0;
-  }
-  r.ll = c.logl[slot];
-  r.lp = c.logp[slot];
-  r.inds = 0;
-  if (c.inds) {
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-      const int l = lane + CHAIN_LANES * j;
-      if (l < c.L && c.inds[slot * c.L + l]) r.inds |= (1u << j);
-    }
-  }
+__host__ __device__ inline SwapLayout swap_layout(int T, int LD, int L, int cpb, bool has_inds, bool stage_rows) {
+  SwapLayout s;
+  const int RS = (LD + 2) & ~1;                            // row stride in doubles (coords + logp), 16-byte rows
+  size_t o = 0;
+  s.rows = o; o += stage_rows ? sizeof(double) * T * RS * cpb : 0;   // [chain][rung][RS]
+  s.betas = o; o += sizeof(double) * T;
+  s.dts = o; o += sizeof(double) * T;
+  s.ll = o; o += sizeof(double) * T * cpb;
+  s.lu = o; o += sizeof(double) * T * cpb;
+  s.keys = o; o += sizeof(uint32_t) * FEISTEL_ROUNDS * T;
+  s.pos = o; o += sizeof(int) * T * cpb;
+  s.src = o; o += sizeof(int) * T * cpb;
+  s.cnt = o; o += sizeof(int) * T;
+  s.inds = o; o += (has_inds && stage_rows) ? (size_t)T * L * cpb : 0;
+  s.total = (o + 15) & ~(size_t)15;
+  return s;
 }
 
-template <int NPL>
-__device__ __forceinline__ void store_walker(const Common& c, int rung, int pos, int lane, const WalkerRegs<NPL>& r) {
-  const size_t slot = (size_t)rung * c.W + pos;
-  double* row = c.coords + slot * c.LD;
-#pragma unroll
-  for (int j = 0; j < NPL; ++j) {
-    const int e = lane + CHAIN_LANES * j;
-    if (e < c.LD) row[e] = r.x[j];
-  }
-  if (lane == 0) {
-    c.logl[slot] = r.ll;
-    c.logp[slot] = r.lp;
-  }
-  if (c.inds) {
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-      const int l = lane + CHAIN_LANES * j;
-      if (l < c.L) c.inds[slot * c.L + l] = (r.inds >> j) & 1u;
-    }
-  }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
-
-// tempering.py:563-596 on one thread (T <= 256)
-__device__ void adapt_ladder(const SwapArgs& p, eb_ctrl* ctrl) {
-  const int T = p.c.T;
-  double* betas = p.c.betas;
-  const double time = (double)ctrl->time;
-  if (p.stop_adaptation < 0 || ctrl->time < (long long)p.stop_adaptation) {
-    const double decay = p.lag / (time + p.lag);                             // :571
-    const double kappa = decay / p.t0;                                       // :572
-    const double nw = (double)p.c.W;
-    const double inv_b0 = 1.0 / betas[0];
-    double cum = 0.0;
-    double b_prev_old = betas[0];
-    // deltaTs[j] = (1/betas[j+1] - 1/betas[j]) * exp(kappa*(ratios[j]-ratios[j+1])),  j = 0..T-3
-    for (int j = 0; j + 2 < T; ++j) {
-      const double bj1_old = betas[j + 1];
-      const double r0 = (double)ctrl->swaps_accepted[j] / nw;                // :587
-      const double r1 = (double)ctrl->swaps_accepted[j + 1] / nw;
-      const double dS = kappa * (r0 - r1);                                   // :575
-      double dT = 1.0 / bj1_old - 1.0 / b_prev_old;                          // :578
-      dT = dT * exp(dS);                                                     // :579
-      cum = cum + dT;                                                        // np.cumsum
-      const double bnew = 1.0 / (cum + inv_b0);                              // :580
-      betas[j + 1] = bj1_old + (bnew - bj1_old);                             // :583, :593
-      b_prev_old = bj1_old;
-    }
-  }
-  ctrl->time += 1;                                                           // :596
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int NPL, bool PHILOX>
-__global__ void __launch_bounds__(BLOCK) pt_swap_kernel(const SwapArgs p) {
+// Lane l of a chain's 8-lane group owns rungs l, l+8, l+16, ... in every phase.
+template <bool PHILOX, bool SHARDED>
+__global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
   const Common& c = p.c;
-  __shared__ int s_cnt[EB_MAX_TEMPS];
+  const int T = p.T, W = c.W, LD = c.LD, L = c.L, cpb = p.cpb;
+  const int RS = (LD + 2) & ~1;
+  const SwapLayout lay = swap_layout(T, LD, L, cpb, c.inds != nullptr, !SHARDED);
+  double* s_betas = reinterpret_cast<double*>(smraw + lay.betas);
+  double* s_dts = reinterpret_cast<double*>(smraw + lay.dts);
+  uint32_t* s_keys = reinterpret_cast<uint32_t*>(smraw + lay.keys);
+  int* s_cnt = reinterpret_cast<int*>(smraw + lay.cnt);
   __shared__ bool s_last;
-  for (int i = threadIdx.x; i < c.T; i += blockDim.x) s_cnt[i] = 0;
+
+  const int tid = threadIdx.x;
+  const int g = tid / CHAIN_LANES, lane = tid % CHAIN_LANES;
+  const int chain = blockIdx.x * cpb + g;
+  const bool valid = g < cpb && chain < W;
+  const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
+  const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
+
+  // ---- phase 0: ladder and per-rung bijection keys, once per block ------------------------------
+  for (int r = tid; r < T; r += blockDim.x) {
+    s_betas[r] = p.betas[r];
+    s_cnt[r] = 0;
+    if (PHILOX && p.permute) Feistel::make_keys(key, TAG_SWAP_KEY, (uint32_t)r, s_keys + FEISTEL_ROUNDS * r);
+  }
   __syncthreads();
 
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int chain = gtid / CHAIN_LANES;
-  const int lane = gtid % CHAIN_LANES;
-  if (chain < c.W) {
-    const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
-    const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
-    const int T = c.T;
-    int pos = chain;                       // p_{T-1}
-    int origin = T - 1;
-    WalkerRegs<NPL> carry, nxt, nn;
-    load_walker<NPL>(c, T - 1, pos, lane, carry);
-    int pos_n; double u_i;
-    pair_lookup<PHILOX>(p, key, T - 1, pos, pos_n, u_i);
-    load_walker<NPL>(c, T - 2, pos_n, lane, nxt);
-    for (int i = T - 1; i >= 1; --i) {
-      int pos_nn = 0; double u_n = 0.5;
-      if (i >= 2) {                        // prefetch the partner of the next rung before any store
-        pair_lookup<PHILOX>(p, key, i - 1, pos_n, pos_nn, u_n);
-        load_walker<NPL>(c, i - 2, pos_nn, lane, nn);
+  const int gg = valid ? g : 0;
+  double* ll = reinterpret_cast<double*>(smraw + lay.ll) + (size_t)gg * T;
+  double* lu = reinterpret_cast<double*>(smraw + lay.lu) + (size_t)gg * T;
+  double* rows = reinterpret_cast<double*>(smraw + lay.rows) + (size_t)gg * T * RS;
+  int* pos = reinterpret_cast<int*>(smraw + lay.pos) + (size_t)gg * T;
+  int* src = reinterpret_cast<int*>(smraw + lay.src) + (size_t)gg * T;
+  uint8_t* sinds = smraw + lay.inds + (size_t)gg * T * L;
+
+  // ---- phase 1: chain positions, logl and log(u) of the owned rungs ----------------------------
+  if (!PHILOX) {
+    if (valid && lane == 0) {            // replay: p_{i-1} = i1perm_i[iperm_i^{-1}[p_i]] (pt_pairmap_kernel)
+      int pz = chain;
+      pos[T - 1] = pz;
+      for (int i = T - 1; i >= 1; --i) {
+        pz = p.next_pos[(size_t)i * W + pz];
+        pos[i - 1] = pz;
       }
-      const double dbeta = c.betas[i - 1] - c.betas[i];                      // tempering.py:518-522
-      const double paccept = dbeta * (carry.ll - nxt.ll);                    // :538
-      const bool sel = paccept > log(u_i);                                   // :535, :541
-      if (sel) {
-        store_walker<NPL>(c, i, pos, lane, nxt);                             // (i-1) walker moves up
-        if (lane == 0) atomicAdd(&s_cnt[i - 1], 1);                          // :542
+    }
+    __syncwarp();
+  }
+  if (valid) {
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    for (int m = 0, r = lane; r < T; ++m, r += CHAIN_LANES) {
+      int pz;
+      if (PHILOX) {
+        pz = chain;
+        if (p.permute) {
+          Feistel sig;
+          sig.init_from(s_keys + FEISTEL_ROUNDS * r, (uint32_t)W);
+          pz = (int)sig((uint32_t)chain);
+        }
+        pos[r] = pz;
       } else {
-        if (origin != i) store_walker<NPL>(c, i, pos, lane, carry);          // carried walker settles here
-        carry = nxt;
+        pz = pos[r];
+      }
+      ll[r] = p.logl_in[(size_t)r * W + pz];
+      double u;
+      if (PHILOX) {                      // one Philox block serves two owned rungs (r and r + 8)
+        if ((m & 1) == 0) q = stream(key, TAG_SWAP_U, (uint32_t)chain, (uint32_t)(lane + CHAIN_LANES * (m >> 1)));
+        u = (m & 1) ? u01_52(q.z, q.w) : u01_52(q.x, q.y);
+      } else {
+        u = (r >= 1) ? p.u_at[(size_t)r * W + pz] : 0.5;
+      }
+      lu[r] = log(u);                                                          // tempering.py:535
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 2: the cascade, hot -> cold (tempering.py:515-559 restricted to this chain) --------
+  if (valid && lane == 0) {
+    double carry = ll[T - 1];
+    int origin = T - 1;
+    for (int i = T - 1; i >= 1; --i) {
+      const double dbeta = s_betas[i - 1] - s_betas[i];                        // :518-522
+      const double lower = ll[i - 1];
+      const bool sel = dbeta * (carry - lower) > lu[i];                        // :538, :541
+      if (sel) {
+        src[i] = i - 1;                  // the colder walker moves up, the carried one keeps falling
+      } else {
+        src[i] = origin;                 // the carried walker settles on rung i
+        carry = lower;
         origin = i - 1;
       }
-      pos = pos_n; pos_n = pos_nn; u_i = u_n; nxt = nn;
     }
-    if (origin != 0) store_walker<NPL>(c, 0, pos, lane, carry);
+    src[0] = origin;
   }
+  __syncwarp();
+
+  // ---- phase 3: move the rows that changed rung (do_swaps_indexing, tempering.py:351-482) ------
+  // swaps_accepted[r-1] counts src[r] == r-1 (:542): summed over the 4 chains of the warp by shuffles
+  for (int r0 = 0; r0 < T; r0 += CHAIN_LANES) {   // uniform trip count: the loop body shuffles
+    const int r = r0 + lane;
+    int sel = 0;
+    if (valid && r < T) {
+      const int s = src[r];
+      sel = (r >= 1 && s == r - 1) ? 1 : 0;
+      if (!SHARDED && s != r) {
+        const size_t sslot = (size_t)s * W + pos[s];
+        const double* grow = c.coords + sslot * LD;
+        double* srow = rows + (size_t)r * RS;
+        if ((LD & 1) == 0) {
+          for (int e = 0; e < LD; e += 2) cp_async16(srow + e, grow + e);
+        } else {
+          for (int e = 0; e < LD; ++e) cp_async8(srow + e, grow + e);
+        }
+        cp_async8(srow + LD, c.logp + sslot);
+        if (c.inds)
+          for (int l = 0; l < L; ++l) sinds[r * L + l] = c.inds[sslot * L + l];
+      }
+    }
+    sel += __shfl_xor_sync(0xffffffffu, sel, 8);
+    sel += __shfl_xor_sync(0xffffffffu, sel, 16);
+    if (sel && (tid & 31) < CHAIN_LANES) atomicAdd(&s_cnt[r - 1], sel);
+  }
+  if (!SHARDED) {
+    cp_async_wait_all();
+    __syncwarp();                        // every lane has read its sources before any lane writes
+    if (valid) {
+      for (int r = lane; r < T; r += CHAIN_LANES) {
+        const int s = src[r];
+        if (s == r) continue;
+        const size_t dslot = (size_t)r * W + pos[r];
+        double* grow = c.coords + dslot * LD;
+        const double* srow = rows + (size_t)r * RS;
+        if ((LD & 1) == 0) {
+          for (int e = 0; e < LD; e += 2) *reinterpret_cast<double2*>(grow + e) = *reinterpret_cast<const double2*>(srow + e);
+        } else {
+          for (int e = 0; e < LD; ++e) grow[e] = srow[e];
+        }
+        c.logp[dslot] = srow[LD];
+        c.logl[dslot] = ll[s];
+        if (c.inds)
+          for (int l = 0; l < L; ++l) c.inds[dslot * L + l] = sinds[r * L + l];
+      }
+    }
+  } else if (valid) {
+    // Sharded: this rank owns rungs [t_lo, t_hi).  Every owned slot is (re)written into the destination
+    // buffers from the CURRENT buffers of whichever rank holds the source rung (NVLink peer loads), the 8
+    // lanes of the chain sharing each row.  No staging: source and destination buffers are distinct.
+    for (int r = p.t_lo; r < p.t_hi; ++r) {
+      const int s = src[r];
+      int gsrc = 0;
+      while (gsrc + 1 < p.world && s >= p.temp_begin[gsrc + 1]) ++gsrc;
+      const size_t sslot = (size_t)(s - p.temp_begin[gsrc]) * W + pos[s];
+      const size_t dslot = (size_t)(r - p.t_lo) * W + pos[r];
+      const double* grow = p.coords_src[gsrc] + sslot * LD;
+      double* drow = c.coords + dslot * LD;
+      for (int e = lane; e < LD; e += CHAIN_LANES) drow[e] = grow[e];
+      if (lane == (LD & (CHAIN_LANES - 1))) {
+        c.logp[dslot] = p.logp_src[gsrc][sslot];
+        c.logl[dslot] = ll[s];
+      }
+      if (c.inds)
+        for (int l = lane; l < L; l += CHAIN_LANES) c.inds[dslot * L + l] = p.inds_src[gsrc][sslot * L + l];
+    }
+  }
+
+  // ---- swap counts; the last block folds them and adapts the ladder ---------------------------
   __syncthreads();
   eb_ctrl* ctrl = p.ctrl;
-  for (int i = threadIdx.x; i < c.T - 1; i += blockDim.x)
-    if (s_cnt[i]) atomicAdd(&ctrl->swaps_work[i], s_cnt[i]);
+  for (int r = tid; r < T - 1; r += blockDim.x)
+    if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[r], s_cnt[r]);
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     const unsigned int tk = atomicAdd(&ctrl->ticket, 1u);
     s_last = (tk == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
-    for (int i = 0; i < c.T - 1; ++i) {
-      const int v = atomicExch(&ctrl->swaps_work[i], 0);
-      ctrl->swaps_accepted[i] = v;
-      ctrl->swaps_total[i] += (unsigned long long)v;
+  if (!s_last) return;
+  __threadfence();
+  for (int r = tid; r < T - 1; r += blockDim.x) {
+    const int v = atomicExch(&ctrl->swaps_work[r], 0);
+    ctrl->swaps_accepted[r] = v;
+    ctrl->swaps_total[r] += (unsigned long long)v;
+    s_cnt[r] = v;
+  }
+  const long long time_now = ctrl->time;
+  __syncthreads();
+  if (p.adapt_on && p.adaptive && T > 1) {                                     // tempering.py:632-633
+    if (p.stop_adaptation < 0 || time_now < (long long)p.stop_adaptation) {   // :590
+      const double decay = p.lag / ((double)time_now + p.lag);                 // :571
+      const double kappa = decay / p.t0;                                       // :572
+      const double nw = (double)W;
+      // deltaTs[j] = (1/betas[j+1] - 1/betas[j]) * exp(kappa*(ratios[j]-ratios[j+1])),  j = 0..T-3
+      for (int j = tid; j + 2 < T; j += blockDim.x) {
+        const double r0 = (double)s_cnt[j] / nw, r1 = (double)s_cnt[j + 1] / nw;   // :587
+        const double dS = kappa * (r0 - r1);                                   // :575
+        double dT = 1.0 / s_betas[j + 1] - 1.0 / s_betas[j];                   // :578
+        s_dts[j] = dT * exp(dS);                                               // :579
+      }
+      __syncthreads();
+      if (tid == 0) {                                                          // np.cumsum: sequential adds
+        double cum = 0.0;
+        for (int j = 0; j + 2 < T; ++j) { cum = cum + s_dts[j]; s_dts[j] = cum; }
+      }
+      __syncthreads();
+      const double inv_b0 = 1.0 / s_betas[0];
+      for (int j = tid; j + 2 < T; j += blockDim.x) {
+        const double bold = s_betas[j + 1];
+        const double bnew = 1.0 / (s_dts[j] + inv_b0);                         // :580
+        p.betas[j + 1] = bold + (bnew - bold);                                 // :583, :593
+      }
     }
-    if (p.adapt_on && p.adaptive && c.T > 1) adapt_ladder(p, ctrl);          // tempering.py:632-633
+    if (tid == 0) ctrl->time = time_now + 1;                                   // :596
+  }
+  if (tid == 0) {
     ctrl->iter += 1ull;
     ctrl->ticket = 0u;
   }
@@ -209,21 +306,10 @@ __global__ void __launch_bounds__(BLOCK) pt_pairmap_kernel(const int32_t* __rest
 
 }  // namespace eb
 
-using namespace eb;
+namespace eb {
 
-extern "C" {
-
-int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl, void* stream) {
-  SwapArgs args;
-  int rc = fill_common(args.c, st, nullptr, nullptr, false);
-  if (rc) return rc;
+static int fill_swap_common(SwapArgs& args, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl) {
   if (!rng || !ctrl) return fail(EB_ERR_INVALID, "rng/ctrl is NULL");
-  if (!st->betas) return fail(EB_ERR_INVALID, "swap pass needs betas");
-  cudaStream_t s = (cudaStream_t)stream;
-  const int T = args.c.T, W = args.c.W;
-  if (T < 2) return eb_advance_iter(ctrl, stream);  // range(ntemps-1, 0, -1) is empty
-  if (args.c.LD > CHAIN_LANES * 4 || args.c.L > CHAIN_LANES * 4)
-    return fail(EB_ERR_UNSUPPORTED, "swap kernel covers nleaves*ndim <= %d (got %d)", CHAIN_LANES * 4, args.c.LD);
   args.philox = rng->mode == EB_RNG_PHILOX; args.permute = rng->permute;
   args.next_pos = rng->next_pos; args.u_at = rng->u_at;
   args.seed_lo = (uint32_t)(rng->seed & 0xFFFFFFFFull); args.seed_hi = (uint32_t)(rng->seed >> 32);
@@ -234,8 +320,56 @@ int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt
   args.stop_adaptation = adapt ? adapt->stop_adaptation : -1;
   args.lag = adapt ? adapt->adaptation_lag : 10000.0;
   args.t0 = adapt ? adapt->adaptation_time : 100.0;
+  if (!args.philox && rng->mode != EB_RNG_REPLAY) return fail(EB_ERR_INVALID, "unknown rng mode %d", rng->mode);
+  return EB_OK;
+}
+
+template <bool SHARDED>
+static int launch_swap(SwapArgs& args, cudaStream_t s) {
+  // chains per block: as many as fit shared memory, at most 16 (128 threads)
+  const int T = args.T, W = args.c.W;
+  const bool has_inds = args.c.inds != nullptr;
+  int cpb = 16;
+  while (cpb > 1 && swap_layout(T, args.c.LD, args.c.L, cpb, has_inds, !SHARDED).total > 96 * 1024) cpb >>= 1;
+  const size_t sb = swap_layout(T, args.c.LD, args.c.L, cpb, has_inds, !SHARDED).total;
+  if (sb > 200 * 1024)
+    return fail(EB_ERR_UNSUPPORTED, "swap pass: one chain of %d rungs x %d doubles does not fit shared memory", T,
+                args.c.LD);
+  args.cpb = cpb;
+  const int threads = max(32, cpb * CHAIN_LANES);
+  const int grid = (W + cpb - 1) / cpb;
+  int rc;
+  if (args.philox) {
+    rc = set_smem(pt_swap_kernel<true, SHARDED>, sb);
+    if (rc) return rc;
+    pt_swap_kernel<true, SHARDED><<<grid, threads, sb, s>>>(args);
+  } else {
+    rc = set_smem(pt_swap_kernel<false, SHARDED>, sb);
+    if (rc) return rc;
+    pt_swap_kernel<false, SHARDED><<<grid, threads, sb, s>>>(args);
+  }
+  return check_launch("pt_swap");
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" {
+
+int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl, void* stream) {
+  SwapArgs args;
+  memset(&args, 0, sizeof(args));
+  int rc = fill_common(args.c, st, nullptr, nullptr, false);
+  if (rc) return rc;
+  rc = fill_swap_common(args, rng, adapt, ctrl);
+  if (rc) return rc;
+  if (!st->betas) return fail(EB_ERR_INVALID, "swap pass needs betas");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int T = args.c.T, W = args.c.W;
+  if (T < 2) return eb_advance_iter(ctrl, stream);  // range(ntemps-1, 0, -1) is empty
+  args.T = T; args.logl_in = args.c.logl; args.betas = args.c.betas;
   if (!args.philox) {
-    if (rng->mode != EB_RNG_REPLAY) return fail(EB_ERR_INVALID, "unknown rng mode %d", rng->mode);
     if (!rng->iperm || !rng->i1perm || !rng->u || !rng->next_pos || !rng->u_at)
       return fail(EB_ERR_INVALID, "replay mode needs iperm, i1perm, u and the next_pos/u_at scratch");
     const int n = T * W;
@@ -244,20 +378,41 @@ int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt
     rc = check_launch("pt_pairmap");
     if (rc) return rc;
   }
-  const int npl = (max(args.c.LD, args.c.L) + CHAIN_LANES - 1) / CHAIN_LANES;
-  const int nthreads = W * CHAIN_LANES;
-  const int grid = (nthreads + BLOCK - 1) / BLOCK;
-#define SW_(N)                                                                     \
-  if (args.philox) pt_swap_kernel<N, true><<<grid, BLOCK, 0, s>>>(args);           \
-  else pt_swap_kernel<N, false><<<grid, BLOCK, 0, s>>>(args)
-  switch (npl) {
-    case 1: SW_(1); break;
-    case 2: SW_(2); break;
-    case 3: SW_(3); break;
-    default: SW_(4); break;
+  return launch_swap<false>(args, s);
+}
+
+int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rng* rng, const eb_adapt* adapt,
+                       eb_ctrl* ctrl, void* stream) {
+  SwapArgs args;
+  memset(&args, 0, sizeof(args));
+  if (!sh) return fail(EB_ERR_INVALID, "shard description is NULL");
+  int rc = fill_common(args.c, dst, nullptr, nullptr, false);
+  if (rc) return rc;
+  rc = fill_swap_common(args, rng, adapt, ctrl);
+  if (rc) return rc;
+  if (!args.philox) return fail(EB_ERR_UNSUPPORTED, "temperature-sharded swaps run in philox mode only");
+  if (sh->world < 1 || sh->world > EB_MAX_RANKS || sh->rank < 0 || sh->rank >= sh->world)
+    return fail(EB_ERR_INVALID, "bad rank/world %d/%d", sh->rank, sh->world);
+  const int T = sh->ntemps_total;
+  if (T < 1 || T > EB_MAX_TEMPS) return fail(EB_ERR_INVALID, "ntemps_total %d out of range", T);
+  if (!sh->logl_all || !sh->betas_all) return fail(EB_ERR_INVALID, "logl_all/betas_all is NULL");
+  if (sh->temp_begin[0] != 0 || sh->temp_begin[sh->world] != T)
+    return fail(EB_ERR_INVALID, "temp_begin must run from 0 to ntemps_total");
+  for (int g = 0; g < sh->world; ++g) {
+    if (sh->temp_begin[g + 1] < sh->temp_begin[g]) return fail(EB_ERR_INVALID, "temp_begin must be non-decreasing");
+    const bool owns = sh->temp_begin[g + 1] > sh->temp_begin[g];
+    if (owns && (!sh->coords_src[g] || !sh->logp_src[g] || (dst->inds && !sh->inds_src[g])))
+      return fail(EB_ERR_INVALID, "source pointers of rank %d are NULL", g);
+    args.coords_src[g] = sh->coords_src[g]; args.logp_src[g] = sh->logp_src[g]; args.inds_src[g] = sh->inds_src[g];
   }
-#undef SW_
-  return check_launch("pt_swap");
+  for (int g = 0; g <= sh->world; ++g) args.temp_begin[g] = sh->temp_begin[g];
+  args.sharded = 1; args.world = sh->world;
+  args.t_lo = sh->temp_begin[sh->rank]; args.t_hi = sh->temp_begin[sh->rank + 1];
+  if (dst->ntemps != args.t_hi - args.t_lo || dst->temp_offset != args.t_lo)
+    return fail(EB_ERR_INVALID, "destination state must hold this rank's temperatures [%d, %d)", args.t_lo, args.t_hi);
+  args.T = T; args.logl_in = sh->logl_all; args.betas = sh->betas_all;
+  if (T < 2) return eb_advance_iter(ctrl, stream);
+  return launch_swap<true>(args, (cudaStream_t)stream);
 }
 
 }  // extern "C"

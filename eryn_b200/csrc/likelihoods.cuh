@@ -98,15 +98,19 @@ struct Like<0> {  // EB_LIKE_GAUSSIAN: params mu[D], P[D*D]
     double d[DMAX];
 #pragma unroll
     for (int i = 0; i < DMAX; ++i) d[i] = (i < D) ? x[i] - mu[i] : 0.0;
+    // explicit FMAs (the build uses --fmad=false for the reference-ordered arithmetic of the proposal);
+    // two accumulators per row keep the dependent chains short
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < DMAX; ++i) {
       if (i < D) {
-        double r = 0.0;
+        double r0 = 0.0, r1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < DMAX; ++j)
-          if (j < D) r += P[i * D + j] * d[j];
-        acc += d[i] * r;
+        for (int j = 0; j < DMAX; j += 2) {
+          if (j < D) r0 = fma(P[i * D + j], d[j], r0);
+          if (j + 1 < D) r1 = fma(P[i * D + j + 1], d[j + 1], r1);
+        }
+        acc = fma(d[i], r0 + r1, acc);
       }
     }
     return -0.5 * acc;

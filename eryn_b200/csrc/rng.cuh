@@ -46,26 +46,63 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   return h;
 }
 
-// Keyed bijection of [0, n): 6-round balanced Feistel network on 2*hb bits + cycle walking.
+// (integer, fraction) of x * n / 2^64 for a 64-bit uniform x: the integer part is uniform on [0, n), the
+// fraction is uniform on [0, 1) and independent of it (one draw -> randint + rand)
+__device__ __forceinline__ void split_draw(uint32_t lo, uint32_t hi, uint32_t n, uint32_t& ipart, double& frac) {
+  const unsigned long long x = ((unsigned long long)hi << 32) | (unsigned long long)lo;
+  ipart = (uint32_t)__umul64hi(x, (unsigned long long)n);
+  const unsigned long long f = x * (unsigned long long)n;
+  frac = __dmul_rn(__dadd_rn((double)(f >> 12), 0.5), 2.220446049250313e-16);
+}
+
+// Keyed bijection of [0, n): 4-round balanced Feistel network on 2*hb bits + cycle walking.  The four
+// round keys are one Philox block.
+constexpr int FEISTEL_ROUNDS = 4;
 struct Feistel {
-  uint32_t k[6];
+  uint32_t k[FEISTEL_ROUNDS];
   uint32_t n, hb, mask;
 
-  __device__ __forceinline__ void init(const RngKey& key, uint32_t tag, uint32_t idx, uint32_t n_) {
-    uint4 w = stream(key, tag, idx, 0u);
-    k[0] = w.x; k[1] = w.y; k[2] = w.z; k[3] = w.w;
-    k[4] = w.x ^ 0x9E3779B9u; k[5] = w.y ^ 0xBB67AE85u;
+  __device__ __forceinline__ void set_size(uint32_t n_) {
     n = n_;
     uint32_t bits = (n_ <= 2u) ? 1u : (32u - (uint32_t)__clz((int)(n_ - 1u)));
     hb = (bits + 1u) >> 1;
     mask = (1u << hb) - 1u;
+  }
+  // round keys of bijection number `idx` of stream `tag`
+  static __device__ __forceinline__ void make_keys(const RngKey& key, uint32_t tag, uint32_t idx, uint32_t* k4) {
+    uint4 w = stream(key, tag, idx, 0u);
+    k4[0] = w.x; k4[1] = w.y; k4[2] = w.z; k4[3] = w.w;
+  }
+  __device__ __forceinline__ void init(const RngKey& key, uint32_t tag, uint32_t idx, uint32_t n_) {
+    make_keys(key, tag, idx, k);
+    set_size(n_);
+  }
+  // keys computed once per block and staged in shared memory
+  __device__ __forceinline__ void init_from(const uint32_t* k4, uint32_t n_) {
+#pragma unroll
+    for (int r = 0; r < FEISTEL_ROUNDS; ++r) k[r] = k4[r];
+    set_size(n_);
+  }
+  // inverse bijection: rounds undone last to first, cycle walking on the inverse permutation
+  __device__ __forceinline__ uint32_t inv(uint32_t x) const {
+    if (n <= 1u) return 0u;
+    do {
+      uint32_t L = x >> hb, R = x & mask;
+#pragma unroll
+      for (int r = FEISTEL_ROUNDS - 1; r >= 0; --r) {
+        uint32_t pl = R ^ (fmix32(L ^ k[r]) & mask);
+        R = L; L = pl;
+      }
+      x = (L << hb) | R;
+    } while (x >= n);
+    return x;
   }
   __device__ __forceinline__ uint32_t operator()(uint32_t x) const {
     if (n <= 1u) return 0u;
     do {
       uint32_t L = x >> hb, R = x & mask;
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
+      for (int r = 0; r < FEISTEL_ROUNDS; ++r) {
         uint32_t nr = L ^ (fmix32(R ^ k[r]) & mask);
         L = R; R = nr;
       }

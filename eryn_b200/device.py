@@ -24,10 +24,11 @@ class DeviceState(object):
     """Walker state of one branch as CUDA tensors, laid out like the reference's arrays:
     coords [T,W,L,D] f64, logl/logp [T,W] f64, inds [T,W,L] u8 (or None), betas [T] f64 (or None)."""
 
-    def __init__(self, coords, logl, logp, inds=None, betas=None, branch_name="model_0"):
+    def __init__(self, coords, logl, logp, inds=None, betas=None, branch_name="model_0", temp_offset=0):
         assert coords.is_cuda and coords.dtype == torch.float64 and coords.is_contiguous() and coords.dim() == 4
         self.coords, self.logl, self.logp, self.inds, self.betas = coords, logl, logp, inds, betas
         self.branch_name = branch_name
+        self.temp_offset = int(temp_offset)  # temperature-sharded runs: global index of local temperature 0
         self.shape = tuple(coords.shape)
         self._c = None
 
@@ -37,14 +38,14 @@ class DeviceState(object):
 
     def c_struct(self):
         T, W, L, D = self.shape
-        st = _lib.eb_state(T, W, L, D, _ptr(self.coords), _ptr(self.logl), _ptr(self.logp), _ptr(self.inds),
-                           _ptr(self.betas))
+        st = _lib.eb_state(T, W, L, D, self.temp_offset, 0, _ptr(self.coords), _ptr(self.logl), _ptr(self.logp),
+                           _ptr(self.inds), _ptr(self.betas))
         return st
 
     def clone(self):
         return DeviceState(self.coords.clone(), self.logl.clone(), self.logp.clone(),
                            None if self.inds is None else self.inds.clone(),
-                           None if self.betas is None else self.betas.clone(), self.branch_name)
+                           None if self.betas is None else self.betas.clone(), self.branch_name, self.temp_offset)
 
 
 class DeviceContext(object):
@@ -199,6 +200,7 @@ class DeviceContext(object):
         return ll
 
     def _stretch_rng(self, randomize_split, replay):
+        """replay = dict(lists [2][T,Ns_s], rint [2], u_z [2], u_acc [2]) of host NumPy draws."""
         r = _lib.eb_stretch_rng()
         r.randomize_split = int(bool(randomize_split))
         keep = None
@@ -207,48 +209,51 @@ class DeviceContext(object):
             r.seed = self.seed
             r.iter_dev = self.iter_ptr
         else:
-            sub, comp, rint, u_z, u_acc = replay
-            keep = (self.to_dev(sub, np.int32), self.to_dev(comp, np.int32), self.to_dev(rint, np.int64),
-                    self.to_dev(u_z, np.float64), None if u_acc is None else self.to_dev(u_acc, np.float64))
+            keep = dict(list=[self.to_dev(x, np.int32) for x in replay["lists"]],
+                        rint=[self.to_dev(x, np.int64) for x in replay["rint"]],
+                        u_z=[self.to_dev(x, np.float64) for x in replay["u_z"]],
+                        u_acc=[None if x is None else self.to_dev(x, np.float64) for x in replay["u_acc"]])
             r.mode = _lib.EB_RNG_REPLAY
-            r.sub_idx, r.comp_idx, r.rint, r.u_z, r.u_acc = [_ptr(t) for t in keep]
+            for s in range(2):
+                r.list[s], r.rint[s] = _ptr(keep["list"][s]), _ptr(keep["rint"][s])
+                r.u_z[s], r.u_acc[s] = _ptr(keep["u_z"][s]), _ptr(keep["u_acc"][s])
         return r, keep
 
-    def stretch_half_step(self, d, split, a, randomize_split=True, replay=None, accepted_count=None):
-        """StretchMove half step, fused (red_blue.py:148-323 + stretch.py:74-231 + move.py:472)."""
+    def stretch_step(self, d, a, randomize_split=True, replay=None, accepted_count=None):
+        """StretchMove step, both halves fused (red_blue.py:148-323 + stretch.py:74-231 + move.py:472)."""
         self._require_fused()
         T, W, L, D = d.shape
         st = d.c_struct()
         r, keep = self._stretch_rng(randomize_split, replay)
         acc = self.accepted_mask(T, W)
-        _lib.check(self.lib.eb_stretch_half_step(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c),
-                                                 float(a), int(split), C.byref(r), _ptr(acc), _ptr(accepted_count),
-                                                 self.stream()), "eb_stretch_half_step")
+        _lib.check(self.lib.eb_stretch_step(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c),
+                                            float(a), C.byref(r), _ptr(acc), _ptr(accepted_count),
+                                            self.stream()), "eb_stretch_step")
         self.launches += 1
         return acc
 
-    def stretch_half_step_split(self, d, split, a, randomize_split=True, replay=None, accepted_count=None):
-        """Split path for callables: propose kernel -> prior kernel -> user likelihood -> accept kernel."""
+    def stretch_step_split(self, d, a, randomize_split=True, replay=None, accepted_count=None):
+        """Split path for callables, per half: propose kernel -> prior kernel -> user likelihood -> accept kernel."""
         T, W, L, D = d.shape
-        Ns = (W + 1) // 2 if split == 0 else W // 2
         st = d.c_struct()
         r, keep = self._stretch_rng(randomize_split, replay)
-        q = torch.empty((T * Ns, L, D), dtype=torch.float64, device=self.device)
-        factors = torch.empty(T * Ns, dtype=torch.float64, device=self.device)
-        sub = torch.empty(T * Ns, dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.eb_stretch_propose(C.byref(st), float(a), int(split), C.byref(r), _ptr(q), _ptr(factors),
-                                               _ptr(sub), self.stream()), "eb_stretch_propose")
-        inds_sub = None
-        if d.inds is not None:
-            inds_sub = torch.gather(d.inds, 1, sub.view(T, Ns, 1).long().expand(T, Ns, L)).reshape(T * Ns, L).contiguous()
-        lp = self.box_log_prior(q, inds_sub)
-        ll = self.user_log_like(q, lp)
         acc = self.accepted_mask(T, W)
-        u_acc = keep[4] if keep is not None else None
-        _lib.check(self.lib.eb_accept_update(C.byref(st), _ptr(sub), Ns, _ptr(q), _ptr(factors), _ptr(ll), _ptr(lp),
-                                             _ptr(u_acc), int(split), C.byref(r), _ptr(acc), _ptr(accepted_count),
-                                             self.stream()), "eb_accept_update")
-        self.launches += 3
+        for split in range(2):
+            Ns = (W + 1) // 2 if split == 0 else W // 2
+            q = torch.empty((T * Ns, L, D), dtype=torch.float64, device=self.device)
+            factors = torch.empty(T * Ns, dtype=torch.float64, device=self.device)
+            sub = torch.empty(T * Ns, dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.eb_stretch_propose(C.byref(st), float(a), int(split), C.byref(r), _ptr(q),
+                                                   _ptr(factors), _ptr(sub), self.stream()), "eb_stretch_propose")
+            inds_sub = None
+            if d.inds is not None:
+                inds_sub = torch.gather(d.inds, 1, sub.view(T, Ns, 1).long().expand(T, Ns, L)).reshape(T * Ns, L).contiguous()
+            lp = self.box_log_prior(q, inds_sub)
+            ll = self.user_log_like(q, lp)
+            _lib.check(self.lib.eb_accept_update(C.byref(st), _ptr(sub), Ns, _ptr(q), _ptr(factors), _ptr(ll), _ptr(lp),
+                                                 int(split), C.byref(r), _ptr(acc), _ptr(accepted_count),
+                                                 self.stream()), "eb_accept_update")
+            self.launches += 3
         return acc
 
     def gaussian_step(self, d, proposal, replay=None, accepted_count=None):

@@ -30,7 +30,7 @@ class StretchMove(Move):
                 "It is unadvisable to use a red-blue move with fewer walkers than twice the number of "
                 "dimensions. If you would like to do this, please set live_dangerously to True.")
         cnt = self._count_buffer(ctx, T, W)
-        step = ctx.stretch_half_step if ctx.fused else ctx.stretch_half_step_split
+        step = ctx.stretch_step if ctx.fused else ctx.stretch_step_split
         if ctx.rng == "numpy-replay":
             # same draws, same order as the reference: global shuffle (red_blue.py:124), then per split
             # private randint / rand / rand (stretch.py:93, :131, red_blue.py:294)
@@ -39,15 +39,15 @@ class StretchMove(Move):
             if self.randomize_split:
                 [np.random.shuffle(x) for x in labels]
             lists = [ids[labels == s].reshape(T, -1) for s in range(2)]
+            rint, u_z, u_acc = [], [], []
             for split in range(2):
-                sub, comp = lists[split], lists[1 - split]
-                Ns, Nc = sub.shape[1], comp.shape[1]
-                rint = model.random.randint(Nc, size=(T, Ns))
-                u_z = model.random.rand(T, Ns)
-                u_acc = model.random.rand(T, Ns)
-                acc = step(d, split, self.a, replay=(sub, comp, rint, u_z, u_acc), accepted_count=cnt)
+                Ns, Nc = lists[split].shape[1], lists[1 - split].shape[1]
+                rint.append(model.random.randint(Nc, size=(T, Ns)))
+                u_z.append(model.random.rand(T, Ns))
+                u_acc.append(model.random.rand(T, Ns))
+            acc = step(d, self.a, replay=dict(lists=lists, rint=rint, u_z=u_z, u_acc=u_acc),
+                       accepted_count=cnt)
         else:
-            for split in range(2):
-                acc = step(d, split, self.a, randomize_split=self.randomize_split, accepted_count=cnt)
+            acc = step(d, self.a, randomize_split=self.randomize_split, accepted_count=cnt)
         self.num_proposals += 1
         return self._exit(ctx, d, host_state, acc)

@@ -35,6 +35,7 @@ extern "C" {
 #define EB_ABI_VERSION 1
 #define EB_MAX_TEMPS 256
 #define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
+#define EB_MAX_RANKS 16 /* GPUs of one temperature-sharded run */
 
 typedef enum {
   EB_OK = 0,
@@ -56,6 +57,10 @@ typedef enum {
 /* Walker state of one branch — state.py:387 (State) / :330 (Branch). */
 typedef struct {
   int32_t ntemps, nwalkers, nleaves, ndim;
+  int32_t temp_offset; /* index of local temperature 0 in the full ladder (temperature-sharded runs; else 0):
+                          the random streams are keyed by the GLOBAL temperature, so a sharded run
+                          reproduces the single-GPU chain */
+  int32_t _pad;
   double* coords;      /* [T][W][L][D] */
   double* logl;        /* [T][W]  State.log_like  */
   double* logp;        /* [T][W]  State.log_prior */
@@ -78,18 +83,22 @@ typedef struct {
   const double* params; /* device */
 } eb_like;
 
-/* Random inputs of one stretch half step.
- * replay: host NumPy draws in reference order (stretch.py:93, :131, red_blue.py:294) and the
- *         ascending walker-id lists of the split (red_blue.py:150-154).
- * philox: everything is generated in-kernel from (seed, *iter_dev, tags). */
+/* Random inputs of one StretchMove step (both red/blue halves).
+ * replay: the host NumPy draws in reference order.  `list[s]` holds the ascending walker ids of split s
+ *         after the label shuffle (red_blue.py:121-124, :150-154) and, per split, the three draws of
+ *         stretch.py:93 (rint), stretch.py:131 (u_z) and red_blue.py:294 (u_acc); everything is
+ *         [T][Ns_s] with Ns_0 = ceil(W/2), Ns_1 = floor(W/2).  The device composes them exactly as the
+ *         reference does: the k-th walker of split s is list[s][t][k] and its partner is
+ *         list[1-s][t][rint[s][t][k]] (stretch.py:100).
+ * philox: everything is generated in-kernel from (seed, *iter_dev, purpose tag, global temperature,
+ *         position in the split). */
 typedef struct {
   int32_t mode; /* eb_rng_mode */
-  int32_t randomize_split; /* red_blue.py:123 (philox mode; replay encodes it in sub_idx) */
-  const int32_t* sub_idx;  /* replay [T][Ns] walkers that move */
-  const int32_t* comp_idx; /* replay [T][Nc] complement walkers */
-  const int64_t* rint;     /* replay [T][Ns] */
-  const double* u_z;       /* replay [T][Ns] */
-  const double* u_acc;     /* replay [T][Ns] */
+  int32_t randomize_split; /* red_blue.py:123 (philox mode; replay encodes it in list) */
+  const int32_t* list[2];  /* replay [T][Ns_s] */
+  const int64_t* rint[2];  /* replay [T][Ns_s] */
+  const double* u_z[2];    /* replay [T][Ns_s] */
+  const double* u_acc[2];  /* replay [T][Ns_s]; may be NULL for eb_stretch_propose */
   uint64_t seed;           /* philox */
   const uint64_t* iter_dev; /* philox: device iteration counter (eb_ctrl.iter) or NULL */
   uint64_t iter;           /* philox: used when iter_dev == NULL */
@@ -147,7 +156,7 @@ EB_API const char* eb_last_error(void);
 EB_API int eb_device_count(void);
 EB_API size_t eb_ctrl_size(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 eb_state, 1 eb_prior, 2 eb_like,
- * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job */
+ * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job, 9 eb_shard */
 EB_API size_t eb_struct_size(int which);
 
 /* ---- probability evaluation:  EnsembleSampler.compute_log_prior (ensemble.py:1127) and
@@ -155,13 +164,14 @@ EB_API size_t eb_struct_size(int which);
  *      Walkers with logp = -inf are not evaluated and get -1e300 (ensemble.py:1279-1282,1486). */
 EB_API int eb_eval_state(const eb_state* st, const eb_prior* prior, const eb_like* like, void* stream);
 
-/* ---- StretchMove: one red/blue half step = red_blue.py:148-323 + stretch.py:74-231 +
- *      Move.update (move.py:472-703), fused.  `split` is 0 or 1.  `accepted` [T][W] uint8 gets
- *      the flags of the walkers that moved this half step; `accepted_count` (nullable,
+/* ---- StretchMove.propose without the tempering tail: BOTH red/blue half steps of
+ *      red_blue.py:148-323 + stretch.py:74-231 + Move.update (move.py:472-703), fused into one
+ *      launch (a thread-block cluster owns a temperature; a cluster barrier separates the halves;
+ *      shapes with too few temperatures for that fall back to one launch per half).
+ *      `accepted` [T][W] uint8 gets the accept flag of every walker; `accepted_count` (nullable,
  *      [T][W] uint32) is incremented (Move.accepted, move.py:404). */
-EB_API int eb_stretch_half_step(const eb_state* st, const eb_prior* prior, const eb_like* like, double a,
-                         int32_t split, const eb_stretch_rng* rng, uint8_t* accepted,
-                         uint32_t* accepted_count, void* stream);
+EB_API int eb_stretch_step(const eb_state* st, const eb_prior* prior, const eb_like* like, double a,
+                    const eb_stretch_rng* rng, uint8_t* accepted, uint32_t* accepted_count, void* stream);
 
 /* ---- GaussianMove: one Metropolis step over all walkers = mh.py:56-193 + gaussian.py:68-195. */
 EB_API int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* like,
@@ -175,6 +185,29 @@ EB_API int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_
 EB_API int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl,
                void* stream);
 
+/* ---- the same pass when the ladder is sharded over GPUs by temperature (one process per GPU; rank g
+ *      owns temperatures [temp_begin[g], temp_begin[g+1]) of all walkers).  The moves need
+ *      no communication (red_blue.py:183-197 gathers along the walker axis only).  For the swap pass the
+ *      caller all-gathers logl (NCCL); every rank then resolves the whole ladder redundantly from
+ *      `logl_all` — decisions depend on logl only (tempering.py:538), so all ranks agree bit for bit on
+ *      swap counts and on the adapted ladder — and writes ITS rungs into `dst` (its alternate buffers),
+ *      pulling each source row from the CURRENT buffers of the rank that owns it over NVLink
+ *      (`*_src[g]` are peer-mapped device pointers; entry `rank` is local).  The caller then flips
+ *      current/alternate.  The all-gather of the next pass orders those peer reads before the buffers are
+ *      overwritten again.  Philox mode only. */
+typedef struct {
+  int32_t rank, world;
+  int32_t ntemps_total;                   /* T of the full ladder */
+  int32_t temp_begin[EB_MAX_RANKS + 1];
+  const double* coords_src[EB_MAX_RANKS];  /* [T_g][W][L][D] current coords of rank g */
+  const double* logp_src[EB_MAX_RANKS];    /* [T_g][W] */
+  const uint8_t* inds_src[EB_MAX_RANKS];   /* [T_g][W][L] or NULL */
+  const double* logl_all;                  /* [T][W] local copy of every rank's logl */
+  double* betas_all;                       /* [T] local copy of the full ladder; adapted in place */
+} eb_shard;
+EB_API int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rng* rng,
+                       const eb_adapt* adapt, eb_ctrl* ctrl, void* stream);
+
 /* iteration counter tick for untempered runs (no swap pass) */
 EB_API int eb_advance_iter(eb_ctrl* ctrl, void* stream);
 
@@ -186,7 +219,7 @@ EB_API int eb_stretch_propose(const eb_state* st, double a, int32_t split, const
                        double* q, double* factors, int32_t* sub_out, void* stream);
 EB_API int eb_accept_update(const eb_state* st, const int32_t* sub, int32_t nsub, const double* q,
                      const double* factors, const double* logl_new, const double* logp_new,
-                     const double* u_acc, int32_t slot, const eb_stretch_rng* rng,
+                     int32_t split, const eb_stretch_rng* rng,
                      uint8_t* accepted, uint32_t* accepted_count, void* stream);
 /* box prior of proposed points q [T][Ns][L][D] -> logp_out [T][Ns] (ensemble.py:1192-1212) */
 EB_API int eb_box_log_prior(const double* q, const uint8_t* inds_sub, int32_t nrows, int32_t nleaves,

@@ -368,9 +368,10 @@ class PhiloxStreams:
         return [subs0, subs1]
 
     def stretch(self, it, split, T, Ns, Nc, sub):
-        rint, u_z = px.stretch_draws(it, self.seed, T, Ns, Nc, split)
-        W = None
-        return rint, u_z, None  # accept uniforms are keyed by walker id: see accept_for
+        # one Philox block per walker, keyed by (position in the split permutation, temperature)
+        pos = (2 * np.arange(Ns) + split)[None, :].repeat(T, axis=0)
+        t = np.arange(T)[:, None].repeat(Ns, axis=1)
+        return px.stretch_draws(it, self.seed, t, pos, Nc)
 
     def accept_for(self, it, slot, flat_walker):
         return px.accept_draws(it, self.seed, flat_walker, slot)
@@ -392,9 +393,12 @@ class PhiloxStreams:
 
     def swap_draws(self, it, T, W, permute=True):
         iperms, i1perms, us = [None] * T, [None] * T, [None] * T
+        # one keyed bijection sigma_r per rung; pair k of rung i is (i, sigma_i(k)) with (i-1, sigma_{i-1}(k)),
+        # i.e. iperm = sigma_i, i1perm = sigma_{i-1} in tempering.py:526-527; uniform k belongs to pair k
+        sig = [px.swap_perm(it, self.seed, r, W) if permute else np.arange(W) for r in range(T)]
         for i in range(T - 1, 0, -1):
-            iperms[i] = np.arange(W)
-            i1perms[i] = px.swap_perm(it, self.seed, i, W) if permute else np.arange(W)
+            iperms[i] = sig[i]
+            i1perms[i] = sig[i - 1]
             us[i] = px.swap_uniforms(it, self.seed, i, W)
         return iperms, i1perms, us
 

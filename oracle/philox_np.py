@@ -16,7 +16,7 @@ algorithmic use of each draw is identical in both modes and is restated in
 Contents
   philox4x32_10      Random123 / cuRAND Philox4x32-10 block function
   u01_52             two 32-bit words -> double in the open interval (0, 1)
-  feistel_perm       keyed bijection on [0, n) (6-round Feistel + cycle walk)
+  feistel_perm       keyed bijection on [0, n) (4-round Feistel + cycle walk)
   draw_*             the named streams (purpose tags) the kernels consume
 """
 import numpy as np
@@ -84,11 +84,13 @@ def _fmix32(h):
     return h
 
 
+FEISTEL_ROUNDS = 4
+
+
 def feistel_keys(tag, it, seed, idx):
-    """Six round keys for the bijection number `idx` of stream `tag` at iteration `it`."""
+    """Four round keys (one Philox block) for the bijection number `idx` of stream `tag` at iteration `it`."""
     w0, w1, w2, w3 = _stream(tag, it, seed, np.uint32(idx), np.uint32(0))
-    w0, w1, w2, w3 = [np.uint32(w) for w in (w0, w1, w2, w3)]
-    return [w0, w1, w2, w3, np.uint32(w0 ^ _W0), np.uint32(w1 ^ _W1)]
+    return [np.uint32(w) for w in (w0, w1, w2, w3)]
 
 
 def half_bits(n):
@@ -108,7 +110,7 @@ def feistel_perm(x, n, keys):
         v = x[todo]
         L = v >> hb
         R = v & mask
-        for r in range(6):
+        for r in range(FEISTEL_ROUNDS):
             L, R = R, L ^ (_fmix32(R ^ keys[r]) & mask)
         v = (L << hb) | R
         x[todo] = v
@@ -125,13 +127,29 @@ def split_perm(it, seed, t, W):
     return feistel_perm(np.arange(W, dtype=np.uint32), W, keys).astype(np.int64)
 
 
-def stretch_draws(it, seed, T, Ns, Nc, split):
-    """(rint, u_z) for subset ranks k<Ns of every temperature; counter (k, 2t+split)."""
-    k = np.arange(Ns, dtype=np.uint32)[None, :]
-    t = (np.arange(T, dtype=np.uint32) * np.uint32(2) + np.uint32(split))[:, None]
-    r0, r1, r2, r3 = _stream(TAG_STRETCH, it, seed, k, t)
-    rint = ((r0.astype(np.uint64) * np.uint64(Nc)) >> np.uint64(32)).astype(np.int64)
-    return rint, u01_52(r2, r3)
+def split_draw(lo, hi, n):
+    """(integer, fraction) of x*n/2^64 for the 64-bit uniform x = hi:lo — rng.cuh split_draw."""
+    lo = np.asarray(lo, dtype=np.uint64)
+    hi = np.asarray(hi, dtype=np.uint64)
+    n = int(n)
+    # x*n as a 96-bit product from 32-bit halves (uint64 arithmetic wraps, which is what we want for the low word)
+    with np.errstate(over="ignore"):
+        p_lo = lo * np.uint64(n)                      # < 2^64 (n < 2^32)
+        p_hi = hi * np.uint64(n)                      # weight 2^32
+        mid = (p_lo >> np.uint64(32)) + (p_hi & _MASK32)
+        ipart = (p_hi >> np.uint64(32)) + (mid >> np.uint64(32))
+        f = ((mid & _MASK32) << np.uint64(32)) | (p_lo & _MASK32)
+    frac = ((f >> np.uint64(12)).astype(np.float64) + 0.5) * (2.0 ** -52)
+    return ipart.astype(np.int64), frac
+
+
+def stretch_draws(it, seed, t_global, pos, Nc):
+    """(rint, u_z, u_acc) of the walkers at split positions `pos` of global temperature `t_global`;
+    one Philox block per walker, counter (pos, t_global)."""
+    r0, r1, r2, r3 = _stream(TAG_STRETCH, it, seed, np.asarray(pos, dtype=np.uint32),
+                             np.asarray(t_global, dtype=np.uint32))
+    rint, u_z = split_draw(r0, r1, Nc)
+    return rint, u_z, u01_52(r2, r3)
 
 
 def accept_draws(it, seed, flat_walker, slot):
@@ -162,5 +180,9 @@ def swap_perm(it, seed, rung, W):
 
 
 def swap_uniforms(it, seed, rung, W):
-    r0, r1, _, _ = _stream(TAG_SWAP_U, it, seed, np.arange(W, dtype=np.uint32), np.uint32(rung))
-    return u01_52(r0, r1)
+    """u of pair (chain) k at rung `rung`: one Philox block serves rungs r and r+8 of a chain
+    (k_swap.cu: lane r%8 owns rungs r, r+8, ...): counter (k, (r&7) | ((r>>4)<<3)), word pair (r>>3)&1."""
+    r = int(rung)
+    j = (r & 7) | ((r >> 4) << 3)
+    r0, r1, r2, r3 = _stream(TAG_SWAP_U, it, seed, np.arange(W, dtype=np.uint32), np.uint32(j))
+    return u01_52(r2, r3) if (r >> 3) & 1 else u01_52(r0, r1)
