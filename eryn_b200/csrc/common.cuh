@@ -38,6 +38,23 @@ int check_launch(const char* what);
 
 constexpr int BLOCK = 128;
 
+// Phase timers of the profiling build (-DEB_PHASE_TIMERS, tools/microbench.cu): CTA (0,0) thread 0 records the
+// SM cycle counter at named points; the production library compiles them away.
+#ifdef EB_PHASE_TIMERS
+static __device__ long long eb_dbg_marks[64];   // one copy per translation unit (no relocatable device code)
+#define EB_DEFINE_MARK_READER(NAME)                                                                   \
+  extern "C" __attribute__((visibility("default"))) int NAME(long long* out_host) {                  \
+    return cudaMemcpyFromSymbol(out_host, eb_dbg_marks, sizeof(long long) * 64) == cudaSuccess ? 0 : 3; \
+  }
+#define EB_MARK(i)                                                                     \
+  do {                                                                                 \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) eb_dbg_marks[i] = clock64(); \
+  } while (0)
+#else
+#define EB_MARK(i) do { } while (0)
+#define EB_DEFINE_MARK_READER(NAME)
+#endif
+
 struct Common {
   double* coords; double* logl; double* logp; uint8_t* inds; double* betas;
   int T, W, L, D, LD;

@@ -61,35 +61,58 @@ __device__ __forceinline__ void stretch_draw(const StretchArgs& p, const RngKey&
   }
 }
 
-template <int DMAX, int LIKE>
-__device__ __forceinline__ void stretch_walker(const StretchArgs& p, const double* sm, int t, int w, int wc, double u_z,
-                                               double u_acc) {
-  const Common& c = p.c;
-  const size_t slot = (size_t)t * c.W + w;
-  double q[DMAX], cc[DMAX];
-  load_row<DMAX>(c.coords + slot * c.LD, c.LD, q);                          // s  (red_blue.py:173-179)
-  load_row<DMAX>(c.coords + ((size_t)t * c.W + wc) * c.LD, c.LD, cc);       // c_temp (stretch.py:100)
-  const double ll0 = c.logl[slot], lp0 = c.logp[slot];
-  const bool active = c.inds ? (c.inds[slot] != 0) : true;
-  const bool tempered = c.betas != nullptr;
-  const double beta = tempered ? c.betas[t] : 1.0;
+// One proposal = two stages.  `prepare` does everything that does not depend on the other split: the draws,
+// the own row / logl / logp loads and both logarithms.  `finish` gathers the partner row (which, in half 1,
+// the other split may have just rewritten), evaluates and applies the Metropolis test.  The kernel prepares
+// BOTH halves of a thread up front, so that after the barrier between the halves only `finish` remains.
+template <int DMAX>
+struct WalkerJob {
+  double q[DMAX];      // own coordinates (s), then the proposal
+  double ll0, lp0, zz, factors, log_u;
+  int w, wc;
+  bool live, active;
+};
 
+template <int DMAX, bool PHILOX>
+__device__ __forceinline__ void job_prepare(const StretchArgs& p, const RngKey& key, const Feistel& sig, int t, int k,
+                                            int s, WalkerJob<DMAX>& j) {
+  const Common& c = p.c;
+  j.live = k < p.Ns[s];
+  if (!j.live) return;
+  double u_z, u_acc;
+  stretch_draw<PHILOX>(p, key, sig, t, k, s, j.w, j.wc, u_z, u_acc);
+  const size_t slot = (size_t)t * c.W + j.w;
+  load_row<DMAX>(c.coords + slot * c.LD, c.LD, j.q);                         // s  (red_blue.py:173-179)
+  j.ll0 = c.logl[slot];
+  j.lp0 = c.logp[slot];
+  j.active = c.inds ? (c.inds[slot] != 0) : true;
   double zz = (p.a - 1.0) * u_z + 1.0;                                       // stretch.py:129-132
   zz = zz * zz / p.a;
+  j.zz = zz;
+  j.factors = ((double)c.LD - 1.0) * log(zz);                                // stretch.py:223
+  j.log_u = log(u_acc);                                                      // red_blue.py:294
+}
+
+template <int DMAX, int LIKE>
+__device__ __forceinline__ void job_finish(const StretchArgs& p, const double* sm, int t, WalkerJob<DMAX>& j) {
+  if (!j.live) return;
+  const Common& c = p.c;
+  const size_t slot = (size_t)t * c.W + j.w;
+  double cc[DMAX];
+  load_row<DMAX>(c.coords + ((size_t)t * c.W + j.wc) * c.LD, c.LD, cc);     // c_temp (stretch.py:100)
+  const bool tempered = c.betas != nullptr;
+  const double beta = tempered ? c.betas[t] : 1.0;
 #pragma unroll
-  for (int j = 0; j < DMAX; ++j)
-    if (j < c.LD) q[j] = cc[j] - (cc[j] - q[j]) * zz;                        // stretch.py:143-145
-  const double factors = ((double)c.LD - 1.0) * log(zz);                     // stretch.py:223
-
+  for (int d = 0; d < DMAX; ++d)
+    if (d < c.LD) j.q[d] = cc[d] - (cc[d] - j.q[d]) * j.zz;                  // stretch.py:143-145
   double lp, ll;
-  eval_point<DMAX, LIKE>(q, c, sm, active, lp, ll);                          // red_blue.py:260,270
+  eval_point<DMAX, LIKE>(j.q, c, sm, j.active, lp, ll);                      // red_blue.py:260,270
   const double logP = log_posterior(ll, lp, beta, tempered);                 // red_blue.py:283
-  const double prevP = log_posterior(ll0, lp0, beta, tempered);              // red_blue.py:285-290
-  const double lnpdiff = factors + logP - prevP;                             // red_blue.py:292
-  const bool keep = lnpdiff > log(u_acc);                                    // red_blue.py:294
-
+  const double prevP = log_posterior(j.ll0, j.lp0, beta, tempered);          // red_blue.py:285-290
+  const double lnpdiff = j.factors + logP - prevP;                           // red_blue.py:292
+  const bool keep = lnpdiff > j.log_u;                                       // red_blue.py:294
   if (keep) {                                                                // move.py:472-703
-    store_row<DMAX>(c.coords + slot * c.LD, c.LD, q);
+    store_row<DMAX>(c.coords + slot * c.LD, c.LD, j.q);
     c.logl[slot] = ll;
     c.logp[slot] = isinf(lp) ? 0.0 : lp;                                     // move.py:526
     if (p.accepted_count) p.accepted_count[slot] += 1u;
@@ -99,32 +122,49 @@ __device__ __forceinline__ void stretch_walker(const StretchArgs& p, const doubl
 
 // grid = (cpt, T); with p.both the launch carries cluster dimension (cpt, 1, 1)
 template <int DMAX, int LIKE, bool PHILOX>
-__global__ void __launch_bounds__(STRETCH_THREADS) stretch_step_kernel(const StretchArgs p) {
+__global__ void __launch_bounds__(STRETCH_THREADS, DMAX <= 8 ? 2 : 1) stretch_step_kernel(const StretchArgs p) {
   extern __shared__ double sm[];
-  __shared__ uint32_t s_keys[FEISTEL_ROUNDS];
   const Common& c = p.c;
   const int t = blockIdx.y;
+  EB_MARK(0);
   RngKey key;
+  Feistel sig;
   if (PHILOX) {
     const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
     key = make_rng_key(p.seed_lo, p.seed_hi, it);
-    if (p.randomize && threadIdx.x == 0) Feistel::make_keys(key, TAG_SPLIT_KEY, (uint32_t)(c.t0 + t), s_keys);
+    // every thread derives the split bijection of its temperature itself: one more Philox block per
+    // thread, but no block barrier in front of the draws
+    if (p.randomize) sig.init(key, TAG_SPLIT_KEY, (uint32_t)(c.t0 + t), (uint32_t)c.W);
   }
-  stage_params(c, sm);  // ends with __syncthreads()
-  Feistel sig;
-  if (PHILOX && p.randomize) sig.init_from(s_keys, (uint32_t)c.W);
   const int stride = p.cpt * blockDim.x;
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
   const int s_first = p.both ? 0 : p.split, s_last = p.both ? 1 : p.split;
-  for (int s = s_first; s <= s_last; ++s) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < p.Ns[s]; k += stride) {
-      int w, wc;
-      double u_z, u_acc;
-      stretch_draw<PHILOX>(p, key, sig, t, k, s, w, wc, u_z, u_acc);
-      stretch_walker<DMAX, LIKE>(p, sm, t, w, wc, u_z, u_acc);
-    }
-    if (p.both && s == 0) {  // half 1 gathers what half 0 wrote, inside this temperature only
-      if (p.cpt > 1) cluster_barrier();
-      else __syncthreads();
+  constexpr bool PRE = DMAX <= 16;       // both jobs live in registers at once
+  WalkerJob<DMAX> ja, jb;
+  EB_MARK(1);
+  job_prepare<DMAX, PHILOX>(p, key, sig, t, k0, s_first, ja);
+  if (PRE && p.both) job_prepare<DMAX, PHILOX>(p, key, sig, t, k0, 1, jb);
+  EB_MARK(2);
+  stage_params(c, sm);  // ends with __syncthreads()
+  EB_MARK(3);
+  job_finish<DMAX, LIKE>(p, sm, t, ja);
+  EB_MARK(4);
+  for (int k = k0 + stride; k < p.Ns[s_first]; k += stride) {
+    job_prepare<DMAX, PHILOX>(p, key, sig, t, k, s_first, ja);
+    job_finish<DMAX, LIKE>(p, sm, t, ja);
+  }
+  if (s_last != s_first) {
+    if (!PRE) job_prepare<DMAX, PHILOX>(p, key, sig, t, k0, 1, jb);   // own row: not touched by half 0
+    // half 1 gathers what half 0 wrote, inside this temperature only
+    EB_MARK(5);
+    if (p.cpt > 1) cluster_barrier();
+    else __syncthreads();
+    EB_MARK(6);
+    job_finish<DMAX, LIKE>(p, sm, t, jb);
+    EB_MARK(7);
+    for (int k = k0 + stride; k < p.Ns[1]; k += stride) {
+      job_prepare<DMAX, PHILOX>(p, key, sig, t, k, 1, jb);
+      job_finish<DMAX, LIKE>(p, sm, t, jb);
     }
   }
 }
@@ -352,3 +392,5 @@ int eb_accept_update(const eb_state* st, const int32_t* sub, int32_t nsub, const
 }
 
 }  // extern "C"
+
+EB_DEFINE_MARK_READER(eb_debug_marks_stretch)

@@ -31,6 +31,7 @@ struct SwapArgs {
   int temp_begin[EB_MAX_RANKS + 1];
   const double* coords_src[EB_MAX_RANKS]; const double* logp_src[EB_MAX_RANKS]; const uint8_t* inds_src[EB_MAX_RANKS];
   int philox, permute, cpb;                       // cpb = chains per block
+  int spec;                                       // prefetch every row of the chain before the decisions (small, L2-resident states)
   const int32_t* next_pos; const double* u_at;  // replay pair map [T][W]
   uint32_t seed_lo, seed_hi; const unsigned long long* iter_dev; unsigned long long iter;
   eb_ctrl* ctrl;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
   const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
   const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
 
+  EB_MARK(16);
   // ---- phase 0: ladder and per-rung bijection keys, once per block ------------------------------
   for (int r = tid; r < T; r += blockDim.x) {
     s_betas[r] = p.betas[r];
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
   int* src = reinterpret_cast<int*>(smraw + lay.src) + (size_t)gg * T;
   uint8_t* sinds = smraw + lay.inds + (size_t)gg * T * L;
 
+  EB_MARK(17);
   // ---- phase 1: chain positions, logl and log(u) of the owned rungs ----------------------------
   if (!PHILOX) {
     if (valid && lane == 0) {            // replay: p_{i-1} = i1perm_i[iperm_i^{-1}[p_i]] (pt_pairmap_kernel)
@@ -135,6 +138,19 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
         pz = pos[r];
       }
       ll[r] = p.logl_in[(size_t)r * W + pz];
+      if (!SHARDED && p.spec) {          // the rows can start moving before the decisions are known
+        const size_t slot = (size_t)r * W + pz;
+        const double* grow = c.coords + slot * LD;
+        double* srow = rows + (size_t)r * RS;
+        if ((LD & 1) == 0) {
+          for (int e = 0; e < LD; e += 2) cp_async16(srow + e, grow + e);
+        } else {
+          for (int e = 0; e < LD; ++e) cp_async8(srow + e, grow + e);
+        }
+        cp_async8(srow + LD, c.logp + slot);
+        if (c.inds)
+          for (int l = 0; l < L; ++l) sinds[r * L + l] = c.inds[slot * L + l];
+      }
       double u;
       if (PHILOX) {                      // one Philox block serves two owned rungs (r and r + 8)
         if ((m & 1) == 0) q = stream(key, TAG_SWAP_U, (uint32_t)chain, (uint32_t)(lane + CHAIN_LANES * (m >> 1)));
@@ -147,6 +163,7 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
   }
   __syncwarp();
 
+  EB_MARK(18);
   // ---- phase 2: the cascade, hot -> cold (tempering.py:515-559 restricted to this chain) --------
   if (valid && lane == 0) {
     double carry = ll[T - 1];
@@ -167,15 +184,34 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
   }
   __syncwarp();
 
-  // ---- phase 3: move the rows that changed rung (do_swaps_indexing, tempering.py:351-482) ------
-  // swaps_accepted[r-1] counts src[r] == r-1 (:542): summed over the 4 chains of the warp by shuffles
+  EB_MARK(19);
+  // ---- swap counts: swaps_accepted[r-1] counts src[r] == r-1 (:542), summed over the 4 chains of the
+  //      warp by shuffles, over the block in shared memory, over the grid by atomics.  The ticket is taken
+  //      here, before the rows move, so that its round trip overlaps phase 3.
   for (int r0 = 0; r0 < T; r0 += CHAIN_LANES) {   // uniform trip count: the loop body shuffles
     const int r = r0 + lane;
-    int sel = 0;
-    if (valid && r < T) {
-      const int s = src[r];
-      sel = (r >= 1 && s == r - 1) ? 1 : 0;
-      if (!SHARDED && s != r) {
+    int sel = (valid && r >= 1 && r < T && src[r] == r - 1) ? 1 : 0;
+    sel += __shfl_xor_sync(0xffffffffu, sel, 8);
+    sel += __shfl_xor_sync(0xffffffffu, sel, 16);
+    if (sel && (tid & 31) < CHAIN_LANES) atomicAdd(&s_cnt[r - 1], sel);
+  }
+  __syncthreads();
+  eb_ctrl* ctrl = p.ctrl;
+  for (int r = tid; r < T - 1; r += blockDim.x)
+    if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[r], s_cnt[r]);
+  __threadfence();
+  __syncthreads();
+  unsigned int ticket = 0u;
+  if (tid == 0) ticket = atomicAdd(&ctrl->ticket, 1u);
+
+  EB_MARK(20);
+  // ---- phase 3: move the rows that changed rung (do_swaps_indexing, tempering.py:351-482) ------
+  if (!SHARDED) {
+    // staging row index: by source rung when prefetched (phase 1), by destination rung otherwise
+    if (!p.spec && valid) {
+      for (int r = lane; r < T; r += CHAIN_LANES) {
+        const int s = src[r];
+        if (s == r) continue;
         const size_t sslot = (size_t)s * W + pos[s];
         const double* grow = c.coords + sslot * LD;
         double* srow = rows + (size_t)r * RS;
@@ -189,20 +225,16 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
           for (int l = 0; l < L; ++l) sinds[r * L + l] = c.inds[sslot * L + l];
       }
     }
-    sel += __shfl_xor_sync(0xffffffffu, sel, 8);
-    sel += __shfl_xor_sync(0xffffffffu, sel, 16);
-    if (sel && (tid & 31) < CHAIN_LANES) atomicAdd(&s_cnt[r - 1], sel);
-  }
-  if (!SHARDED) {
     cp_async_wait_all();
     __syncwarp();                        // every lane has read its sources before any lane writes
     if (valid) {
       for (int r = lane; r < T; r += CHAIN_LANES) {
         const int s = src[r];
         if (s == r) continue;
+        const int st = p.spec ? s : r;
         const size_t dslot = (size_t)r * W + pos[r];
         double* grow = c.coords + dslot * LD;
-        const double* srow = rows + (size_t)r * RS;
+        const double* srow = rows + (size_t)st * RS;
         if ((LD & 1) == 0) {
           for (int e = 0; e < LD; e += 2) *reinterpret_cast<double2*>(grow + e) = *reinterpret_cast<const double2*>(srow + e);
         } else {
@@ -211,7 +243,7 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
         c.logp[dslot] = srow[LD];
         c.logl[dslot] = ll[s];
         if (c.inds)
-          for (int l = 0; l < L; ++l) c.inds[dslot * L + l] = sinds[r * L + l];
+          for (int l = 0; l < L; ++l) c.inds[dslot * L + l] = sinds[st * L + l];
       }
     }
   } else if (valid) {
@@ -236,18 +268,11 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
     }
   }
 
-  // ---- swap counts; the last block folds them and adapts the ladder ---------------------------
+  EB_MARK(21);
+  // ---- the block that drew the last ticket folds the counts and adapts the ladder -----------------
+  if (tid == 0) s_last = (ticket == gridDim.x - 1);
   __syncthreads();
-  eb_ctrl* ctrl = p.ctrl;
-  for (int r = tid; r < T - 1; r += blockDim.x)
-    if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[r], s_cnt[r]);
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int tk = atomicAdd(&ctrl->ticket, 1u);
-    s_last = (tk == gridDim.x - 1);
-  }
-  __syncthreads();
+  EB_MARK(22);
   if (!s_last) return;
   __threadfence();
   for (int r = tid; r < T - 1; r += blockDim.x) {
@@ -336,6 +361,7 @@ static int launch_swap(SwapArgs& args, cudaStream_t s) {
     return fail(EB_ERR_UNSUPPORTED, "swap pass: one chain of %d rungs x %d doubles does not fit shared memory", T,
                 args.c.LD);
   args.cpb = cpb;
+  args.spec = (!SHARDED && (size_t)T * W * (args.c.LD + 2) * sizeof(double) <= (size_t)48 << 20) ? 1 : 0;
   const int threads = max(32, cpb * CHAIN_LANES);
   const int grid = (W + cpb - 1) / cpb;
   int rc;
@@ -416,3 +442,5 @@ int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rn
 }
 
 }  // extern "C"
+
+EB_DEFINE_MARK_READER(eb_debug_marks_swap)
