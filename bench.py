@@ -192,7 +192,32 @@ def run_gpu(args):
     T, W, d = wl["T"], wl["W"], wl["d"]
     if world > 1:
         from eryn_b200.dist import run_sharded_bench
-        return run_sharded_bench(args, wl, rank, world, local)
+        wl["device_like"] = device_like(wl)
+        wl["x0"] = initial_coords(wl)
+        res = run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=ClockSampler, comm=args.comm)
+        if rank == 0:
+            peak, peak_src = measured_peak_gbs()
+            out = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                       ms_per_step=res["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                       dtype="f64", data="synthetic",
+                       config=dict(workload=wl["label"], ntemps=T, nwalkers=W, ndim=d, rng="philox",
+                                   parallelism=f"temperature-sharded x{world} (temp_begin={res['temp_begin']}), "
+                                               f"walkers grow with N (4096 per GPU-equivalent)",
+                                   comm=("NVLink peer stores + flag words, no NCCL on the data path" if res["comm"] == "p2p"
+                                         else "NCCL all_gather of logl + NVLink peer row pulls"),
+                                   l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
+                                   step="one iteration = move kernel + publish kernel + sharded swap/adapt kernel"
+                                        + (" (CUDA graph replay)" if res["graph"] else "")),
+                       clocks=res["clocks"], e2e=dict(unit=UNIT, **res["e2e"]), gpu_launches=res["launches"],
+                       roofline=None, cpu_baseline=None,
+                       extra=dict(ms_per_step_resident_no_flush=res["resident_ms"],
+                                  value_resident_no_flush=T * W / (res["resident_ms"] * 1e-3),
+                                  betas_cold_hot=res["betas"], swaps_accepted_last=res["swaps"],
+                                  timing="per-step CUDA events on each rank, summed, MAX over ranks"))
+            print(json.dumps(out))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     dev = torch.device("cuda", local)
     pri = ProbDistContainer({i: uniform_dist(wl["lo"], wl["hi"]) for i in range(d)})
@@ -367,6 +392,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="multi-GPU logl exchange (N > 1)")
     ap.add_argument("--profile", action="store_true", help="shorten the CPU-baseline leg (for runs under ncu)")
     a = ap.parse_args()
     if a.warmup < 3:

@@ -13,6 +13,8 @@ EB_MAX_ROW = 32
 EB_MAX_RANKS = 16
 EB_RNG_REPLAY, EB_RNG_PHILOX = 0, 1
 EB_LIKE_GAUSSIAN, EB_LIKE_ROSENBROCK, EB_LIKE_GMIX = 0, 1, 2
+EB_IPC_HANDLE_BYTES = 64
+EB_DEVERR_PEER_TIMEOUT = 1
 
 _STATUS = {1: "EB_ERR_INVALID", 2: "EB_ERR_UNSUPPORTED", 3: "EB_ERR_CUDA", 4: "EB_ERR_NODEVICE"}
 
@@ -51,7 +53,7 @@ class eb_swap_rng(C.Structure):
 
 
 class eb_ctrl(C.Structure):
-    _fields_ = [("iter", C.c_uint64), ("time", C.c_int64), ("ticket", C.c_uint32), ("_pad", C.c_uint32),
+    _fields_ = [("iter", C.c_uint64), ("time", C.c_int64), ("ticket", C.c_uint32), ("error", C.c_uint32),
                 ("swaps_work", C.c_int32 * EB_MAX_TEMPS), ("swaps_accepted", C.c_int32 * EB_MAX_TEMPS),
                 ("swaps_total", C.c_uint64 * EB_MAX_TEMPS)]
 
@@ -76,7 +78,13 @@ class eb_shard(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ntemps_total", C.c_int32),
                 ("temp_begin", C.c_int32 * (EB_MAX_RANKS + 1)),
                 ("coords_src", vp * EB_MAX_RANKS), ("logp_src", vp * EB_MAX_RANKS), ("inds_src", vp * EB_MAX_RANKS),
-                ("logl_all", vp), ("betas_all", vp)]
+                ("logl_all", vp), ("betas_all", vp), ("flags", vp)]
+
+
+class eb_publish(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ntemps_total", C.c_int32), ("nwalkers", C.c_int32),
+                ("temp_begin", C.c_int32 * (EB_MAX_RANKS + 1)),
+                ("logl_local", vp), ("logl_all_peer", vp * EB_MAX_RANKS), ("flags_peer", vp * EB_MAX_RANKS)]
 
 
 # every symbol include/eryn_b200.h declares: name -> (restype, argtypes)
@@ -92,6 +100,12 @@ SYMBOLS = {
     "eb_gaussian_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), P(eb_gauss_rng), vp, vp, vp]),
     "eb_pt_swap": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_pt_swap_sharded": (C.c_int, [P(eb_shard), P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
+    "eb_publish_logl": (C.c_int, [P(eb_publish), vp, vp]),
+    "eb_dev_malloc": (C.c_int, [C.c_size_t, P(vp)]),
+    "eb_dev_free": (C.c_int, [vp]),
+    "eb_ipc_export": (C.c_int, [vp, vp]),
+    "eb_ipc_open": (C.c_int, [vp, P(vp)]),
+    "eb_ipc_close": (C.c_int, [vp]),
     "eb_advance_iter": (C.c_int, [vp, vp]),
     "eb_stretch_propose": (C.c_int, [P(eb_state), C.c_double, C.c_int32, P(eb_stretch_rng), vp, vp, vp, vp]),
     "eb_accept_update": (C.c_int, [P(eb_state), vp, C.c_int32, vp, vp, vp, vp, C.c_int32, P(eb_stretch_rng),
@@ -101,7 +115,7 @@ SYMBOLS = {
 }
 
 STRUCTS = [eb_state, eb_prior, eb_like, eb_stretch_rng, eb_gauss_rng, eb_swap_rng, eb_ctrl, eb_adapt, eb_host_job,
-           eb_shard]
+           eb_shard, eb_publish]
 
 _lib = None
 

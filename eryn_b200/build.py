@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "liberyn_b200.so")
-SOURCES = ["abi_core.cu", "k_stretch.cu", "k_gauss.cu", "k_swap.cu", "host_job.cu"]
+SOURCES = ["abi_core.cu", "k_stretch.cu", "k_gauss.cu", "k_swap.cu", "k_shard.cu", "host_job.cu"]
 HEADERS = ["common.cuh", "likelihoods.cuh", "rng.cuh", os.path.join("..", "..", "include", "eryn_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false",

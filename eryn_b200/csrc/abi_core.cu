@@ -133,6 +133,7 @@ size_t eb_struct_size(int which) {
     case 7: return sizeof(eb_adapt);
     case 8: return sizeof(eb_host_job);
     case 9: return sizeof(eb_shard);
+    case 10: return sizeof(eb_publish);
     default: return 0;
   }
 }

@@ -30,6 +30,7 @@ struct SwapArgs {
   int sharded, world, t_lo, t_hi;
   int temp_begin[EB_MAX_RANKS + 1];
   const double* coords_src[EB_MAX_RANKS]; const double* logp_src[EB_MAX_RANKS]; const uint8_t* inds_src[EB_MAX_RANKS];
+  const unsigned long long* flags;                // sharded: local flag words raised by every rank's publish kernel
   int philox, permute, cpb;                       // cpb = chains per block
   int spec;                                       // prefetch every row of the chain before the decisions (small, L2-resident states)
   const int32_t* next_pos; const double* u_at;  // replay pair map [T][W]
@@ -93,6 +94,30 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
   const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
 
   EB_MARK(16);
+  if (SHARDED && p.flags) {
+    // every rank's logl rows of THIS iteration must have landed in logl_in (eb_publish_logl): bounded spin on
+    // the local flag words, one thread per CTA
+    __shared__ bool s_ok;
+    if (tid == 0) {
+      bool ok = *reinterpret_cast<volatile unsigned int*>(&p.ctrl->error) == 0u;
+      const unsigned long long target = p.ctrl->iter + 1ull;
+      unsigned long long t_start;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+      for (int gr = 0; ok && gr < p.world; ++gr) {
+        const volatile unsigned long long* f = p.flags + gr;
+        while (*f < target) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (now - t_start > EB_PEER_TIMEOUT_NS) { ok = false; break; }
+        }
+      }
+      if (!ok) atomicExch(&p.ctrl->error, EB_DEVERR_PEER_TIMEOUT);
+      __threadfence_system();
+      s_ok = ok;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+  }
   // ---- phase 0: ladder and per-rung bijection keys, once per block ------------------------------
   for (int r = tid; r < T; r += blockDim.x) {
     s_betas[r] = p.betas[r];
@@ -437,6 +462,7 @@ int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rn
   if (dst->ntemps != args.t_hi - args.t_lo || dst->temp_offset != args.t_lo)
     return fail(EB_ERR_INVALID, "destination state must hold this rank's temperatures [%d, %d)", args.t_lo, args.t_hi);
   args.T = T; args.logl_in = sh->logl_all; args.betas = sh->betas_all;
+  args.flags = (const unsigned long long*)sh->flags;
   if (T < 2) return eb_advance_iter(ctrl, stream);
   return launch_swap<true>(args, (cudaStream_t)stream);
 }

@@ -47,6 +47,9 @@ typedef enum {
 
 typedef enum { EB_RNG_REPLAY = 0, EB_RNG_PHILOX = 1 } eb_rng_mode;
 
+#define EB_DEVERR_PEER_TIMEOUT 1u /* eb_ctrl.error: a peer's flag did not arrive within EB_PEER_TIMEOUT_NS */
+#define EB_PEER_TIMEOUT_NS 2000000000ull
+
 /* device-side log-likelihood functors (SURVEY.md §8d synthetic targets) */
 typedef enum {
   EB_LIKE_GAUSSIAN = 0,   /* params: mu[D], P[D*D]           logL = -1/2 (x-mu)^T P (x-mu)          */
@@ -137,7 +140,7 @@ typedef struct {
   uint64_t iter;                        /* incremented by eb_pt_swap (or eb_advance_iter) */
   int64_t time;                         /* TemperatureControl.time */
   uint32_t ticket;                      /* last-block election */
-  uint32_t _pad;
+  uint32_t error;                       /* 0, or EB_DEVERR_* set by a kernel (e.g. a peer never signalled) */
   int32_t swaps_work[EB_MAX_TEMPS];     /* scratch, zero between passes */
   int32_t swaps_accepted[EB_MAX_TEMPS]; /* result of the last pass, entry i-1 = rung i */
   uint64_t swaps_total[EB_MAX_TEMPS];   /* running sum */
@@ -156,7 +159,8 @@ EB_API const char* eb_last_error(void);
 EB_API int eb_device_count(void);
 EB_API size_t eb_ctrl_size(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 eb_state, 1 eb_prior, 2 eb_like,
- * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job, 9 eb_shard */
+ * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job, 9 eb_shard,
+ * 10 eb_publish */
 EB_API size_t eb_struct_size(int which);
 
 /* ---- probability evaluation:  EnsembleSampler.compute_log_prior (ensemble.py:1127) and
@@ -187,14 +191,18 @@ EB_API int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt
 
 /* ---- the same pass when the ladder is sharded over GPUs by temperature (one process per GPU; rank g
  *      owns temperatures [temp_begin[g], temp_begin[g+1]) of all walkers).  The moves need
- *      no communication (red_blue.py:183-197 gathers along the walker axis only).  For the swap pass the
- *      caller all-gathers logl (NCCL); every rank then resolves the whole ladder redundantly from
- *      `logl_all` — decisions depend on logl only (tempering.py:538), so all ranks agree bit for bit on
- *      swap counts and on the adapted ladder — and writes ITS rungs into `dst` (its alternate buffers),
- *      pulling each source row from the CURRENT buffers of the rank that owns it over NVLink
- *      (`*_src[g]` are peer-mapped device pointers; entry `rank` is local).  The caller then flips
- *      current/alternate.  The all-gather of the next pass orders those peer reads before the buffers are
- *      overwritten again.  Philox mode only. */
+ *      no communication (red_blue.py:183-197 gathers along the walker axis only).  One iteration is
+ *        move kernel (local)  ->  eb_publish_logl  ->  eb_pt_swap_sharded  ->  flip current/alternate
+ *      eb_publish_logl is the all-gather of logl written as peer stores: every rank copies its rows into
+ *      the `logl_all` buffer of EVERY rank over NVLink and then raises its flag word (value iter+1) on
+ *      every rank.  eb_pt_swap_sharded first waits (bounded spin on LOCAL memory) until all flag words
+ *      reached iter+1, then resolves the whole ladder redundantly from `logl_all` — decisions depend on
+ *      logl only (tempering.py:538), so all ranks agree bit for bit on swap counts and on the adapted
+ *      ladder — and writes ITS rungs into `dst` (its alternate buffers), pulling each source row from the
+ *      CURRENT buffers of the rank that owns it (`*_src[g]` are peer-mapped device pointers; entry `rank`
+ *      is local).  The caller then flips current/alternate AND the logl_all parity buffer: a rank may run
+ *      one publish ahead of a slow peer, never two (its next swap waits for that peer's next flag).
+ *      Philox mode only. */
 typedef struct {
   int32_t rank, world;
   int32_t ntemps_total;                   /* T of the full ladder */
@@ -202,11 +210,33 @@ typedef struct {
   const double* coords_src[EB_MAX_RANKS];  /* [T_g][W][L][D] current coords of rank g */
   const double* logp_src[EB_MAX_RANKS];    /* [T_g][W] */
   const uint8_t* inds_src[EB_MAX_RANKS];   /* [T_g][W][L] or NULL */
-  const double* logl_all;                  /* [T][W] local copy of every rank's logl */
+  const double* logl_all;                  /* [T][W] local copy of every rank's logl (this parity) */
   double* betas_all;                       /* [T] local copy of the full ladder; adapted in place */
+  const uint64_t* flags;                   /* [EB_MAX_RANKS] local flag words (NULL: caller ordered the ranks itself,
+                                              e.g. with an NCCL all-gather of logl) */
 } eb_shard;
 EB_API int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rng* rng,
                        const eb_adapt* adapt, eb_ctrl* ctrl, void* stream);
+
+typedef struct {
+  int32_t rank, world;
+  int32_t ntemps_total, nwalkers;
+  int32_t temp_begin[EB_MAX_RANKS + 1];
+  const double* logl_local;               /* [T_rank][W] */
+  double* logl_all_peer[EB_MAX_RANKS];    /* peer-mapped logl_all (this parity) of every rank; entry `rank` local */
+  uint64_t* flags_peer[EB_MAX_RANKS];     /* peer-mapped flag arrays of every rank */
+} eb_publish;
+EB_API int eb_publish_logl(const eb_publish* pub, eb_ctrl* ctrl, void* stream);
+
+/* device memory that can be shared between the processes of one box (cudaMalloc + CUDA IPC):
+ * the handle is the 64-byte cudaIpcMemHandle_t; eb_ipc_open maps a peer's allocation (peer access is
+ * enabled lazily by the driver) and eb_ipc_close unmaps it. */
+#define EB_IPC_HANDLE_BYTES 64
+EB_API int eb_dev_malloc(size_t bytes, void** out);
+EB_API int eb_dev_free(void* p);
+EB_API int eb_ipc_export(const void* dev_ptr, uint8_t* handle64);
+EB_API int eb_ipc_open(const uint8_t* handle64, void** out);
+EB_API int eb_ipc_close(void* p);
 
 /* iteration counter tick for untempered runs (no swap pass) */
 EB_API int eb_advance_iter(eb_ctrl* ctrl, void* stream);

@@ -269,6 +269,15 @@ def temperature_swaps(state, betas, iperms, i1perms, us):
     return swaps_accepted
 
 
+def resolve_ladder(logl, betas, iperms, i1perms, us):
+    """The swap pass needs logl only (tempering.py:538): run it on slot ids.  Returns (src [T,W] flat slot
+    t*W+w whose walker ends at each slot, swaps_accepted [T-1])."""
+    T, W = logl.shape
+    ids = OState(np.arange(T * W, dtype=np.float64).reshape(T, W, 1, 1), logl=logl, logp=np.zeros((T, W)))
+    sw = temperature_swaps(ids, betas, iperms, i1perms, us)
+    return ids.coords[:, :, 0, 0].astype(np.int64), sw
+
+
 def adapt_temps(betas, swaps_accepted, nwalkers, time, adaptation_lag=10000, adaptation_time=100):
     """tempering.py:563-596: returns the new ladder (betas0 + (new - betas0), as the reference)."""
     ratios = swaps_accepted / np.full(len(swaps_accepted), nwalkers)  # :587, :282
@@ -349,9 +358,10 @@ class PhiloxStreams:
 
     mode = "philox"
 
-    def __init__(self, seed, schedule_random=None):
+    def __init__(self, seed, schedule_random=None, t0=0):
         self.seed = int(seed)
         self.sched = schedule_random if schedule_random is not None else np.random.RandomState(self.seed & 0x7FFFFFFF)
+        self.t0 = int(t0)  # global index of local temperature 0 (temperature-sharded runs key the streams globally)
 
     def move_choice(self, it, weights):
         return int(self.sched.choice(len(weights), p=weights))  # host-side schedule, as the reference
@@ -362,7 +372,7 @@ class PhiloxStreams:
         subs0 = np.empty((T, n0), dtype=np.int64)
         subs1 = np.empty((T, n1), dtype=np.int64)
         for t in range(T):
-            sig = px.split_perm(it, self.seed, t, W)
+            sig = px.split_perm(it, self.seed, self.t0 + t, W)
             subs0[t] = sig[0::2][:n0]
             subs1[t] = sig[1::2][:n1]
         return [subs0, subs1]
@@ -370,7 +380,7 @@ class PhiloxStreams:
     def stretch(self, it, split, T, Ns, Nc, sub):
         # one Philox block per walker, keyed by (position in the split permutation, temperature)
         pos = (2 * np.arange(Ns) + split)[None, :].repeat(T, axis=0)
-        t = np.arange(T)[:, None].repeat(Ns, axis=1)
+        t = self.t0 + np.arange(T)[:, None].repeat(Ns, axis=1)
         return px.stretch_draws(it, self.seed, t, pos, Nc)
 
     def accept_for(self, it, slot, flat_walker):
@@ -378,7 +388,7 @@ class PhiloxStreams:
 
     def gauss_increment(self, it, inds, D, proposal):
         T, W, L = inds.shape
-        flat = np.arange(T * W * L, dtype=np.uint32)
+        flat = np.arange(T * W * L, dtype=np.uint32) + np.uint32(self.t0 * W * L)
         z = px.gauss_draws(it, self.seed, flat, D)
         if proposal["kind"] == "scalar":
             d = proposal["scale"] * z
@@ -389,7 +399,8 @@ class PhiloxStreams:
         return delta
 
     def accept_uniforms(self, it, slot, T, W):
-        return px.accept_draws(it, self.seed, np.arange(T * W, dtype=np.uint32), slot).reshape(T, W)
+        flat = np.arange(T * W, dtype=np.uint32) + np.uint32(self.t0 * W)
+        return px.accept_draws(it, self.seed, flat, slot).reshape(T, W)
 
     def swap_draws(self, it, T, W, permute=True):
         iperms, i1perms, us = [None] * T, [None] * T, [None] * T

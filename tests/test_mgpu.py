@@ -1,0 +1,72 @@
+"""2-GPU parity of the temperature-sharded run (run with `gpurun --gpus 2 -- python -m pytest tests/test_mgpu.py -m gpu`).
+
+The sharded run (one process per GPU, NVLink peer stores + flags) must reproduce the unsharded
+oracle chain: swap counts / accept counts bit-equal, floats to 1e-10 relative."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import eryn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle(T, W, d, nit, seed, mix):
+    A = np.random.RandomState(99).randn(d, d)
+    like = orc.GaussianLike(np.zeros(d), np.linalg.inv(A @ A.T / d + np.eye(d)))
+    prior = orc.BoxPrior(np.full(d, -10.0), np.full(d, 10.0))
+    moves = [dict(kind="stretch", a=2.0), dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.1))]
+    weights = [0.5, 0.5] if mix else [1.0, 0.0]
+    sched = np.random.RandomState(7)
+
+    class Sched:  # the worker draws choice(2, p=[.5,.5]) only when mixing
+        def choice(self, n, p):
+            return sched.choice(n, p=[0.5, 0.5]) if mix else 0
+
+    smp = orc.OracleSampler(prior, like, moves, weights, orc.PhiloxStreams(seed, schedule_random=Sched()),
+                            betas=orc.make_ladder_default(d, T))
+    st = smp.initialise(orc.OState(np.random.RandomState(1).uniform(-3, 3, size=(T, W, 1, d))))
+    acc = np.zeros((T, W))
+    for _ in range(nit):
+        acc += smp.iterate(st)
+    return smp, st, acc
+
+
+@pytest.mark.parametrize("comm,T,W,mix", [("p2p", 4, 256, 0), ("nccl", 4, 256, 0), ("p2p", 5, 99, 1), ("p2p", 16, 4096, 0)])
+def test_sharded_run_matches_unsharded_oracle(tmp_path, comm, T, W, mix):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    d, nit, seed = 8, 6, 4242
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--out",
+           str(tmp_path), "--comm", comm, "--T", str(T), "--W", str(W), "--d", str(d), "--nit", str(nit), "--seed",
+           str(seed), "--mix", str(mix)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    got = np.load(tmp_path / f"mgpu_{comm}.npz")
+    smp, st, acc = _oracle(T, W, d, nit, seed, mix)
+    np.testing.assert_allclose(got["coords"], st.coords, rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(got["logl"], st.logl, rtol=1e-10)
+    np.testing.assert_allclose(got["logp"], st.logp, rtol=1e-10)
+    np.testing.assert_allclose(got["betas"], smp.betas, rtol=1e-10)
+    assert np.array_equal(got["swaps"], smp.swaps_accepted)
+    assert np.array_equal(got["accepted"], acc)
+    assert int(got["time"]) == nit
