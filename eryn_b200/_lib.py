@@ -8,9 +8,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "liberyn_b200.so")
 
-EB_MAX_TEMPS = 256
+EB_MAX_TEMPS = 128
 EB_MAX_ROW = 32
 EB_MAX_RANKS = 16
+EB_SWAP_SLOTS = 32
 EB_RNG_REPLAY, EB_RNG_PHILOX = 0, 1
 EB_LIKE_GAUSSIAN, EB_LIKE_ROSENBROCK, EB_LIKE_GMIX = 0, 1, 2
 EB_IPC_HANDLE_BYTES = 64
@@ -37,7 +38,7 @@ class eb_like(C.Structure):
 
 
 class eb_stretch_rng(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("randomize_split", C.c_int32),
+    _fields_ = [("mode", C.c_int32), ("randomize_split", C.c_int32), ("pdl_chain", C.c_int32), ("_pad", C.c_int32),
                 ("list", vp * 2), ("rint", vp * 2), ("u_z", vp * 2), ("u_acc", vp * 2),
                 ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
 
@@ -49,13 +50,15 @@ class eb_gauss_rng(C.Structure):
 
 class eb_swap_rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("permute", C.c_int32), ("iperm", vp), ("i1perm", vp), ("u", vp),
-                ("next_pos", vp), ("u_at", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+                ("next_pos", vp), ("u_at", vp), ("row_scratch", vp), ("logp_scratch", vp), ("inds_scratch", vp),
+                ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
 
 
 class eb_ctrl(C.Structure):
     _fields_ = [("iter", C.c_uint64), ("time", C.c_int64), ("ticket", C.c_uint32), ("error", C.c_uint32),
-                ("swaps_work", C.c_int32 * EB_MAX_TEMPS), ("swaps_accepted", C.c_int32 * EB_MAX_TEMPS),
-                ("swaps_total", C.c_uint64 * EB_MAX_TEMPS)]
+                ("swaps_work", (C.c_int32 * EB_MAX_TEMPS) * EB_SWAP_SLOTS), ("swaps_accepted", C.c_int32 * EB_MAX_TEMPS),
+                ("swaps_total", C.c_uint64 * EB_MAX_TEMPS), ("arrive", C.c_uint32 * EB_SWAP_SLOTS),
+                ("iter_next", C.c_uint64)]
 
 
 class eb_adapt(C.Structure):
@@ -138,7 +141,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.eb_abi_version() != 1:
+    if lib.eb_abi_version() != 2:
         raise ErynB200Error("liberyn_b200.so ABI version mismatch; rebuild")
     for i, st in enumerate(STRUCTS):
         if lib.eb_struct_size(i) != C.sizeof(st):

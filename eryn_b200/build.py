@@ -17,7 +17,13 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "liberyn_b200.so")
-SOURCES = ["abi_core.cu", "k_stretch.cu", "k_gauss.cu", "k_swap.cu", "k_shard.cu", "host_job.cu"]
+# (source, extra defines, object name): the two move kernels are compiled once per likelihood kind so the template
+# instantiations build in parallel
+SOURCES = [("abi_core.cu", [], "abi_core.o"), ("k_swap.cu", [], "k_swap.o"), ("k_shard.cu", [], "k_shard.o"),
+           ("host_job.cu", [], "host_job.o")]
+for _k in range(3):
+    SOURCES.append(("k_stretch.cu", [f"-DEB_ONLY_LIKE={_k}"], f"k_stretch_{_k}.o"))
+    SOURCES.append(("k_gauss.cu", [f"-DEB_ONLY_LIKE={_k}"], f"k_gauss_{_k}.o"))
 HEADERS = ["common.cuh", "likelihoods.cuh", "rng.cuh", os.path.join("..", "..", "include", "eryn_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false",
@@ -34,10 +40,11 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS:
+    for f in sorted({x[0] for x in SOURCES}) + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(SOURCES).encode())
     return h.hexdigest()
 
 
@@ -50,15 +57,16 @@ def build(force=False, verbose=True):
         return LIB
     nvcc = _nvcc()
 
-    def compile_one(src):
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(item):
+        src, defs, objname = item
+        obj = os.path.join(OBJDIR, objname)
+        cmd = [nvcc] + NVCC_FLAGS + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+            raise RuntimeError(f"nvcc failed on {src} {defs}:\n{r.stdout}\n{r.stderr}")
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(BLOCK) eval_state_kernel(const Common c) {
   load_row<DMAX>(c.coords + (size_t)tid * c.LD, c.LD, x);
   const bool active = c.inds ? (c.inds[tid] != 0) : true;
   double lp, ll;
-  eval_point<DMAX, LIKE>(x, c, sm, active, lp, ll);
+  eval_point<DMAX, LIKE, false>(x, c, sm, active, lp, ll);
   c.logp[tid] = lp;
   c.logl[tid] = ll;
 }
@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(BLOCK) box_prior_kernel(const double* __restri
   out[r] = tot;
 }
 
-__global__ void advance_iter_kernel(eb_ctrl* ctrl) { ctrl->iter += 1ull; }
+__global__ void advance_iter_kernel(eb_ctrl* ctrl) {
+  ctrl->iter += 1ull;
+  ctrl->iter_next = ctrl->iter;
+}
 
 int fill_common(Common& c, const eb_state* st, const eb_prior* prior, const eb_like* like, bool need_fused) {
   if (!st) return fail(EB_ERR_INVALID, "state is NULL");
@@ -76,7 +79,8 @@ int fill_common(Common& c, const eb_state* st, const eb_prior* prior, const eb_l
   c.t0 = st->temp_offset;
   c.lo = c.hi = c.lpdf = nullptr; c.like_params = nullptr; c.like_nparams = 0; c.like_ncomp = 0;
   if (prior) { c.lo = prior->lo; c.hi = prior->hi; c.lpdf = prior->logpdf; }
-  if (like) { c.like_params = like->params; c.like_nparams = like->nparams; c.like_ncomp = like->ncomp; }
+  c.like_kind = -1;
+  if (like) { c.like_params = like->params; c.like_nparams = like->nparams; c.like_ncomp = like->ncomp; c.like_kind = like->kind; }
   if (need_fused) {
     if (!prior || !prior->lo || !prior->hi || !prior->logpdf) return fail(EB_ERR_INVALID, "prior is required");
     if (!like) return fail(EB_ERR_INVALID, "likelihood functor is required");
@@ -150,12 +154,12 @@ int eb_eval_state(const eb_state* st, const eb_prior* prior, const eb_like* like
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
 #define L2_(K) rc = launch_eval<DM_, K>(c, s)
-#define L1_(DM)                              \
+#define L1_(DM, EX)                          \
   {                                          \
     constexpr int DM_ = DM;                  \
     EB_DISPATCH_LIKE(like->kind, L2_)        \
   }
-  EB_DISPATCH_DMAX(c.LD, L1_)
+  EB_DISPATCH_DMAX_GENERIC(c.LD, L1_)
 #undef L1_
 #undef L2_
   if (rc) return rc;

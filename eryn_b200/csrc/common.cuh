@@ -41,18 +41,37 @@ constexpr int BLOCK = 128;
 // Phase timers of the profiling build (-DEB_PHASE_TIMERS, tools/microbench.cu): CTA (0,0) thread 0 records the
 // SM cycle counter at named points; the production library compiles them away.
 #ifdef EB_PHASE_TIMERS
+#define EB_DBG_SKIP(bit) ((p.dbg_skip & (bit)) != 0)   // profiling build: switch phases off to time the rest
 static __device__ long long eb_dbg_marks[64];   // one copy per translation unit (no relocatable device code)
 #define EB_DEFINE_MARK_READER(NAME)                                                                   \
   extern "C" __attribute__((visibility("default"))) int NAME(long long* out_host) {                  \
     return cudaMemcpyFromSymbol(out_host, eb_dbg_marks, sizeof(long long) * 64) == cudaSuccess ? 0 : 3; \
+  }                                                                                                   \
+  extern "C" __attribute__((visibility("default"))) int NAME##_global(unsigned long long* mn, unsigned long long* mx, int reset) { \
+    if (reset) {                                                                                      \
+      unsigned long long big[64], zero[64];                                                           \
+      for (int i = 0; i < 64; ++i) { big[i] = ~0ull; zero[i] = 0ull; }                                \
+      cudaMemcpyToSymbol(eb_dbg_gmin, big, sizeof(big));                                              \
+      cudaMemcpyToSymbol(eb_dbg_gmax, zero, sizeof(zero));                                            \
+      return 0;                                                                                       \
+    }                                                                                                 \
+    cudaMemcpyFromSymbol(mn, eb_dbg_gmin, sizeof(unsigned long long) * 64);                           \
+    return cudaMemcpyFromSymbol(mx, eb_dbg_gmax, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : 3; \
   }
+static __device__ unsigned long long eb_dbg_gmin[64], eb_dbg_gmax[64];   // globaltimer (ns) spread over all CTAs
 #define EB_MARK(i)                                                                     \
   do {                                                                                 \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) eb_dbg_marks[i] = clock64(); \
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {  \
+      unsigned long long gt_;                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                          \
+      if (blockIdx.x == 0) { eb_dbg_gmin[i] = gt_; eb_dbg_marks[i] = clock64(); }      \
+      if (blockIdx.x == gridDim.x - 1) eb_dbg_gmax[i] = gt_;                           \
+    }                                                                                  \
   } while (0)
 #else
 #define EB_MARK(i) do { } while (0)
 #define EB_DEFINE_MARK_READER(NAME)
+#define EB_DBG_SKIP(bit) false
 #endif
 
 struct Common {
@@ -60,29 +79,75 @@ struct Common {
   int T, W, L, D, LD;
   int t0;  // global index of local temperature 0 (random-stream keying)
   const double* lo; const double* hi; const double* lpdf;
-  const double* like_params; int like_nparams, like_ncomp;
+  const double* like_params; int like_nparams, like_ncomp, like_kind;
 };
 
-// stage [lo D][hi D][lpdf D][like params] into shared memory
-__device__ __forceinline__ void stage_params(const Common& c, double* sm) {
-  const int D = c.D;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    sm[i] = c.lo[i]; sm[D + i] = c.hi[i]; sm[2 * D + i] = c.lpdf[i];
+// stage [lo D][hi D][lpdf D][like params] into shared memory.  The Gaussian functor's precision matrix is staged as
+// the packed upper triangle S_ii = P_ii, S_ij = P_ij + P_ji (x^T P x needs D(D+1)/2 products instead of D^2).
+// Two steps so that the global-load latency hides behind other work: `stage_load` issues the loads of this thread's
+// (first) element into registers, `stage_store` writes them to shared memory and copies whatever exceeds one element
+// per thread; the caller synchronises the block afterwards.
+struct Staged { double lo, hi, lpdf, p0, p1, p2; };
+
+__device__ __forceinline__ void stage_store_gauss(double* sp, int D, int e, double pij, double pji) {
+  const int i = e / D, j = e - i * D;
+  if (j == i) sp[D + sym_row_offset(i, D)] = pij;
+  else if (j > i) sp[D + sym_row_offset(i, D) + (j - i)] = pij + pji;
+}
+
+__device__ __forceinline__ void stage_load(const Common& c, Staged& r) {
+  const int D = c.D, tid = threadIdx.x;
+  if (tid < D) { r.lo = c.lo[tid]; r.hi = c.hi[tid]; r.lpdf = c.lpdf[tid]; }
+  if (c.like_kind == EB_LIKE_GAUSSIAN) {
+    if (tid < D) r.p0 = c.like_params[tid];
+    if (tid < D * D) {
+      const int i = tid / D, j = tid - i * D;
+      const double* P = c.like_params + D;
+      r.p1 = P[tid];
+      r.p2 = (j > i) ? P[j * D + i] : 0.0;
+    }
+  } else if (tid < c.like_nparams) {
+    r.p0 = c.like_params[tid];
   }
-  for (int i = threadIdx.x; i < c.like_nparams; i += blockDim.x) sm[3 * D + i] = c.like_params[i];
+}
+
+__device__ __forceinline__ void stage_store(const Common& c, const Staged& r, double* sm) {
+  const int D = c.D, tid = threadIdx.x, nt = blockDim.x;
+  if (tid < D) { sm[tid] = r.lo; sm[D + tid] = r.hi; sm[2 * D + tid] = r.lpdf; }
+  for (int i = tid + nt; i < D; i += nt) { sm[i] = c.lo[i]; sm[D + i] = c.hi[i]; sm[2 * D + i] = c.lpdf[i]; }
+  double* sp = sm + 3 * D;
+  if (c.like_kind == EB_LIKE_GAUSSIAN) {
+    const double* P = c.like_params + D;
+    if (tid < D) sp[tid] = r.p0;
+    for (int i = tid + nt; i < D; i += nt) sp[i] = c.like_params[i];
+    if (tid < D * D) stage_store_gauss(sp, D, tid, r.p1, r.p2);
+    for (int e = tid + nt; e < D * D; e += nt) {
+      const int i = e / D, j = e - i * D;
+      stage_store_gauss(sp, D, e, P[e], P[j * D + i]);
+    }
+  } else {
+    if (tid < c.like_nparams) sp[tid] = r.p0;
+    for (int i = tid + nt; i < c.like_nparams; i += nt) sp[i] = c.like_params[i];
+  }
+}
+
+__device__ __forceinline__ void stage_params(const Common& c, double* sm) {
+  Staged r;
+  stage_load(c, r);
+  stage_store(c, r, sm);
   __syncthreads();
 }
 
 // log-prior (single leaf, L == 1) and gated log-like of a proposed point
-template <int DMAX, int LIKE>
+template <int DMAX, int LIKE, bool EXACT>
 __device__ __forceinline__ void eval_point(const double (&q)[DMAX], const Common& c, const double* sm, bool leaf_active,
                                            double& lp, double& ll) {
-  const int D = c.D;
-  lp = leaf_active ? box_logpdf_leaf<DMAX>(q, 0, D, sm, sm + D, sm + 2 * D) : 0.0;
+  const int D = EXACT ? DMAX : c.D;
+  lp = leaf_active ? box_logpdf_leaf<DMAX, EXACT>(q, D, sm, sm + D, sm + 2 * D) : 0.0;
   if (isinf(lp) || !leaf_active) {
     ll = FILL_LOGL;  // ensemble.py:1279-1282, :1486 / fill_zero_leaves_val :1499
   } else {
-    ll = Like<LIKE>::template eval<DMAX>(q, D, sm + 3 * D, c.like_ncomp);
+    ll = Like<LIKE>::template eval<DMAX, EXACT>(q, D, sm + 3 * D, c.like_ncomp);
     if (ll != ll) ll = FILL_LOGL;  // red_blue.py:279-281
   }
 }
@@ -104,12 +169,26 @@ static int set_smem(K kernel, size_t bytes) {
   return EB_OK;
 }
 
-#define EB_DISPATCH_DMAX(LD, MACRO)          \
-  switch (bucket(LD)) {                      \
-    case 8: MACRO(8); break;                 \
-    case 16: MACRO(16); break;               \
-    case 24: MACRO(24); break;               \
-    default: MACRO(32); break;               \
+// MACRO(DMAX, EXACT): exact-length kernels for the BASELINE row lengths (8, 20), padded buckets otherwise
+#define EB_DISPATCH_DMAX(LD, MACRO)              \
+  switch (LD) {                                  \
+    case 8: MACRO(8, true); break;               \
+    case 20: MACRO(20, true); break;             \
+    default:                                     \
+      switch (bucket(LD)) {                      \
+        case 8: MACRO(8, false); break;          \
+        case 16: MACRO(16, false); break;        \
+        case 24: MACRO(24, false); break;        \
+        default: MACRO(32, false); break;        \
+      }                                          \
+  }
+// padded buckets only (kernels off the hot path)
+#define EB_DISPATCH_DMAX_GENERIC(LD, MACRO)      \
+  switch (bucket(LD)) {                          \
+    case 8: MACRO(8, false); break;              \
+    case 16: MACRO(16, false); break;            \
+    case 24: MACRO(24, false); break;            \
+    default: MACRO(32, false); break;            \
   }
 #define EB_DISPATCH_LIKE(KIND, MACRO2)       \
   switch (KIND) {                            \

@@ -31,7 +31,7 @@ struct Pool {
 };
 
 struct HostCtx {
-  Pool coords, logl, logp, betas, prior, like, acc, acc_cnt, ctrl;
+  Pool coords, logl, logp, betas, prior, like, acc, acc_cnt, ctrl, row_scratch, logp_scratch;
   cudaStream_t stream = nullptr;
   std::mutex mu;
 };
@@ -63,7 +63,8 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   const size_t bc = n * L * D * sizeof(double), bs = n * sizeof(double);
   if (cx.coords.ensure(bc) || cx.logl.ensure(bs) || cx.logp.ensure(bs) || cx.betas.ensure(T * sizeof(double)) ||
       cx.prior.ensure(3 * D * sizeof(double)) || cx.like.ensure((job->like_nparams + 1) * sizeof(double)) ||
-      cx.acc.ensure(n) || cx.acc_cnt.ensure(n * sizeof(uint32_t)) || cx.ctrl.ensure(sizeof(eb_ctrl)))
+      cx.acc.ensure(n) || cx.acc_cnt.ensure(n * sizeof(uint32_t)) || cx.ctrl.ensure(sizeof(eb_ctrl)) ||
+      (T > 64 && (cx.row_scratch.ensure(bc) || cx.logp_scratch.ensure(bs))))
     return EB_ERR_CUDA;
 
   // ---- host -> device -------------------------------------------------------------------------
@@ -86,6 +87,7 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   eb_ctrl hc;
   std::memset(&hc, 0, sizeof(hc));
   hc.iter = job->iter0;
+  hc.iter_next = job->iter0;
   hc.time = job->adapt_time0;
   HJ_CUDA(cudaMemcpyAsync(cx.ctrl.p, &hc, sizeof(hc), cudaMemcpyHostToDevice, s));
   HJ_CUDA(cudaMemsetAsync(cx.acc_cnt.p, 0, n * sizeof(uint32_t), s));
@@ -101,7 +103,8 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   eb_stretch_rng srng;
   std::memset(&srng, 0, sizeof(srng));
   srng.mode = EB_RNG_PHILOX; srng.randomize_split = job->randomize_split; srng.seed = job->seed;
-  srng.iter_dev = &dctrl->iter;
+  srng.iter_dev = &dctrl->iter_next;   // published early by the swap pass: the next move may start its draws
+  srng.pdl_chain = 1;
   eb_gauss_rng grng;
   std::memset(&grng, 0, sizeof(grng));
   grng.mode = EB_RNG_PHILOX; grng.cov_kind = 0; grng.scale = job->gauss_scale; grng.seed = job->seed;
@@ -109,6 +112,7 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   eb_swap_rng wrng;
   std::memset(&wrng, 0, sizeof(wrng));
   wrng.mode = EB_RNG_PHILOX; wrng.permute = job->permute; wrng.seed = job->seed; wrng.iter_dev = &dctrl->iter;
+  if (T > 64) { wrng.row_scratch = (double*)cx.row_scratch.p; wrng.logp_scratch = (double*)cx.logp_scratch.p; }
   for (int it = 0; it < niter; ++it) {
     const int mv = job->move_schedule_host ? job->move_schedule_host[it] : 0;
     int rc;

@@ -14,12 +14,12 @@ struct GaussArgs {
   uint8_t* accepted; uint32_t* accepted_count;
 };
 
-template <int DMAX, int LIKE, bool PHILOX>
+template <int DMAX, int LIKE, bool PHILOX, bool EXACT>
 __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const Common& c = p.c;
   stage_params(c, sm);
-  const int D = c.D;
+  const int D = EXACT ? DMAX : c.D;
   double* s_chol = sm + 3 * D + c.like_nparams;
   if (PHILOX && p.cov_kind == 1) {
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) s_chol[i] = p.chol[i];
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
   if (tid >= c.T * c.W) return;
   const int t = tid / c.W;
   double q[DMAX];
-  load_row<DMAX>(c.coords + (size_t)tid * c.LD, c.LD, q);
+  load_row<DMAX>(c.coords + (size_t)tid * D, D, q);
   const bool active = c.inds ? (c.inds[tid] != 0) : true;
   double u_acc;
   if (PHILOX) {
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
     double z[DMAX];
 #pragma unroll
     for (int j = 0; j < DMAX; j += 2) {
-      if (j < D) {
+      if (EXACT || j < D) {
         const uint4 r = stream(key, TAG_GAUSS, (uint32_t)(tid + c.t0 * c.W), (uint32_t)(j >> 1));
         const double rad = sqrt(-2.0 * log(u01_52(r.x, r.y)));
         double sn, cs;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
       if (p.cov_kind == 0) {
 #pragma unroll
         for (int j = 0; j < DMAX; ++j)
-          if (j < D) q[j] = q[j] + p.scale * z[j];                          // gaussian.py:166-167
+          if (EXACT || j < D) q[j] = q[j] + p.scale * z[j];                          // gaussian.py:166-167
       } else {
 #pragma unroll
         for (int i = 0; i < DMAX; ++i)
@@ -69,11 +69,11 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
     const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)(tid + c.t0 * c.W), 0u);
     u_acc = u01_52(ra.x, ra.y);
   } else {
-    const double* dl = p.delta + (size_t)tid * c.LD;
+    const double* dl = p.delta + (size_t)tid * D;
     if (active) {
 #pragma unroll
       for (int j = 0; j < DMAX; ++j)
-        if (j < D) q[j] = q[j] + dl[j];
+        if (EXACT || j < D) q[j] = q[j] + dl[j];
     }
     u_acc = p.u_acc[tid];
   }
@@ -81,12 +81,12 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
   const bool tempered = c.betas != nullptr;
   const double beta = tempered ? c.betas[t] : 1.0;
   double lp, ll;
-  eval_point<DMAX, LIKE>(q, c, sm, active, lp, ll);                          // mh.py:134-148
+  eval_point<DMAX, LIKE, EXACT>(q, c, sm, active, lp, ll);                          // mh.py:134-148
   const double logP = log_posterior(ll, lp, beta, tempered);
   const double prevP = log_posterior(ll0, lp0, beta, tempered);
   const bool keep = (0.0 + logP - prevP) > log(u_acc);                       // mh.py:168-171
   if (keep) {
-    store_row<DMAX>(c.coords + (size_t)tid * c.LD, c.LD, q);
+    store_row<DMAX>(c.coords + (size_t)tid * D, D, q);
     c.logl[tid] = ll;
     c.logp[tid] = isinf(lp) ? 0.0 : lp;
   }
@@ -94,24 +94,51 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
   if (p.accepted_count && keep) p.accepted_count[tid] += 1u;
 }
 
-template <int DMAX, int LIKE>
+template <int DMAX, int LIKE, bool EXACT>
 static int launch_gauss(const GaussArgs& a, cudaStream_t s) {
   const int n = a.c.T * a.c.W;
   const size_t sb = smem_bytes(a.c, a.c.D * a.c.D);
   if (a.philox) {
-    int rc = set_smem(gaussian_step_kernel<DMAX, LIKE, true>, sb);
+    int rc = set_smem(gaussian_step_kernel<DMAX, LIKE, true, EXACT>, sb);
     if (rc) return rc;
-    gaussian_step_kernel<DMAX, LIKE, true><<<(n + BLOCK - 1) / BLOCK, BLOCK, sb, s>>>(a);
+    gaussian_step_kernel<DMAX, LIKE, true, EXACT><<<(n + BLOCK - 1) / BLOCK, BLOCK, sb, s>>>(a);
   } else {
-    int rc = set_smem(gaussian_step_kernel<DMAX, LIKE, false>, sb);
+    int rc = set_smem(gaussian_step_kernel<DMAX, LIKE, false, EXACT>, sb);
     if (rc) return rc;
-    gaussian_step_kernel<DMAX, LIKE, false><<<(n + BLOCK - 1) / BLOCK, BLOCK, sb, s>>>(a);
+    gaussian_step_kernel<DMAX, LIKE, false, EXACT><<<(n + BLOCK - 1) / BLOCK, BLOCK, sb, s>>>(a);
   }
   return EB_OK;
 }
 
+// one object file per likelihood kind (build.py compiles this source with -DEB_ONLY_LIKE=k)
+template <int LIKE>
+int launch_gauss_like(const GaussArgs& a, cudaStream_t s);
+#ifndef EB_ONLY_LIKE
+#define EB_ONLY_LIKE -1
+#endif
+#define EB_GAUSS_LIKE_DEF(K)                                      \
+  template <>                                                     \
+  int launch_gauss_like<K>(const GaussArgs& a, cudaStream_t s) {  \
+    int rc = EB_OK;                                               \
+    EB_DISPATCH_DMAX(a.c.LD, EB_GAUSS_L1_##K)                     \
+    return rc;                                                    \
+  }
+#define EB_GAUSS_L1_0(DM, EX) rc = launch_gauss<DM, 0, EX>(a, s)
+#define EB_GAUSS_L1_1(DM, EX) rc = launch_gauss<DM, 1, EX>(a, s)
+#define EB_GAUSS_L1_2(DM, EX) rc = launch_gauss<DM, 2, EX>(a, s)
+#if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 0
+EB_GAUSS_LIKE_DEF(0)
+#endif
+#if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 1
+EB_GAUSS_LIKE_DEF(1)
+#endif
+#if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 2
+EB_GAUSS_LIKE_DEF(2)
+#endif
+
 }  // namespace eb
 
+#if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 0
 using namespace eb;
 
 extern "C" {
@@ -137,17 +164,14 @@ int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* l
     return fail(EB_ERR_INVALID, "unknown rng mode %d", rng->mode);
   }
   cudaStream_t s = (cudaStream_t)stream;
-#define L2_(K) rc = launch_gauss<DM_, K>(args, s)
-#define L1_(DM)                              \
-  {                                          \
-    constexpr int DM_ = DM;                  \
-    EB_DISPATCH_LIKE(like->kind, L2_)        \
+  switch (like->kind) {
+    case 0: rc = launch_gauss_like<0>(args, s); break;
+    case 1: rc = launch_gauss_like<1>(args, s); break;
+    default: rc = launch_gauss_like<2>(args, s); break;
   }
-  EB_DISPATCH_DMAX(args.c.LD, L1_)
-#undef L1_
-#undef L2_
   if (rc) return rc;
   return check_launch("gaussian_step");
 }
 
 }  // extern "C"
+#endif  // EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 0

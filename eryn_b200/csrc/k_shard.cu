@@ -15,9 +15,15 @@ struct PublishArgs {
   eb_ctrl* ctrl;
 };
 
-// K5: every CTA copies a contiguous slice of the local logl rows into the logl_all buffer of every rank
-// (16-byte peer stores, coalesced), fences at system scope, and the last CTA to finish raises this rank's flag
-// word (value iter+1) in every rank's flag array.
+__host__ __device__ inline int publish_grid(size_t ndoubles) {
+  size_t g = (ndoubles / 2 + 255) / 256;
+  return g < 1 ? 1 : g > 148 ? 148 : (int)g;
+}
+
+// K5: every CTA copies a contiguous slice of the local logl rows into the logl_all buffer of every rank (16-byte peer
+// stores, coalesced); after a block barrier its thread 0 issues one system-scope release fence and ADDS 1 to this
+// rank's flag word on every rank (NVLink atomics).  A flag word therefore counts publishing CTAs: a reader of iteration
+// `it` waits for (it + 1) * publish_grid(rows of that rank).  No ticket, no last-block election, no host.
 __global__ void __launch_bounds__(256) publish_logl_kernel(const PublishArgs p) {
   const size_t n = (size_t)p.nrows * p.W;                   // doubles to publish
   const size_t off = (size_t)p.t_lo * p.W;
@@ -39,20 +45,11 @@ __global__ void __launch_bounds__(256) publish_logl_kernel(const PublishArgs p) 
       for (int g = 0; g < p.world; ++g) p.logl_all_peer[g][off + i] = v;
     }
   }
-  __threadfence_system();
   __syncthreads();
-  __shared__ bool last;
-  if (threadIdx.x == 0) last = (atomicAdd(&p.ctrl->ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!last) return;
-  __threadfence_system();
   if (threadIdx.x < p.world) {
-    const unsigned long long v = p.ctrl->iter + 1ull;
-    volatile unsigned long long* f = p.flags_peer[threadIdx.x] + p.rank;
-    *f = v;
-    __threadfence_system();
+    asm volatile("fence.acq_rel.sys;" ::: "memory");   // cumulative over the block's stores (ordered by the barrier)
+    atomicAdd_system(p.flags_peer[threadIdx.x] + p.rank, 1ull);
   }
-  if (threadIdx.x == 0) p.ctrl->ticket = 0u;
 }
 
 }  // namespace eb
@@ -82,10 +79,8 @@ int eb_publish_logl(const eb_publish* pub, eb_ctrl* ctrl, void* stream) {
   }
   a.logl_local = pub->logl_local;
   a.ctrl = ctrl;
-  const size_t n = (size_t)a.nrows * a.W;
-  int grid = (int)((n / 2 + 255) / 256);
-  if (grid < 1) grid = 1;
-  if (grid > 148) grid = 148;
+  if (a.world > 256) return fail(EB_ERR_INVALID, "world too large");
+  const int grid = publish_grid((size_t)a.nrows * a.W);
   publish_logl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("publish_logl");
 }

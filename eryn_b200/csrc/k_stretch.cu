@@ -1,6 +1,8 @@
 // Part of eryn_b200 (kernel overview in common.cuh). Built with --fmad=false.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eb {
@@ -20,9 +22,9 @@ struct StretchArgs {
   Common c;
   double a;
   int philox, randomize;
-  int both;        // 1: both halves in this launch (cluster barrier in between); 0: only `split`
+  int both;        // 1: both halves in this launch (one CTA per temperature); 0: only `split`
   int split;
-  int cpt;         // CTAs per temperature (= cluster size when both == 1)
+  int pdl;         // this launch carries the programmatic-stream-serialization attribute
   int Ns[2];
   // replay
   const int32_t* list[2]; const long long* rint[2]; const double* u_z[2]; const double* u_acc[2];
@@ -33,11 +35,7 @@ struct StretchArgs {
   double* q_out; double* factors_out; int32_t* sub_out;
 };
 
-constexpr int STRETCH_THREADS = 256;
-
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+constexpr int STRETCH_HALF_THREADS = 256;   // threads per CTA of a per-half launch
 
 // The k-th walker of split s at local temperature t: its id, its partner and the two uniforms.
 template <bool PHILOX>
@@ -61,114 +59,137 @@ __device__ __forceinline__ void stretch_draw(const StretchArgs& p, const RngKey&
   }
 }
 
-// One proposal = two stages.  `prepare` does everything that does not depend on the other split: the draws,
-// the own row / logl / logp loads and both logarithms.  `finish` gathers the partner row (which, in half 1,
-// the other split may have just rewritten), evaluates and applies the Metropolis test.  The kernel prepares
-// BOTH halves of a thread up front, so that after the barrier between the halves only `finish` remains.
+// One proposal = three stages.  `draw`: the random draws and both logarithms — no state is read, so it can run
+// before the previous kernel has finished (programmatic dependent launch).  `load_own`: the walker's own row, logl,
+// logp.  `finish`: gather the partner row, evaluate, Metropolis test, in-place update.
 template <int DMAX>
 struct WalkerJob {
   double q[DMAX];      // own coordinates (s), then the proposal
-  double ll0, lp0, zz, factors, log_u;
+  double ll0, lp0, zz, factors, log_u, beta;
   int w, wc;
   bool live, active;
 };
 
-template <int DMAX, bool PHILOX>
-__device__ __forceinline__ void job_prepare(const StretchArgs& p, const RngKey& key, const Feistel& sig, int t, int k,
-                                            int s, WalkerJob<DMAX>& j) {
-  const Common& c = p.c;
+template <int DMAX, bool PHILOX, bool EXACT>
+__device__ __forceinline__ void job_draw(const StretchArgs& p, const RngKey& key, const Feistel& sig, int t, int k,
+                                         int s, WalkerJob<DMAX>& j) {
+  const int LD = EXACT ? DMAX : p.c.LD;
   j.live = k < p.Ns[s];
   if (!j.live) return;
   double u_z, u_acc;
   stretch_draw<PHILOX>(p, key, sig, t, k, s, j.w, j.wc, u_z, u_acc);
-  const size_t slot = (size_t)t * c.W + j.w;
-  load_row<DMAX>(c.coords + slot * c.LD, c.LD, j.q);                         // s  (red_blue.py:173-179)
-  j.ll0 = c.logl[slot];
-  j.lp0 = c.logp[slot];
-  j.active = c.inds ? (c.inds[slot] != 0) : true;
   double zz = (p.a - 1.0) * u_z + 1.0;                                       // stretch.py:129-132
   zz = zz * zz / p.a;
   j.zz = zz;
-  j.factors = ((double)c.LD - 1.0) * log(zz);                                // stretch.py:223
+  j.factors = ((double)LD - 1.0) * log(zz);                                  // stretch.py:223
   j.log_u = log(u_acc);                                                      // red_blue.py:294
 }
 
-template <int DMAX, int LIKE>
+template <int DMAX, bool EXACT>
+__device__ __forceinline__ void job_load_own(const StretchArgs& p, int t, WalkerJob<DMAX>& j) {
+  if (!j.live) return;
+  const Common& c = p.c;
+  const int LD = EXACT ? DMAX : c.LD;
+  const size_t slot = (size_t)t * c.W + j.w;
+  load_row<DMAX>(c.coords + slot * LD, LD, j.q);                             // s  (red_blue.py:173-179)
+  j.ll0 = c.logl[slot];
+  j.lp0 = c.logp[slot];
+  j.active = c.inds ? (c.inds[slot] != 0) : true;
+}
+
+template <int DMAX, int LIKE, bool EXACT>
 __device__ __forceinline__ void job_finish(const StretchArgs& p, const double* sm, int t, WalkerJob<DMAX>& j) {
   if (!j.live) return;
   const Common& c = p.c;
+  const int LD = EXACT ? DMAX : c.LD;
   const size_t slot = (size_t)t * c.W + j.w;
   double cc[DMAX];
-  load_row<DMAX>(c.coords + ((size_t)t * c.W + j.wc) * c.LD, c.LD, cc);     // c_temp (stretch.py:100)
+  load_row<DMAX>(c.coords + ((size_t)t * c.W + j.wc) * LD, LD, cc);          // c_temp (stretch.py:100)
   const bool tempered = c.betas != nullptr;
-  const double beta = tempered ? c.betas[t] : 1.0;
 #pragma unroll
   for (int d = 0; d < DMAX; ++d)
-    if (d < c.LD) j.q[d] = cc[d] - (cc[d] - j.q[d]) * j.zz;                  // stretch.py:143-145
+    if (EXACT || d < LD) j.q[d] = cc[d] - (cc[d] - j.q[d]) * j.zz;           // stretch.py:143-145
   double lp, ll;
-  eval_point<DMAX, LIKE>(j.q, c, sm, j.active, lp, ll);                      // red_blue.py:260,270
-  const double logP = log_posterior(ll, lp, beta, tempered);                 // red_blue.py:283
-  const double prevP = log_posterior(j.ll0, j.lp0, beta, tempered);          // red_blue.py:285-290
+  eval_point<DMAX, LIKE, EXACT>(j.q, c, sm, j.active, lp, ll);               // red_blue.py:260,270
+  const double logP = log_posterior(ll, lp, j.beta, tempered);               // red_blue.py:283
+  const double prevP = log_posterior(j.ll0, j.lp0, j.beta, tempered);        // red_blue.py:285-290
   const double lnpdiff = j.factors + logP - prevP;                           // red_blue.py:292
   const bool keep = lnpdiff > j.log_u;                                       // red_blue.py:294
   if (keep) {                                                                // move.py:472-703
-    store_row<DMAX>(c.coords + slot * c.LD, c.LD, j.q);
+    store_row<DMAX>(c.coords + slot * LD, LD, j.q);
     c.logl[slot] = ll;
-    c.logp[slot] = isinf(lp) ? 0.0 : lp;                                     // move.py:526
+    c.logp[slot] = isinf(lp) ? 0.0 : lp;
     if (p.accepted_count) p.accepted_count[slot] += 1u;
   }
   p.accepted[slot] = keep ? 1 : 0;
 }
 
-// grid = (cpt, T); with p.both the launch carries cluster dimension (cpt, 1, 1)
-template <int DMAX, int LIKE, bool PHILOX>
-__global__ void __launch_bounds__(STRETCH_THREADS, DMAX <= 8 ? 2 : 1) stretch_step_kernel(const StretchArgs p) {
-  extern __shared__ double sm[];
+// programmatic dependent launch (PDL): the next kernel in the stream may start its state-independent prologue once
+// every CTA of this grid has executed launch_dependents; it blocks in grid_dependency_wait until this grid has
+// completed and its writes are visible.  Both are no-ops for launches without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Per-half launch (!p.both): grid = (ceil(Ns[split] / blockDim), T), every thread owns one walker of `split`; half 1
+// is launched as a programmatic dependent of half 0, so its draws overlap half 0 and only its `finish` waits.
+// Small ensembles (p.both: Ns[0] <= blockDim/2, grid = (1, T)): both halves in one CTA per temperature, the first
+// half of the threads owns split 0, the second half split 1, a block barrier in between.
+template <int DMAX, int LIKE, bool PHILOX, bool EXACT>
+__global__ void __launch_bounds__(STRETCH_HALF_THREADS, 2) stretch_step_kernel(const StretchArgs p) {
+  extern __shared__ __align__(16) double sm[];
   const Common& c = p.c;
   const int t = blockIdx.y;
   EB_MARK(0);
+  unsigned long long it = p.iter;
+  if (PHILOX && p.iter_dev) it = *reinterpret_cast<const volatile unsigned long long*>(p.iter_dev);
+  // half 1 lets the swap pass start its own prologue right away; half 0 releases half 1 only after its wait, so that
+  // half 1 never runs ahead of the kernel BEFORE half 0 (it loads its own rows before waiting)
+  if (!p.both && p.split == 1) pdl_launch_dependents();
+  Staged staged;
+  stage_load(c, staged);                // constant parameters: global loads in flight while the draws are computed
   RngKey key;
   Feistel sig;
   if (PHILOX) {
-    const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
     key = make_rng_key(p.seed_lo, p.seed_hi, it);
     // every thread derives the split bijection of its temperature itself: one more Philox block per
     // thread, but no block barrier in front of the draws
     if (p.randomize) sig.init(key, TAG_SPLIT_KEY, (uint32_t)(c.t0 + t), (uint32_t)c.W);
   }
-  const int stride = p.cpt * blockDim.x;
-  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
-  const int s_first = p.both ? 0 : p.split, s_last = p.both ? 1 : p.split;
-  constexpr bool PRE = DMAX <= 16;       // both jobs live in registers at once
-  WalkerJob<DMAX> ja, jb;
+  int s, k;
+  if (p.both) {
+    const int ht = blockDim.x >> 1;
+    s = threadIdx.x >= ht ? 1 : 0;
+    k = threadIdx.x - s * ht;
+  } else {
+    s = p.split;
+    k = blockIdx.x * blockDim.x + threadIdx.x;
+  }
+  WalkerJob<DMAX> job;
   EB_MARK(1);
-  job_prepare<DMAX, PHILOX>(p, key, sig, t, k0, s_first, ja);
-  if (PRE && p.both) job_prepare<DMAX, PHILOX>(p, key, sig, t, k0, 1, jb);
+  job_draw<DMAX, PHILOX, EXACT>(p, key, sig, t, k, s, job);
+  job.beta = 1.0;
   EB_MARK(2);
-  stage_params(c, sm);  // ends with __syncthreads()
+  const bool own_early = !p.both && s == 1;   // split-1 rows are not touched by half 0
+  if (own_early) job_load_own<DMAX, EXACT>(p, t, job);
+  pdl_wait();
+  if (p.both || s == 0) pdl_launch_dependents();
+  if (!own_early) job_load_own<DMAX, EXACT>(p, t, job);
+  if (c.betas) job.beta = c.betas[t];         // adapted by the swap pass: read after the wait
+  stage_store(c, staged, sm);
+  __syncthreads();                            // staged parameters visible
   EB_MARK(3);
-  job_finish<DMAX, LIKE>(p, sm, t, ja);
+  // Half 1 gathers what half 0 wrote, inside this temperature only.  In a fused CTA the split-1 warps arrive at the
+  // barrier first and wait there for the split-0 warps, which arrive after their `finish`.
+  const bool wait_first = p.both && s == 1;
+  if (wait_first) asm volatile("barrier.sync.aligned 0;" ::: "memory");
   EB_MARK(4);
-  for (int k = k0 + stride; k < p.Ns[s_first]; k += stride) {
-    job_prepare<DMAX, PHILOX>(p, key, sig, t, k, s_first, ja);
-    job_finish<DMAX, LIKE>(p, sm, t, ja);
-  }
-  if (s_last != s_first) {
-    if (!PRE) job_prepare<DMAX, PHILOX>(p, key, sig, t, k0, 1, jb);   // own row: not touched by half 0
-    // half 1 gathers what half 0 wrote, inside this temperature only
-    EB_MARK(5);
-    if (p.cpt > 1) cluster_barrier();
-    else __syncthreads();
-    EB_MARK(6);
-    job_finish<DMAX, LIKE>(p, sm, t, jb);
-    EB_MARK(7);
-    for (int k = k0 + stride; k < p.Ns[1]; k += stride) {
-      job_prepare<DMAX, PHILOX>(p, key, sig, t, k, 1, jb);
-      job_finish<DMAX, LIKE>(p, sm, t, jb);
-    }
-  }
+  job_finish<DMAX, LIKE, EXACT>(p, sm, t, job);
+  EB_MARK(6);
+  if (p.both && s == 0) asm volatile("barrier.sync.aligned 0;" ::: "memory");
+  EB_MARK(7);
 }
 
+#if !defined(EB_ONLY_LIKE) || EB_ONLY_LIKE == 0
 // split path: proposal only, thread per (t, k) of split s.  Generic in L and D (rows streamed).
 template <bool PHILOX>
 __global__ void __launch_bounds__(BLOCK) stretch_propose_kernel(const StretchArgs p) {
@@ -243,39 +264,77 @@ __global__ void __launch_bounds__(BLOCK) accept_update_kernel(const AcceptArgs p
   if (p.accepted_count && keep) p.accepted_count[slot] += 1u;
 }
 
+#endif  // split path kernels (object 0 only)
+
 template <typename K>
 static int launch_stretch_kernel(K kernel, const StretchArgs& a, size_t sb, cudaStream_t s) {
   int rc = set_smem(kernel, sb);
   if (rc) return rc;
-  int threads = (a.Ns[0] + a.cpt - 1) / a.cpt;   // one walker of the active split per thread
-  threads = ((threads + 31) / 32) * 32;
-  if (threads > STRETCH_THREADS) threads = STRETCH_THREADS;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)a.cpt, (unsigned)a.c.T, 1);
-  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cudaLaunchAttribute attr[1];
+  if (a.both) {
+    const int ht = ((a.Ns[0] + 31) / 32) * 32;
+    cfg.gridDim = dim3(1, (unsigned)a.c.T, 1);
+    cfg.blockDim = dim3((unsigned)(2 * ht), 1, 1);
+    if (a.pdl) {
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+    }
+  } else {
+    const int n = a.Ns[a.split];
+    const int threads = n < STRETCH_HALF_THREADS ? ((n + 31) / 32) * 32 : STRETCH_HALF_THREADS;
+    cfg.gridDim = dim3((unsigned)((n + threads - 1) / threads), (unsigned)a.c.T, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    if (a.pdl) {
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+    }
+  }
   cfg.dynamicSmemBytes = sb;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  if (a.both && a.cpt > 1) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)a.cpt;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  }
   EB_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
   return EB_OK;
 }
 
-template <int DMAX, int LIKE>
+template <int DMAX, int LIKE, bool EXACT>
 static int launch_stretch(const StretchArgs& a, cudaStream_t s) {
   const size_t sb = smem_bytes(a.c);
-  if (a.philox) return launch_stretch_kernel(stretch_step_kernel<DMAX, LIKE, true>, a, sb, s);
-  return launch_stretch_kernel(stretch_step_kernel<DMAX, LIKE, false>, a, sb, s);
+  if (a.philox) return launch_stretch_kernel(stretch_step_kernel<DMAX, LIKE, true, EXACT>, a, sb, s);
+  return launch_stretch_kernel(stretch_step_kernel<DMAX, LIKE, false, EXACT>, a, sb, s);
 }
 
+// one object file per likelihood kind (build.py compiles this source with -DEB_ONLY_LIKE=k): the kernels of kind k
+template <int LIKE>
+int launch_stretch_like(const StretchArgs& a, cudaStream_t s);
+#ifndef EB_ONLY_LIKE
+#define EB_ONLY_LIKE -1   // single-object build: everything
+#endif
+#define EB_STRETCH_LIKE_DEF(K)                                        \
+  template <>                                                         \
+  int launch_stretch_like<K>(const StretchArgs& a, cudaStream_t s) {  \
+    int rc = EB_OK;                                                   \
+    EB_DISPATCH_DMAX(a.c.LD, EB_STRETCH_L1_##K)                       \
+    return rc;                                                        \
+  }
+#define EB_STRETCH_L1_0(DM, EX) rc = launch_stretch<DM, 0, EX>(a, s)
+#define EB_STRETCH_L1_1(DM, EX) rc = launch_stretch<DM, 1, EX>(a, s)
+#define EB_STRETCH_L1_2(DM, EX) rc = launch_stretch<DM, 2, EX>(a, s)
+#if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 0
+EB_STRETCH_LIKE_DEF(0)
+#endif
+#if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 1
+EB_STRETCH_LIKE_DEF(1)
+#endif
+#if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 2
+EB_STRETCH_LIKE_DEF(2)
+#endif
+
+#if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 0
 static int fill_stretch_args(StretchArgs& a, const eb_state* st, double stretch_a, const eb_stretch_rng* rng,
                              bool need_u_acc) {
   if (!rng) return fail(EB_ERR_INVALID, "rng is NULL");
@@ -295,7 +354,8 @@ static int fill_stretch_args(StretchArgs& a, const eb_state* st, double stretch_
   a.iter_dev = (const unsigned long long*)rng->iter_dev; a.iter = rng->iter;
   a.q_out = nullptr; a.factors_out = nullptr; a.sub_out = nullptr;
   a.accepted = nullptr; a.accepted_count = nullptr;
-  a.both = 0; a.split = 0; a.cpt = 1;
+  a.both = 0; a.split = 0; a.pdl = 0;
+  if (rng->pdl_chain && rng->mode != EB_RNG_PHILOX) return fail(EB_ERR_INVALID, "pdl_chain is a philox-mode option");
   if (rng->mode == EB_RNG_REPLAY) {
     for (int s = 0; s < 2; ++s)
       if (!rng->list[s] || !rng->rint[s] || !rng->u_z[s] || (need_u_acc && !rng->u_acc[s]))
@@ -322,30 +382,22 @@ int eb_stretch_step(const eb_state* st, const eb_prior* prior, const eb_like* li
   if (!accepted) return fail(EB_ERR_INVALID, "accepted is NULL");
   args.accepted = accepted; args.accepted_count = accepted_count;
   cudaStream_t s = (cudaStream_t)stream;
-  // One cluster (<= 8 CTAs, portable size) per temperature runs both halves when that still fills the
-  // chip or the temperature is small; otherwise one grid-wide launch per half.
-  const int T = args.c.T, half = args.Ns[0];
-  int cpt = 1;
-  while (cpt < 8 && cpt * STRETCH_THREADS < half) cpt <<= 1;
-  const bool fused = (half <= cpt * STRETCH_THREADS * 4) || (T * cpt >= 148);
-  int nlaunch = 1;
-  if (fused) {
-    args.both = 1; args.cpt = cpt;
-  } else {
-    args.both = 0; args.cpt = (half + STRETCH_THREADS - 1) / STRETCH_THREADS;
-    nlaunch = 2;
-  }
+  // One launch per half; half 1 is a programmatic dependent of half 0 (its draws overlap half 0's evaluation).  Small
+  // ensembles run both halves in one CTA per temperature.  (A cluster-per-temperature variant with a cluster barrier
+  // between the halves measured slower: 16 clusters of 8 CTAs do not all fit the GPCs at once — DESIGN.md §4.1.)
+  static const int pdl_mask = getenv("EB_PDL_MASK") ? atoi(getenv("EB_PDL_MASK")) : 7;   // 1: half 1, 4: half 0 after a swap pass
+  const int half = args.Ns[0];
+  const bool fused = half <= STRETCH_HALF_THREADS / 2;
+  const int nlaunch = fused ? 1 : 2;
+  args.both = fused ? 1 : 0;
   for (int l = 0; l < nlaunch; ++l) {
     args.split = l;
-#define L2_(K) rc = launch_stretch<DM_, K>(args, s)
-#define L1_(DM)                              \
-  {                                          \
-    constexpr int DM_ = DM;                  \
-    EB_DISPATCH_LIKE(like->kind, L2_)        \
-  }
-    EB_DISPATCH_DMAX(args.c.LD, L1_)
-#undef L1_
-#undef L2_
+    args.pdl = ((l == 1 && (pdl_mask & 1)) || (l == 0 && rng->pdl_chain && (pdl_mask & 4))) ? 1 : 0;
+    switch (like->kind) {
+      case 0: rc = launch_stretch_like<0>(args, s); break;
+      case 1: rc = launch_stretch_like<1>(args, s); break;
+      default: rc = launch_stretch_like<2>(args, s); break;
+    }
     if (rc) return rc;
   }
   return check_launch("stretch_step");
@@ -394,3 +446,6 @@ int eb_accept_update(const eb_state* st, const int32_t* sub, int32_t nsub, const
 }  // extern "C"
 
 EB_DEFINE_MARK_READER(eb_debug_marks_stretch)
+#else
+}  // namespace eb
+#endif  // EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 0

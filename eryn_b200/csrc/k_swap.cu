@@ -1,4 +1,6 @@
 // Part of eryn_b200 (kernel overview in common.cuh). Built with --fmad=false.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eb {
@@ -9,16 +11,16 @@ namespace eb {
 // The reference walks the ladder hot -> cold; at rung i it pairs (i, iperm[k]) with
 // (i-1, i1perm[k]) (tempering.py:515-559).  Both permutations are bijections, so the slots touched
 // by successive rungs form W disjoint chains  p_{T-1} -> p_{T-2} -> ... -> p_0  and every exchange
-// stays inside one chain.  The accept test needs logl only (:538), so a chain is resolved in three
-// phases by a group of 8 lanes, all staging in shared memory:
-//   1. positions p_r of the chain on every rung, logl[r][p_r] and log(u) of every rung — independent
-//      across rungs, lanes work on different rungs (philox mode: p_r = sigma_r(chain) with one keyed
-//      bijection per rung, so the pairing of rung i is sigma_{i-1} o sigma_i^{-1}, a uniform random
-//      bijection exactly like i1perm o iperm^{-1}; replay mode: lane 0 follows the host pair map);
-//   2. the hot -> cold cascade on those T numbers (one lane, registers + shared memory) giving
-//      src[r] = rung whose walker ends on rung r;
-//   3. only the rows with src[r] != r move: cp.async global -> shared for all of them at once, one
-//      warp-level sync, then shared -> global.  In place, no second state buffer.
+// stays inside one chain.  The accept test needs logl only (:538), so a chain is resolved by a group of
+// CL lanes (8, 16 or 32: one or two rungs per lane):
+//   0. (before the grid-dependency wait, overlapping the move kernel) positions p_r of the chain on every rung and
+//      log(u) of every rung (philox mode: p_r = sigma_r(chain) with one keyed bijection per rung, so the pairing of
+//      rung i is sigma_{i-1} o sigma_i^{-1}, a uniform random bijection exactly like i1perm o iperm^{-1});
+//   1. gather logl[r][p_r] (replay mode: lane 0 first follows the host pair map);
+//   2. the hot -> cold cascade on those T numbers, run by every lane of the chain (broadcast shared-memory reads),
+//      leaving the accept bits in registers; src[r] = rung whose walker ends on rung r follows from the bits;
+//   3. only the rows with src[r] != r move, in place: every lane gathers the source rows of its rungs into
+//      registers, one warp-level sync, then writes (long rows / leaf flags: through a global staging buffer).
 // The last block to finish folds the per-rung swap counts and adapts the ladder (tempering.py:563-596).
 struct SwapArgs {
   Common c;                                       // local state (sharded: the DESTINATION buffers of this rank)
@@ -32,282 +34,106 @@ struct SwapArgs {
   const double* coords_src[EB_MAX_RANKS]; const double* logp_src[EB_MAX_RANKS]; const uint8_t* inds_src[EB_MAX_RANKS];
   const unsigned long long* flags;                // sharded: local flag words raised by every rank's publish kernel
   int philox, permute, cpb;                       // cpb = chains per block
-  int spec;                                       // prefetch every row of the chain before the decisions (small, L2-resident states)
+  double* scratch_coords; double* scratch_logp; uint8_t* scratch_inds;   // staging of moved rows (RR == 0 path)
   const int32_t* next_pos; const double* u_at;  // replay pair map [T][W]
   uint32_t seed_lo, seed_hi; const unsigned long long* iter_dev; unsigned long long iter;
   eb_ctrl* ctrl;
   int adapt_on, adaptive, stop_adaptation; double lag, t0;
+  int dbg_skip;
 };
 
-constexpr int CHAIN_LANES = 8;
+// CTAs of the publish kernel for `ndoubles` of logl (must match k_shard.cu: a flag word counts publishing CTAs)
+__host__ __device__ inline int publish_grid(size_t ndoubles) {
+  size_t g = (ndoubles / 2 + 255) / 256;
+  return g < 1 ? 1 : g > 148 ? 148 : (int)g;
+}
 
 struct SwapLayout {  // byte offsets into dynamic shared memory
-  size_t betas, dts, ll, lu, rows, keys, pos, src, cnt, inds, total;
+  size_t betas, dts, ll, lu, keys, pos, cnt, total;
 };
-__host__ __device__ inline SwapLayout swap_layout(int T, int LD, int L, int cpb, bool has_inds, bool stage_rows) {
+__host__ __device__ inline SwapLayout swap_layout(int T, int cpb) {
   SwapLayout s;
-  const int RS = (LD + 2) & ~1;                            // row stride in doubles (coords + logp), 16-byte rows
   size_t o = 0;
-  s.rows = o; o += stage_rows ? sizeof(double) * T * RS * cpb : 0;   // [chain][rung][RS]
   s.betas = o; o += sizeof(double) * T;
   s.dts = o; o += sizeof(double) * T;
   s.ll = o; o += sizeof(double) * T * cpb;
   s.lu = o; o += sizeof(double) * T * cpb;
   s.keys = o; o += sizeof(uint32_t) * FEISTEL_ROUNDS * T;
   s.pos = o; o += sizeof(int) * T * cpb;
-  s.src = o; o += sizeof(int) * T * cpb;
   s.cnt = o; o += sizeof(int) * T;
-  s.inds = o; o += (has_inds && stage_rows) ? (size_t)T * L * cpb : 0;
   s.total = (o + 15) & ~(size_t)15;
   return s;
 }
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// release/acquire fence at device scope (__threadfence() is the sequentially consistent one: MEMBAR.SC + L1 invalidate)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// bounded spins count SM cycles (reading %globaltimer is slow): ~2 s at 2 GHz
+constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000ll;
+
+__device__ __forceinline__ bool sel_bit(unsigned long long lo, unsigned long long hi, int i) {
+  return i < 64 ? ((lo >> i) & 1ull) != 0ull : ((hi >> (i - 64)) & 1ull) != 0ull;
 }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+
+// source rung of the walker that ends on rung r, from the accept bits of the cascade (bit i = swap accepted at rung i):
+// an accepted swap at r brings up the walker of rung r-1; otherwise rung r receives the walker that was being carried
+// down, which started at the top of the run of accepted swaps directly above r
+__device__ __forceinline__ int swap_source(unsigned long long lo, unsigned long long hi, int r, int T) {
+  if (r >= 1 && sel_bit(lo, hi, r)) return r - 1;
+  int o = r;
+  while (o + 1 < T && sel_bit(lo, hi, o + 1)) ++o;
+  return o;
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Lane l of a chain's 8-lane group owns rungs l, l+8, l+16, ... in every phase.
-template <bool PHILOX, bool SHARDED>
-__global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const Common& c = p.c;
-  const int T = p.T, W = c.W, LD = c.LD, L = c.L, cpb = p.cpb;
-  const int RS = (LD + 2) & ~1;
-  const SwapLayout lay = swap_layout(T, LD, L, cpb, c.inds != nullptr, !SHARDED);
-  double* s_betas = reinterpret_cast<double*>(smraw + lay.betas);
-  double* s_dts = reinterpret_cast<double*>(smraw + lay.dts);
-  uint32_t* s_keys = reinterpret_cast<uint32_t*>(smraw + lay.keys);
-  int* s_cnt = reinterpret_cast<int*>(smraw + lay.cnt);
-  __shared__ bool s_last;
-
-  const int tid = threadIdx.x;
-  const int g = tid / CHAIN_LANES, lane = tid % CHAIN_LANES;
-  const int chain = blockIdx.x * cpb + g;
-  const bool valid = g < cpb && chain < W;
-  const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
-  const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
-
-  EB_MARK(16);
-  if (SHARDED && p.flags) {
-    // every rank's logl rows of THIS iteration must have landed in logl_in (eb_publish_logl): bounded spin on
-    // the local flag words, one thread per CTA
-    __shared__ bool s_ok;
-    if (tid == 0) {
-      bool ok = *reinterpret_cast<volatile unsigned int*>(&p.ctrl->error) == 0u;
-      const unsigned long long target = p.ctrl->iter + 1ull;
-      unsigned long long t_start;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-      for (int gr = 0; ok && gr < p.world; ++gr) {
-        const volatile unsigned long long* f = p.flags + gr;
-        while (*f < target) {
-          unsigned long long now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (now - t_start > EB_PEER_TIMEOUT_NS) { ok = false; break; }
-        }
-      }
-      if (!ok) atomicExch(&p.ctrl->error, EB_DEVERR_PEER_TIMEOUT);
-      __threadfence_system();
-      s_ok = ok;
+// copy one row between distinct slots through registers; LD is a runtime value
+__device__ __forceinline__ void copy_row(double* __restrict__ dst, const double* __restrict__ src, int LD) {
+  if ((LD & 3) == 0) {
+    for (int e = 0; e < LD; e += 4) {
+      double a, b, c, d;
+      ld256(src + e, a, b, c, d);
+      st256(dst + e, a, b, c, d);
     }
-    __syncthreads();
-    if (!s_ok) return;
+  } else if ((LD & 1) == 0) {
+    for (int e = 0; e < LD; e += 2) *reinterpret_cast<double2*>(dst + e) = *reinterpret_cast<const double2*>(src + e);
+  } else {
+    for (int e = 0; e < LD; ++e) dst[e] = src[e];
   }
-  // ---- phase 0: ladder and per-rung bijection keys, once per block ------------------------------
-  for (int r = tid; r < T; r += blockDim.x) {
-    s_betas[r] = p.betas[r];
-    s_cnt[r] = 0;
-    if (PHILOX && p.permute) Feistel::make_keys(key, TAG_SWAP_KEY, (uint32_t)r, s_keys + FEISTEL_ROUNDS * r);
-  }
-  __syncthreads();
+}
 
-  const int gg = valid ? g : 0;
-  double* ll = reinterpret_cast<double*>(smraw + lay.ll) + (size_t)gg * T;
-  double* lu = reinterpret_cast<double*>(smraw + lay.lu) + (size_t)gg * T;
-  double* rows = reinterpret_cast<double*>(smraw + lay.rows) + (size_t)gg * T * RS;
-  int* pos = reinterpret_cast<int*>(smraw + lay.pos) + (size_t)gg * T;
-  int* src = reinterpret_cast<int*>(smraw + lay.src) + (size_t)gg * T;
-  uint8_t* sinds = smraw + lay.inds + (size_t)gg * T * L;
-
-  EB_MARK(17);
-  // ---- phase 1: chain positions, logl and log(u) of the owned rungs ----------------------------
-  if (!PHILOX) {
-    if (valid && lane == 0) {            // replay: p_{i-1} = i1perm_i[iperm_i^{-1}[p_i]] (pt_pairmap_kernel)
-      int pz = chain;
-      pos[T - 1] = pz;
-      for (int i = T - 1; i >= 1; --i) {
-        pz = p.next_pos[(size_t)i * W + pz];
-        pos[i - 1] = pz;
-      }
-    }
-    __syncwarp();
-  }
-  if (valid) {
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    for (int m = 0, r = lane; r < T; ++m, r += CHAIN_LANES) {
-      int pz;
-      if (PHILOX) {
-        pz = chain;
-        if (p.permute) {
-          Feistel sig;
-          sig.init_from(s_keys + FEISTEL_ROUNDS * r, (uint32_t)W);
-          pz = (int)sig((uint32_t)chain);
-        }
-        pos[r] = pz;
-      } else {
-        pz = pos[r];
-      }
-      ll[r] = p.logl_in[(size_t)r * W + pz];
-      if (!SHARDED && p.spec) {          // the rows can start moving before the decisions are known
-        const size_t slot = (size_t)r * W + pz;
-        const double* grow = c.coords + slot * LD;
-        double* srow = rows + (size_t)r * RS;
-        if ((LD & 1) == 0) {
-          for (int e = 0; e < LD; e += 2) cp_async16(srow + e, grow + e);
-        } else {
-          for (int e = 0; e < LD; ++e) cp_async8(srow + e, grow + e);
-        }
-        cp_async8(srow + LD, c.logp + slot);
-        if (c.inds)
-          for (int l = 0; l < L; ++l) sinds[r * L + l] = c.inds[slot * L + l];
-      }
-      double u;
-      if (PHILOX) {                      // one Philox block serves two owned rungs (r and r + 8)
-        if ((m & 1) == 0) q = stream(key, TAG_SWAP_U, (uint32_t)chain, (uint32_t)(lane + CHAIN_LANES * (m >> 1)));
-        u = (m & 1) ? u01_52(q.z, q.w) : u01_52(q.x, q.y);
-      } else {
-        u = (r >= 1) ? p.u_at[(size_t)r * W + pz] : 0.5;
-      }
-      lu[r] = log(u);                                                          // tempering.py:535
-    }
-  }
-  __syncwarp();
-
-  EB_MARK(18);
-  // ---- phase 2: the cascade, hot -> cold (tempering.py:515-559 restricted to this chain) --------
-  if (valid && lane == 0) {
-    double carry = ll[T - 1];
-    int origin = T - 1;
-    for (int i = T - 1; i >= 1; --i) {
-      const double dbeta = s_betas[i - 1] - s_betas[i];                        // :518-522
-      const double lower = ll[i - 1];
-      const bool sel = dbeta * (carry - lower) > lu[i];                        // :538, :541
-      if (sel) {
-        src[i] = i - 1;                  // the colder walker moves up, the carried one keeps falling
-      } else {
-        src[i] = origin;                 // the carried walker settles on rung i
-        carry = lower;
-        origin = i - 1;
-      }
-    }
-    src[0] = origin;
-  }
-  __syncwarp();
-
-  EB_MARK(19);
-  // ---- swap counts: swaps_accepted[r-1] counts src[r] == r-1 (:542), summed over the 4 chains of the
-  //      warp by shuffles, over the block in shared memory, over the grid by atomics.  The ticket is taken
-  //      here, before the rows move, so that its round trip overlaps phase 3.
-  for (int r0 = 0; r0 < T; r0 += CHAIN_LANES) {   // uniform trip count: the loop body shuffles
-    const int r = r0 + lane;
-    int sel = (valid && r >= 1 && r < T && src[r] == r - 1) ? 1 : 0;
-    sel += __shfl_xor_sync(0xffffffffu, sel, 8);
-    sel += __shfl_xor_sync(0xffffffffu, sel, 16);
-    if (sel && (tid & 31) < CHAIN_LANES) atomicAdd(&s_cnt[r - 1], sel);
-  }
-  __syncthreads();
+// The adapt CTA of the swap pass: wait for the counts of all `nreal` chain CTAs, fold them into swaps_accepted and
+// apply adapt_temps (tempering.py:563-596); ticks the iteration counter.
+__device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, int nreal, unsigned long long it,
+                                              long long time_now_t0, double* s_betas, double* s_dts, int* s_cnt) {
   eb_ctrl* ctrl = p.ctrl;
-  for (int r = tid; r < T - 1; r += blockDim.x)
-    if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[r], s_cnt[r]);
-  __threadfence();
+  const int tid = threadIdx.x;
+  __shared__ long long s_time;
+  __shared__ int s_ok2;
+  if (tid == 0) { s_time = time_now_t0; s_ok2 = 1; }
+  for (int r = tid; r < T; r += blockDim.x) s_cnt[r] = 0;
   __syncthreads();
-  unsigned int ticket = 0u;
-  if (tid == 0) ticket = atomicAdd(&ctrl->ticket, 1u);
-
-  EB_MARK(20);
-  // ---- phase 3: move the rows that changed rung (do_swaps_indexing, tempering.py:351-482) ------
-  if (!SHARDED) {
-    // staging row index: by source rung when prefetched (phase 1), by destination rung otherwise
-    if (!p.spec && valid) {
-      for (int r = lane; r < T; r += CHAIN_LANES) {
-        const int s = src[r];
-        if (s == r) continue;
-        const size_t sslot = (size_t)s * W + pos[s];
-        const double* grow = c.coords + sslot * LD;
-        double* srow = rows + (size_t)r * RS;
-        if ((LD & 1) == 0) {
-          for (int e = 0; e < LD; e += 2) cp_async16(srow + e, grow + e);
-        } else {
-          for (int e = 0; e < LD; ++e) cp_async8(srow + e, grow + e);
-        }
-        cp_async8(srow + LD, c.logp + sslot);
-        if (c.inds)
-          for (int l = 0; l < L; ++l) sinds[r * L + l] = c.inds[sslot * L + l];
-      }
-    }
-    cp_async_wait_all();
-    __syncwarp();                        // every lane has read its sources before any lane writes
-    if (valid) {
-      for (int r = lane; r < T; r += CHAIN_LANES) {
-        const int s = src[r];
-        if (s == r) continue;
-        const int st = p.spec ? s : r;
-        const size_t dslot = (size_t)r * W + pos[r];
-        double* grow = c.coords + dslot * LD;
-        const double* srow = rows + (size_t)st * RS;
-        if ((LD & 1) == 0) {
-          for (int e = 0; e < LD; e += 2) *reinterpret_cast<double2*>(grow + e) = *reinterpret_cast<const double2*>(srow + e);
-        } else {
-          for (int e = 0; e < LD; ++e) grow[e] = srow[e];
-        }
-        c.logp[dslot] = srow[LD];
-        c.logl[dslot] = ll[s];
-        if (c.inds)
-          for (int l = 0; l < L; ++l) c.inds[dslot * L + l] = sinds[st * L + l];
-      }
-    }
-  } else if (valid) {
-    // Sharded: this rank owns rungs [t_lo, t_hi).  Every owned slot is (re)written into the destination
-    // buffers from the CURRENT buffers of whichever rank holds the source rung (NVLink peer loads), the 8
-    // lanes of the chain sharing each row.  No staging: source and destination buffers are distinct.
-    for (int r = p.t_lo; r < p.t_hi; ++r) {
-      const int s = src[r];
-      int gsrc = 0;
-      while (gsrc + 1 < p.world && s >= p.temp_begin[gsrc + 1]) ++gsrc;
-      const size_t sslot = (size_t)(s - p.temp_begin[gsrc]) * W + pos[s];
-      const size_t dslot = (size_t)(r - p.t_lo) * W + pos[r];
-      const double* grow = p.coords_src[gsrc] + sslot * LD;
-      double* drow = c.coords + dslot * LD;
-      for (int e = lane; e < LD; e += CHAIN_LANES) drow[e] = grow[e];
-      if (lane == (LD & (CHAIN_LANES - 1))) {
-        c.logp[dslot] = p.logp_src[gsrc][sslot];
-        c.logl[dslot] = ll[s];
-      }
-      if (c.inds)
-        for (int l = lane; l < L; l += CHAIN_LANES) c.inds[dslot * L + l] = p.inds_src[gsrc][sslot * L + l];
-    }
+  if (tid < EB_SWAP_SLOTS) {
+    const unsigned expected = (unsigned)(nreal / EB_SWAP_SLOTS + (tid < nreal % EB_SWAP_SLOTS ? 1 : 0));
+    const volatile unsigned* a = &ctrl->arrive[tid];
+    const long long t_start = clock64();
+    while (*a < expected)
+      if (clock64() - t_start > SPIN_TIMEOUT_CYCLES) { s_ok2 = 0; break; }
+    fence_acq_rel_gpu();
+    ctrl->arrive[tid] = 0u;
   }
-
-  EB_MARK(21);
-  // ---- the block that drew the last ticket folds the counts and adapts the ladder -----------------
-  if (tid == 0) s_last = (ticket == gridDim.x - 1);
   __syncthreads();
-  EB_MARK(22);
-  if (!s_last) return;
-  __threadfence();
-  for (int r = tid; r < T - 1; r += blockDim.x) {
-    const int v = atomicExch(&ctrl->swaps_work[r], 0);
-    ctrl->swaps_accepted[r] = v;
-    ctrl->swaps_total[r] += (unsigned long long)v;
-    s_cnt[r] = v;
+  if (!s_ok2) {
+    if (tid == 0) atomicExch(&ctrl->error, EB_DEVERR_SWAP_TIMEOUT);
+    return;
   }
-  const long long time_now = ctrl->time;
+  // fold the slot counts (independent loads first, the dependent bookkeeping stores last: the ladder is what the next
+  // kernel waits for)
+  for (int e = tid; e < EB_SWAP_SLOTS * (T - 1); e += blockDim.x) {
+    const int v = *reinterpret_cast<volatile int*>(&ctrl->swaps_work[e / (T - 1)][e % (T - 1)]);
+    if (v) atomicAdd(&s_cnt[e % (T - 1)], v);
+  }
   __syncthreads();
+  const long long time_now = s_time;
   if (p.adapt_on && p.adaptive && T > 1) {                                     // tempering.py:632-633
     if (p.stop_adaptation < 0 || time_now < (long long)p.stop_adaptation) {   // :590
       const double decay = p.lag / ((double)time_now + p.lag);                 // :571
@@ -335,10 +161,317 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(const SwapArgs p) {
     }
     if (tid == 0) ctrl->time = time_now + 1;                                   // :596
   }
-  if (tid == 0) {
-    ctrl->iter += 1ull;
-    ctrl->ticket = 0u;
+  for (int e = tid; e < EB_SWAP_SLOTS * (T - 1); e += blockDim.x) ctrl->swaps_work[e / (T - 1)][e % (T - 1)] = 0;
+  for (int r = tid; r < T - 1; r += blockDim.x) {
+    const int v = s_cnt[r];
+    ctrl->swaps_accepted[r] = v;
+    ctrl->swaps_total[r] += (unsigned long long)v;
   }
+  if (tid == 0) ctrl->iter = it + 1ull;
+}
+
+constexpr int SWAP_THREADS = 256;
+
+// CL lanes resolve one chain; lane l owns rungs l, l+CL, l+2CL, ...  (CL = 8, 16 or 32).
+// RR > 0: rows of up to RR doubles move through registers (needs T <= RPL*CL and no leaf flags); RR == 0: through the
+// global staging buffers.
+template <bool PHILOX, bool SHARDED, int CL, int RR, int RPL>
+__global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const SwapArgs p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const Common& c = p.c;
+  const int T = p.T, W = c.W, LD = c.LD, L = c.L, cpb = p.cpb;
+  const SwapLayout lay = swap_layout(T, cpb);
+  double* s_betas = reinterpret_cast<double*>(smraw + lay.betas);
+  double* s_dts = reinterpret_cast<double*>(smraw + lay.dts);
+  uint32_t* s_keys = reinterpret_cast<uint32_t*>(smraw + lay.keys);
+  int* s_cnt = reinterpret_cast<int*>(smraw + lay.cnt);
+
+  // The grid carries one extra CTA (the last) without chains: it waits until every other CTA has published its swap
+  // counts, then folds them and adapts the ladder WHILE the other CTAs are still moving rows.
+  const bool adapt_cta = blockIdx.x == gridDim.x - 1;
+  const int nreal = (int)gridDim.x - 1;
+  const int tid = threadIdx.x;
+  const int g = tid / CL, lane = tid % CL;
+  const int chain = blockIdx.x * cpb + g;
+  const bool valid = !adapt_cta && g < cpb && chain < W;
+  eb_ctrl* ctrl = p.ctrl;
+  long long time_now = 0;
+  if (adapt_cta && tid == 0) time_now = *reinterpret_cast<const volatile long long*>(&ctrl->time);
+  // ---- prologue: nothing here reads the walker state, so under programmatic dependent launch it overlaps the move
+  //      kernel that precedes this pass.  ctrl->iter is written only by this kernel's own tail.
+  const unsigned long long it = p.iter_dev ? *reinterpret_cast<const volatile unsigned long long*>(p.iter_dev) : p.iter;
+  if (blockIdx.x == 0 && tid == 0) {
+    // the next move kernel may start its draws while this pass still runs: it keys them by iter_next
+    *reinterpret_cast<volatile unsigned long long*>(&ctrl->iter_next) = it + 1ull;
+    fence_acq_rel_gpu();
+  }
+  const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
+
+  EB_MARK(16);
+  for (int r = tid; r < T; r += blockDim.x) {
+    s_cnt[r] = 0;
+    if (PHILOX && p.permute) Feistel::make_keys(key, TAG_SWAP_KEY, (uint32_t)r, s_keys + FEISTEL_ROUNDS * r);
+  }
+  __syncthreads();
+
+  const int gg = valid ? g : 0;
+  double* ll = reinterpret_cast<double*>(smraw + lay.ll) + (size_t)gg * T;
+  double* lu = reinterpret_cast<double*>(smraw + lay.lu) + (size_t)gg * T;
+  int* pos = reinterpret_cast<int*>(smraw + lay.pos) + (size_t)gg * T;
+
+  EB_MARK(17);
+  if (PHILOX && valid && !EB_DBG_SKIP(16)) {
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    for (int r = lane; r < T; r += CL) {
+      int pz = chain;
+      if (p.permute) {
+        Feistel sig;
+        sig.init_from(s_keys + FEISTEL_ROUNDS * r, (uint32_t)W);
+        pz = (int)sig((uint32_t)chain);
+      }
+      pos[r] = pz;
+      // one Philox block serves rungs r and r + 8 of a chain: counter (chain, (r & 7) | ((r >> 4) << 3)),
+      // word pair (r >> 3) & 1
+      const bool second = ((r >> 3) & 1) != 0;
+      if (CL != 8 || !second) q = stream(key, TAG_SWAP_U, (uint32_t)chain, (uint32_t)((r & 7) | ((r >> 4) << 3)));
+      const double u = second ? u01_52(q.z, q.w) : u01_52(q.x, q.y);
+      lu[r] = log(u);                                                          // tempering.py:535
+    }
+  }
+  pdl_wait();                 // the move kernel has completed; its writes are visible
+  pdl_launch_dependents();    // the next move kernel may begin its draws
+  if (SHARDED && p.flags) {
+    // every rank's logl rows of THIS iteration must have landed in logl_in (eb_publish_logl): bounded spin on
+    // the local flag words, one thread per CTA
+    __shared__ bool s_ok;
+    if (tid == 0) {
+      bool ok = *reinterpret_cast<volatile unsigned int*>(&ctrl->error) == 0u;
+      // flag word g counts the CTAs of rank g's publish kernels so far (k_shard.cu)
+      const long long t_start = clock64();
+      for (int gr = 0; ok && gr < p.world; ++gr) {
+        const size_t rows = (size_t)(p.temp_begin[gr + 1] - p.temp_begin[gr]) * W;
+        const unsigned long long target = (it + 1ull) * (unsigned long long)publish_grid(rows);
+        const volatile unsigned long long* f = p.flags + gr;
+        while (*f < target)
+          if (clock64() - t_start > SPIN_TIMEOUT_CYCLES) { ok = false; break; }
+      }
+      if (!ok) atomicExch(&ctrl->error, EB_DEVERR_PEER_TIMEOUT);
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      s_ok = ok;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+  }
+  for (int r = tid; r < T; r += blockDim.x) {   // the ladder is adapted by the previous pass: read after the wait
+    const double b = p.betas[r];
+    s_betas[r] = b;
+    s_dts[r] = r >= 1 ? p.betas[r - 1] - b : 0.0;                              // :518-522
+  }
+  if (!PHILOX) {
+    if (valid && lane == 0) {            // replay: p_{i-1} = i1perm_i[iperm_i^{-1}[p_i]] (pt_pairmap_kernel)
+      int pz = chain;
+      pos[T - 1] = pz;
+      for (int i = T - 1; i >= 1; --i) {
+        pz = p.next_pos[(size_t)i * W + pz];
+        pos[i - 1] = pz;
+      }
+    }
+    __syncwarp();
+    if (valid)
+      for (int r = lane; r < T; r += CL) lu[r] = log((r >= 1) ? p.u_at[(size_t)r * W + pos[r]] : 0.5);
+  }
+  if (valid)
+    for (int r = lane; r < T; r += CL) ll[r] = p.logl_in[(size_t)r * W + pos[r]];
+  __syncthreads();
+
+  EB_MARK(18);
+  // ---- the cascade, hot -> cold (tempering.py:515-559 restricted to this chain); every lane of the chain runs it
+  //      (same operands, broadcast reads), so every lane knows all accept bits
+  unsigned long long sel_lo = 0ull, sel_hi = 0ull;
+  if (valid && !EB_DBG_SKIP(8)) {
+    double carry = ll[T - 1];
+    if (RR > 0) {
+      // short ladders: compile-time trip count, so the operand loads of all rungs are hoisted above the dependent chain
+#pragma unroll
+      for (int i = CL * RPL - 1; i >= 1; --i) {
+        if (i < T) {
+          const double lower = ll[i - 1];
+          const bool sel = s_dts[i] * (carry - lower) > lu[i];                 // :538, :541  (s_dts[i] = betas[i-1]-betas[i])
+          if (sel) {
+            if (i < 64) sel_lo |= 1ull << i;
+            else sel_hi |= 1ull << (i - 64);
+          } else {
+            carry = lower;               // the carried walker settles on rung i, rung i-1's walker is carried on
+          }
+        }
+      }
+    } else {
+      for (int i = T - 1; i >= 1; --i) {
+        const double lower = ll[i - 1];
+        const bool sel = s_dts[i] * (carry - lower) > lu[i];
+        if (sel) {
+          if (i < 64) sel_lo |= 1ull << i;
+          else sel_hi |= 1ull << (i - 64);
+        } else {
+          carry = lower;
+        }
+      }
+    }
+  }
+
+  EB_MARK(19);
+  // ---- swap counts: swaps_accepted[r-1] counts accepted swaps at rung r (:542): ballot over the chains of the warp,
+  //      shared-memory atomics over the block, global atomics over the grid
+  {
+    constexpr int CPW = 32 / CL;                     // chains per warp
+    const int wl = tid & 31;
+    for (int r0 = 0; r0 < T; r0 += CL) {             // uniform trip count: the loop body votes
+      const int r = r0 + lane;
+      const bool b = valid && r >= 1 && r < T && sel_bit(sel_lo, sel_hi, r);
+      const unsigned v = __ballot_sync(0xffffffffu, b);
+      if (wl < CL) {
+        unsigned m = 0u;
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) m |= 1u << (wl + q * CL);
+        const int n = __popc(v & m);
+        if (n) atomicAdd(&s_cnt[r - 1], n);
+      }
+    }
+  }
+
+  // the counts are published here, before the rows move (fire-and-forget reductions + one arrival per CTA, all spread
+  // over EB_SWAP_SLOTS addresses: same-address atomics serialise in L2)
+  __syncthreads();
+  if (EB_DBG_SKIP(2)) {
+    if (adapt_cta) return;
+  } else if (!adapt_cta) {
+    for (int r = tid; r < T - 1; r += blockDim.x)
+      if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[blockIdx.x % EB_SWAP_SLOTS][r], s_cnt[r]);
+    __syncthreads();
+    if (tid == 0) {        // block barrier + one device-scope release by the signalling thread (cumulative)
+      fence_acq_rel_gpu();
+      atomicAdd(&ctrl->arrive[blockIdx.x % EB_SWAP_SLOTS], 1u);
+    }
+  } else {
+    if (EB_DBG_SKIP(4)) { if (tid < EB_SWAP_SLOTS) ctrl->arrive[tid] = 0u; return; }
+    pt_swap_adapt(p, T, W, nreal, it, time_now, s_betas, s_dts, s_cnt);
+    EB_MARK(23);
+    return;
+  }
+
+  EB_MARK(20);
+  // ---- move the rows that changed rung (do_swaps_indexing, tempering.py:351-482): every lane gathers the source rows
+  //      of its rungs, the lanes of the chain synchronise (all reads before any write), then write
+  if (EB_DBG_SKIP(1)) return;
+  if (!SHARDED) {
+    if (RR > 0) {
+      constexpr int RRX = RR > 0 ? RR : 1;
+      double rowv[RPL][RRX], lpv[RPL], llv[RPL];
+      long long dsl[RPL];
+#pragma unroll
+      for (int m = 0; m < RPL; ++m) {
+        const int r = lane + m * CL;
+        dsl[m] = -1;
+        if (valid && r < T) {
+          const int s = swap_source(sel_lo, sel_hi, r, T);
+          if (s != r) {
+            const size_t sslot = (size_t)s * W + pos[s];
+            dsl[m] = (long long)r * W + pos[r];
+            if (EB_DBG_SKIP(32)) {
+#pragma unroll
+              for (int e = 0; e < RRX; ++e) rowv[m][e] = 1.0;
+              lpv[m] = 0.0; llv[m] = ll[s];
+            } else
+            if ((LD & 3) == 0) {
+#pragma unroll
+              for (int e = 0; e < RRX; e += 4)
+                if (e < LD) ld256(c.coords + sslot * LD + e, rowv[m][e], rowv[m][e + 1], rowv[m][e + 2], rowv[m][e + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < RRX; ++e)
+                if (e < LD) rowv[m][e] = c.coords[sslot * LD + e];
+            }
+            if (!EB_DBG_SKIP(32)) lpv[m] = c.logp[sslot];
+            llv[m] = ll[s];
+          }
+        }
+      }
+      EB_MARK(24);
+      if (!EB_DBG_SKIP(128)) __syncwarp();
+      EB_MARK(25);
+      if (EB_DBG_SKIP(64)) {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < RPL; ++m)
+          if (dsl[m] >= 0) {
+#pragma unroll
+            for (int e = 0; e < RRX; ++e) acc += rowv[m][e];
+            acc += lpv[m] + llv[m];
+          }
+        if (acc == 1.2345e300) c.logl[0] = acc;
+        EB_MARK(21);
+        return;
+      }
+#pragma unroll
+      for (int m = 0; m < RPL; ++m)
+        if (dsl[m] >= 0) {
+          const size_t dslot = (size_t)dsl[m];
+          if ((LD & 3) == 0) {
+#pragma unroll
+            for (int e = 0; e < RRX; e += 4)
+              if (e < LD) st256(c.coords + dslot * LD + e, rowv[m][e], rowv[m][e + 1], rowv[m][e + 2], rowv[m][e + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < RRX; ++e)
+              if (e < LD) c.coords[dslot * LD + e] = rowv[m][e];
+          }
+          c.logp[dslot] = lpv[m];
+          c.logl[dslot] = llv[m];
+        }
+    } else {
+      // long rows / leaf flags / long ladders: the moved rows rest in the global staging buffers between the gather
+      // and the scatter (indexed by destination slot, so chains never collide)
+      for (int r = lane; valid && r < T; r += CL) {
+        const int s = swap_source(sel_lo, sel_hi, r, T);
+        if (s == r) continue;
+        const size_t sslot = (size_t)s * W + pos[s], dslot = (size_t)r * W + pos[r];
+        copy_row(p.scratch_coords + dslot * LD, c.coords + sslot * LD, LD);
+        p.scratch_logp[dslot] = c.logp[sslot];
+        if (c.inds)
+          for (int l = 0; l < L; ++l) p.scratch_inds[dslot * L + l] = c.inds[sslot * L + l];
+      }
+      __syncwarp();
+      for (int r = lane; valid && r < T; r += CL) {
+        const int s = swap_source(sel_lo, sel_hi, r, T);
+        if (s == r) continue;
+        const size_t dslot = (size_t)r * W + pos[r];
+        copy_row(c.coords + dslot * LD, p.scratch_coords + dslot * LD, LD);
+        c.logp[dslot] = p.scratch_logp[dslot];
+        c.logl[dslot] = ll[s];
+        if (c.inds)
+          for (int l = 0; l < L; ++l) c.inds[dslot * L + l] = p.scratch_inds[dslot * L + l];
+      }
+    }
+  } else if (valid) {
+    // Sharded: this rank owns rungs [t_lo, t_hi).  Every owned slot is (re)written into the destination buffers
+    // from the CURRENT buffers of whichever rank holds the source rung (NVLink peer loads); lanes work on different
+    // rungs, so the loads of all owned rungs of the chain are in flight together.  Source and destination buffers
+    // are distinct: no staging.
+    for (int r = p.t_lo + lane; r < p.t_hi; r += CL) {
+      const int s = swap_source(sel_lo, sel_hi, r, T);
+      int gsrc = 0;
+      while (gsrc + 1 < p.world && s >= p.temp_begin[gsrc + 1]) ++gsrc;
+      const size_t sslot = (size_t)(s - p.temp_begin[gsrc]) * W + pos[s];
+      const size_t dslot = (size_t)(r - p.t_lo) * W + pos[r];
+      copy_row(c.coords + dslot * LD, p.coords_src[gsrc] + sslot * LD, LD);
+      c.logp[dslot] = p.logp_src[gsrc][sslot];
+      c.logl[dslot] = ll[s];
+      if (c.inds)
+        for (int l = 0; l < L; ++l) c.inds[dslot * L + l] = p.inds_src[gsrc][sslot * L + l];
+    }
+  }
+
+  EB_MARK(21);
 }
 
 // K3r: replay mode — turn the host permutations of every rung into a per-position pair map.
@@ -362,9 +495,11 @@ static int fill_swap_common(SwapArgs& args, const eb_swap_rng* rng, const eb_ada
   if (!rng || !ctrl) return fail(EB_ERR_INVALID, "rng/ctrl is NULL");
   args.philox = rng->mode == EB_RNG_PHILOX; args.permute = rng->permute;
   args.next_pos = rng->next_pos; args.u_at = rng->u_at;
+  args.scratch_coords = rng->row_scratch; args.scratch_logp = rng->logp_scratch; args.scratch_inds = rng->inds_scratch;
   args.seed_lo = (uint32_t)(rng->seed & 0xFFFFFFFFull); args.seed_hi = (uint32_t)(rng->seed >> 32);
   args.iter_dev = (const unsigned long long*)rng->iter_dev; args.iter = rng->iter;
   args.ctrl = ctrl;
+  args.dbg_skip = getenv("EB_SWAP_SKIP") ? atoi(getenv("EB_SWAP_SKIP")) : 0;
   args.adapt_on = adapt != nullptr;
   args.adaptive = adapt ? adapt->adaptive : 0;
   args.stop_adaptation = adapt ? adapt->stop_adaptation : -1;
@@ -374,32 +509,73 @@ static int fill_swap_common(SwapArgs& args, const eb_swap_rng* rng, const eb_ada
   return EB_OK;
 }
 
+template <bool PHILOX, bool SHARDED, int CL, int RR, int RPL>
+static int launch_swap_kernel(SwapArgs& args, cudaStream_t s) {
+  auto kernel = pt_swap_kernel<PHILOX, SHARDED, CL, RR, RPL>;
+  const int W = args.c.W;
+  const int cpb = SWAP_THREADS / CL;
+  args.cpb = cpb;
+  const size_t sb = swap_layout(args.T, cpb).total;
+  int rc = set_smem(kernel, sb);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((W + cpb - 1) / cpb) + 1u, 1, 1);   // + the adapt CTA
+  cfg.blockDim = dim3(SWAP_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = sb;
+  cfg.stream = s;
+  // programmatic dependent of the move kernel: positions and log(u) are computed while the move still runs
+  cudaLaunchAttribute attr[1];
+  static const int pdl_mask = getenv("EB_PDL_MASK") ? atoi(getenv("EB_PDL_MASK")) : 5;
+  if (pdl_mask & 2) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  EB_CUDA(cudaLaunchKernelEx(&cfg, kernel, args));
+  return check_launch("pt_swap");
+}
+
+template <bool PHILOX, bool SHARDED>
+static int launch_swap_shape(SwapArgs& args, cudaStream_t s) {
+  const int T = args.T, LD = args.c.LD;
+  // sharded passes copy every owned row between distinct buffers (no staging): RR is irrelevant there
+  const bool regs_ok = SHARDED || (!args.c.inds && LD <= 32);
+  const int cl = T <= 8 ? 8 : T <= 16 ? 16 : 32;
+  const int rpl = (T + cl - 1) / cl;
+  int rr = 0;
+  if (regs_ok && rpl == 1) rr = LD <= 8 ? 8 : 32;
+  else if (regs_ok && rpl == 2 && LD <= 8) rr = 8;
+  if (SHARDED) rr = 8;
+  if (rr == 0 && !SHARDED && (!args.scratch_coords || !args.scratch_logp || (args.c.inds && !args.scratch_inds)))
+    return fail(EB_ERR_INVALID,
+                "swap pass: this shape (T=%d, row of %d doubles%s) moves rows through staging buffers: set "
+                "eb_swap_rng.row_scratch / logp_scratch%s", T, LD, args.c.inds ? ", leaf flags" : "",
+                args.c.inds ? " / inds_scratch" : "");
+#define EB_SWAP_GO(CL_, RR_, RPL_) return launch_swap_kernel<PHILOX, SHARDED, CL_, RR_, RPL_>(args, s)
+  if (cl == 8) {
+    if (rr == 8) EB_SWAP_GO(8, 8, 1);
+    if (rr == 32) EB_SWAP_GO(8, 32, 1);
+    EB_SWAP_GO(8, 0, 1);
+  }
+  if (cl == 16) {
+    if (rr == 8) EB_SWAP_GO(16, 8, 1);
+    if (rr == 32) EB_SWAP_GO(16, 32, 1);
+    EB_SWAP_GO(16, 0, 1);
+  }
+  if (rr == 8 && rpl == 1) EB_SWAP_GO(32, 8, 1);
+  if (rr == 32 && rpl == 1) EB_SWAP_GO(32, 32, 1);
+  if (rr == 8 && rpl == 2) EB_SWAP_GO(32, 8, 2);
+  EB_SWAP_GO(32, 0, 1);
+#undef EB_SWAP_GO
+}
+
 template <bool SHARDED>
 static int launch_swap(SwapArgs& args, cudaStream_t s) {
-  // chains per block: as many as fit shared memory, at most 16 (128 threads)
-  const int T = args.T, W = args.c.W;
-  const bool has_inds = args.c.inds != nullptr;
-  int cpb = 16;
-  while (cpb > 1 && swap_layout(T, args.c.LD, args.c.L, cpb, has_inds, !SHARDED).total > 96 * 1024) cpb >>= 1;
-  const size_t sb = swap_layout(T, args.c.LD, args.c.L, cpb, has_inds, !SHARDED).total;
-  if (sb > 200 * 1024)
-    return fail(EB_ERR_UNSUPPORTED, "swap pass: one chain of %d rungs x %d doubles does not fit shared memory", T,
-                args.c.LD);
-  args.cpb = cpb;
-  args.spec = (!SHARDED && (size_t)T * W * (args.c.LD + 2) * sizeof(double) <= (size_t)48 << 20) ? 1 : 0;
-  const int threads = max(32, cpb * CHAIN_LANES);
-  const int grid = (W + cpb - 1) / cpb;
-  int rc;
-  if (args.philox) {
-    rc = set_smem(pt_swap_kernel<true, SHARDED>, sb);
-    if (rc) return rc;
-    pt_swap_kernel<true, SHARDED><<<grid, threads, sb, s>>>(args);
-  } else {
-    rc = set_smem(pt_swap_kernel<false, SHARDED>, sb);
-    if (rc) return rc;
-    pt_swap_kernel<false, SHARDED><<<grid, threads, sb, s>>>(args);
-  }
-  return check_launch("pt_swap");
+  if (args.T > 128) return fail(EB_ERR_UNSUPPORTED, "swap pass supports ladders of up to 128 temperatures (got %d)", args.T);
+  if (args.philox) return launch_swap_shape<true, SHARDED>(args, s);
+  return launch_swap_shape<false, SHARDED>(args, s);
 }
 
 }  // namespace eb

@@ -65,23 +65,41 @@ __device__ __forceinline__ void store_row(double* __restrict__ row, int LD, cons
 }
 
 // ---- box prior of one leaf --------------------------------------------------------------------
-template <int DMAX>
-__device__ __forceinline__ double box_logpdf_leaf(const double (&x)[DMAX], int off, int D,
-                                                  const double* __restrict__ lo,
+// EXACT: the row length equals DMAX at compile time (no runtime predicates on D).
+template <int DMAX, bool EXACT>
+__device__ __forceinline__ double box_logpdf_leaf(const double (&x)[DMAX], int D_, const double* __restrict__ lo,
                                                   const double* __restrict__ hi,
                                                   const double* __restrict__ lpdf) {
-  double out = 0.0;
+  const int D = EXACT ? DMAX : D_;
+  // common case first: every parameter inside its box -> the in-order sum of the per-parameter constants
+  // (prior.py:369-385 adds them in index order starting from 0.0); any finite value outside -> -inf
+  int nin = 0;
+  bool has_nan = false;
 #pragma unroll
-  for (int j = 0; j < DMAX; ++j) {
-    const int d = j - off;
-    if (d >= 0 && d < D) {
+  for (int j = 0; j < DMAX; ++j)
+    if (EXACT || j < D) {
+      const double v = x[j];
+      nin += (int)((v >= lo[j]) & (v <= hi[j]));
+      has_nan |= (v != v);
+    }
+  if (nin == D) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if (EXACT || j < D) s += lpdf[j];
+    return s;
+  }
+  if (!has_nan) return neg_inf();
+  double out = 0.0;  // NaN coordinate: that parameter contributes 0 (prior.py:80-88), the rest as usual
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j)
+    if (EXACT || j < D) {
       const double v = x[j];
       double t = 0.0;
-      if (v >= lo[d] && v <= hi[d]) t = lpdf[d];
-      if (v < lo[d] || v > hi[d]) t = neg_inf();
+      if (v >= lo[j] && v <= hi[j]) t = lpdf[j];
+      if (v < lo[j] || v > hi[j]) t = neg_inf();
       out += t;
     }
-  }
   return out;
 }
 
@@ -89,26 +107,31 @@ __device__ __forceinline__ double box_logpdf_leaf(const double (&x)[DMAX], int o
 template <int KIND>
 struct Like;
 
+// packed upper triangle, row i holds j = i..D-1
+__host__ __device__ __forceinline__ int sym_row_offset(int i, int D) { return i * D - (i * (i - 1)) / 2; }
+
 template <>
-struct Like<0> {  // EB_LIKE_GAUSSIAN: params mu[D], P[D*D]
-  template <int DMAX>
-  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D, const double* __restrict__ sp, int) {
+struct Like<0> {  // EB_LIKE_GAUSSIAN: staged params mu[D], S[D(D+1)/2] with S_ii = P_ii, S_ij = P_ij + P_ji (stage_params)
+  template <int DMAX, bool EXACT>
+  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D_, const double* __restrict__ sp, int) {
+    const int D = EXACT ? DMAX : D_;
     const double* mu = sp;
-    const double* P = sp + D;
+    const double* S = sp + D;
     double d[DMAX];
 #pragma unroll
-    for (int i = 0; i < DMAX; ++i) d[i] = (i < D) ? x[i] - mu[i] : 0.0;
-    // explicit FMAs (the build uses --fmad=false for the reference-ordered arithmetic of the proposal);
-    // two accumulators per row keep the dependent chains short
+    for (int i = 0; i < DMAX; ++i) d[i] = (EXACT || i < D) ? x[i] - mu[i] : 0.0;
+    // x^T P x = sum_i d_i (S_ii d_i + sum_{j>i} S_ij d_j): D(D+1)/2 explicit FMAs (the build uses --fmad=false for the
+    // reference-ordered arithmetic of the proposal); two accumulators per row keep the dependent chains short
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < DMAX; ++i) {
-      if (i < D) {
+      if (EXACT || i < D) {
+        const double* row = S + sym_row_offset(i, D) - i;   // row[j] = S_ij for j >= i
         double r0 = 0.0, r1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < DMAX; j += 2) {
-          if (j < D) r0 = fma(P[i * D + j], d[j], r0);
-          if (j + 1 < D) r1 = fma(P[i * D + j + 1], d[j + 1], r1);
+        for (int j = i; j < DMAX; j += 2) {
+          if (EXACT || j < D) r0 = fma(row[j], d[j], r0);
+          if (j + 1 < DMAX && (EXACT || j + 1 < D)) r1 = fma(row[j + 1], d[j + 1], r1);
         }
         acc = fma(d[i], r0 + r1, acc);
       }
@@ -119,12 +142,13 @@ struct Like<0> {  // EB_LIKE_GAUSSIAN: params mu[D], P[D*D]
 
 template <>
 struct Like<1> {  // EB_LIKE_ROSENBROCK
-  template <int DMAX>
-  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D, const double* __restrict__, int) {
+  template <int DMAX, bool EXACT>
+  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D_, const double* __restrict__, int) {
+    const int D = EXACT ? DMAX : D_;
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < DMAX - 1; ++i) {
-      if (i < D - 1) {
+      if (EXACT || i < D - 1) {
         const double a = x[i + 1] - x[i] * x[i];
         const double b = 1.0 - x[i];
         acc += 100.0 * (a * a) + b * b;
@@ -136,8 +160,9 @@ struct Like<1> {  // EB_LIKE_ROSENBROCK
 
 template <>
 struct Like<2> {  // EB_LIKE_GMIX: params logc[K], hinv[K], mu[K*D]
-  template <int DMAX>
-  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D, const double* __restrict__ sp, int K) {
+  template <int DMAX, bool EXACT>
+  static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D_, const double* __restrict__ sp, int K) {
+    const int D = EXACT ? DMAX : D_;
     const double* logc = sp;
     const double* hinv = sp + K;
     const double* mu = sp + 2 * K;
@@ -146,7 +171,7 @@ struct Like<2> {  // EB_LIKE_GMIX: params logc[K], hinv[K], mu[K*D]
       double r2 = 0.0;
 #pragma unroll
       for (int j = 0; j < DMAX; ++j)
-        if (j < D) {
+        if (EXACT || j < D) {
           const double dd = x[j] - mu[k * D + j];
           r2 += dd * dd;
         }

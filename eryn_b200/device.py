@@ -107,6 +107,12 @@ class DeviceContext(object):
     def iter_ptr(self):
         return C.c_void_p(self.ctrl.data_ptr() + _CTRL_ITER_OFF)
 
+    @property
+    def iter_next_ptr(self):
+        """eb_ctrl.iter_next: equals iter between iterations; the swap pass publishes iter+1 there before it releases
+        its programmatic dependents, so the next stretch kernel can start its draws early (pdl_chain)."""
+        return C.c_void_p(self.ctrl.data_ptr() + _lib.eb_ctrl.iter_next.offset)
+
     def read_ctrl(self):
         return _lib.eb_ctrl.from_buffer_copy(self.ctrl.cpu().numpy().tobytes())
 
@@ -114,6 +120,7 @@ class DeviceContext(object):
         c = self.read_ctrl()
         if iter is not None:
             c.iter = int(iter)
+            c.iter_next = int(iter)
         if time is not None:
             c.time = int(time)
         self.ctrl.copy_(torch.frombuffer(bytearray(bytes(c)), dtype=torch.uint8))
@@ -207,7 +214,8 @@ class DeviceContext(object):
         if replay is None:
             r.mode = _lib.EB_RNG_PHILOX
             r.seed = self.seed
-            r.iter_dev = self.iter_ptr
+            r.iter_dev = self.iter_next_ptr
+            r.pdl_chain = 1
         else:
             keep = dict(list=[self.to_dev(x, np.int32) for x in replay["lists"]],
                         rint=[self.to_dev(x, np.int64) for x in replay["rint"]],
@@ -229,7 +237,7 @@ class DeviceContext(object):
         _lib.check(self.lib.eb_stretch_step(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c),
                                             float(a), C.byref(r), _ptr(acc), _ptr(accepted_count),
                                             self.stream()), "eb_stretch_step")
-        self.launches += 1
+        self.launches += 1 if (W + 1) // 2 <= 128 else 2  # one launch per red/blue half (small ensembles: one CTA per temperature)
         return acc
 
     def stretch_step_split(self, d, a, randomize_split=True, replay=None, accepted_count=None):
@@ -301,6 +309,11 @@ class DeviceContext(object):
             r.mode = _lib.EB_RNG_REPLAY
             r.iperm, r.i1perm, r.u, r.next_pos, r.u_at = [_ptr(t) for t in keep]
             self.launches += 1 if T > 1 else 0
+        if d.inds is not None or L * D > 32 or T > 64:  # rows move through staging buffers (eb_swap_rng.row_scratch)
+            r.row_scratch = _ptr(self.scratch("swap_rows", (T, W, L, D), torch.float64))
+            r.logp_scratch = _ptr(self.scratch("swap_logp", (T, W), torch.float64))
+            if d.inds is not None:
+                r.inds_scratch = _ptr(self.scratch("swap_inds", (T, W, L), torch.uint8))
         ad = None
         if adapt is not None:
             ad = _lib.eb_adapt(int(adapt["adaptive"]), int(adapt["stop_adaptation"]), float(adapt["adaptation_lag"]),

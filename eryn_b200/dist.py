@@ -200,6 +200,7 @@ class ShardedRun(object):
             pb.logl_local = self.base + lay.logl[p]
             self._shard.append(sh)
             self._pub.append(pb)
+        ctx.write_ctrl(iter=0)  # the flag words count publish CTAs since iteration 0
         torch.cuda.synchronize(dev)
         dist.barrier(group)  # every arena is mapped and zeroed (flags = 0) before anyone publishes
 

@@ -32,10 +32,11 @@ extern "C" {
 #define EB_API
 #endif
 
-#define EB_ABI_VERSION 1
-#define EB_MAX_TEMPS 256
+#define EB_ABI_VERSION 2
+#define EB_MAX_TEMPS 128
 #define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
 #define EB_MAX_RANKS 16 /* GPUs of one temperature-sharded run */
+#define EB_SWAP_SLOTS 32
 
 typedef enum {
   EB_OK = 0,
@@ -48,7 +49,8 @@ typedef enum {
 typedef enum { EB_RNG_REPLAY = 0, EB_RNG_PHILOX = 1 } eb_rng_mode;
 
 #define EB_DEVERR_PEER_TIMEOUT 1u /* eb_ctrl.error: a peer's flag did not arrive within EB_PEER_TIMEOUT_NS */
-#define EB_PEER_TIMEOUT_NS 2000000000ull
+#define EB_DEVERR_SWAP_TIMEOUT 2u /* eb_ctrl.error: the swap pass never saw the counts of all its CTAs */
+#define EB_PEER_TIMEOUT_NS 2000000000ull /* nominal; the kernels count 4e9 SM cycles */
 
 /* device-side log-likelihood functors (SURVEY.md §8d synthetic targets) */
 typedef enum {
@@ -98,6 +100,10 @@ typedef struct {
 typedef struct {
   int32_t mode; /* eb_rng_mode */
   int32_t randomize_split; /* red_blue.py:123 (philox mode; replay encodes it in list) */
+  int32_t pdl_chain;       /* philox: the previous kernel on the stream is eb_pt_swap[_sharded] of the same eb_ctrl and
+                              iter_dev points at eb_ctrl.iter_next: the first half may then start its draws while that
+                              pass is still moving rows (programmatic dependent launch) */
+  int32_t _pad;
   const int32_t* list[2];  /* replay [T][Ns_s] */
   const int64_t* rint[2];  /* replay [T][Ns_s] */
   const double* u_z[2];    /* replay [T][Ns_s] */
@@ -129,6 +135,10 @@ typedef struct {
   const double* u;        /* replay [T][W] uniforms (log taken on device, :535) */
   int32_t* next_pos;      /* replay scratch [T][W] int32 */
   double* u_at;           /* replay scratch [T][W] */
+  double* row_scratch;    /* [T][W][L][D] staging of moved rows; needed when rows are longer than 32 doubles, the state
+                             has leaf flags, or T > 64 (else may be NULL) */
+  double* logp_scratch;   /* [T][W], with row_scratch */
+  uint8_t* inds_scratch;  /* [T][W][L], with row_scratch when the state has leaf flags */
   uint64_t seed;
   const uint64_t* iter_dev;
   uint64_t iter;
@@ -141,9 +151,14 @@ typedef struct {
   int64_t time;                         /* TemperatureControl.time */
   uint32_t ticket;                      /* last-block election */
   uint32_t error;                       /* 0, or EB_DEVERR_* set by a kernel (e.g. a peer never signalled) */
-  int32_t swaps_work[EB_MAX_TEMPS];     /* scratch, zero between passes */
+  int32_t swaps_work[EB_SWAP_SLOTS][EB_MAX_TEMPS]; /* scratch, zero between passes; CTAs spread their partial counts
+                                                      over the slots (same-address atomics serialise in L2) */
   int32_t swaps_accepted[EB_MAX_TEMPS]; /* result of the last pass, entry i-1 = rung i */
   uint64_t swaps_total[EB_MAX_TEMPS];   /* running sum */
+  uint32_t arrive[EB_SWAP_SLOTS];       /* swap pass: CTAs that have published their counts (spread like swaps_work) */
+  uint64_t iter_next;                   /* = iter between iterations; a swap pass sets it to iter+1 BEFORE it releases
+                                           its programmatic dependents, so the next move kernel can key its draws
+                                           while the pass still runs (eb_stretch_rng.pdl_chain) */
 } eb_ctrl;
 
 typedef struct {
@@ -193,10 +208,11 @@ EB_API int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt
  *      owns temperatures [temp_begin[g], temp_begin[g+1]) of all walkers).  The moves need
  *      no communication (red_blue.py:183-197 gathers along the walker axis only).  One iteration is
  *        move kernel (local)  ->  eb_publish_logl  ->  eb_pt_swap_sharded  ->  flip current/alternate
- *      eb_publish_logl is the all-gather of logl written as peer stores: every rank copies its rows into
- *      the `logl_all` buffer of EVERY rank over NVLink and then raises its flag word (value iter+1) on
- *      every rank.  eb_pt_swap_sharded first waits (bounded spin on LOCAL memory) until all flag words
- *      reached iter+1, then resolves the whole ladder redundantly from `logl_all` — decisions depend on
+ *      eb_publish_logl is the all-gather of logl written as peer stores: every CTA copies its slice of the
+ *      rank's rows into the `logl_all` buffer of EVERY rank over NVLink and then adds 1 to the rank's flag
+ *      word on every rank (release at system scope).  eb_pt_swap_sharded first waits (bounded spin on LOCAL
+ *      memory) until every flag word g reached (iter+1) * (CTAs of rank g's publish kernel), i.e. all of
+ *      iteration iter's rows have landed — ctrl->iter must be 0 when the flag words are zeroed —, then resolves the whole ladder redundantly from `logl_all` — decisions depend on
  *      logl only (tempering.py:538), so all ranks agree bit for bit on swap counts and on the adapted
  *      ladder — and writes ITS rungs into `dst` (its alternate buffers), pulling each source row from the
  *      CURRENT buffers of the rank that owns it (`*_src[g]` are peer-mapped device pointers; entry `rank`

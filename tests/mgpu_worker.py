@@ -13,9 +13,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
     ap.add_argument("--comm", default="p2p")
-    ap.add_argument("--T", type=int, default=4)
-    ap.add_argument("--W", type=int, default=256)
-    ap.add_argument("--d", type=int, default=8)
+    ap.add_argument("--ntemps", type=int, default=4)
+    ap.add_argument("--nwalkers", type=int, default=256)
+    ap.add_argument("--ndim", type=int, default=8)
     ap.add_argument("--nit", type=int, default=6)
     ap.add_argument("--seed", type=int, default=4242)
     ap.add_argument("--mix", type=int, default=0, help="1: stretch/gaussian schedule")
@@ -30,7 +30,7 @@ def main():
     from eryn_b200.likelihood import GaussianLikelihood
     from eryn_b200.moves import GaussianMove, StretchMove
     from eryn_b200.prior import ProbDistContainer, uniform_dist
-    T, W, d = a.T, a.W, a.d
+    T, W, d = a.ntemps, a.nwalkers, a.ndim
     A = np.random.RandomState(99).randn(d, d)
     P = np.linalg.inv(A @ A.T / d + np.eye(d))
     pri = ProbDistContainer({i: uniform_dist(-10.0, 10.0) for i in range(d)})

@@ -57,7 +57,7 @@ def test_sharded_run_matches_unsharded_oracle(tmp_path, comm, T, W, mix):
     d, nit, seed = 8, 6, 4242
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--out",
-           str(tmp_path), "--comm", comm, "--T", str(T), "--W", str(W), "--d", str(d), "--nit", str(nit), "--seed",
+           str(tmp_path), "--comm", comm, "--ntemps", str(T), "--nwalkers", str(W), "--ndim", str(d), "--nit", str(nit), "--seed",
            str(seed), "--mix", str(mix)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -12,3 +12,7 @@ nvcc -shared -o tools/_build/liberyn_b200_prof.so tools/_build/*.o -gencode arch
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I include tools/microbench.cu -L tools/_build -leryn_b200_prof \
      -Xlinker -rpath -Xlinker '$ORIGIN' -o tools/_build/microbench
 echo built tools/_build/microbench
+# the same benchmark against the PRODUCTION library (no phase timers): these are the timings to quote
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I include -DNO_MARKS tools/microbench.cu -L eryn_b200/lib -leryn_b200 \
+     -Xlinker -rpath -Xlinker '$ORIGIN/../../eryn_b200/lib' -o tools/_build/microbench_prod
+echo built tools/_build/microbench_prod

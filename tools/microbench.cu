@@ -17,8 +17,12 @@
 
 #include "eryn_b200.h"
 
+#ifndef NO_MARKS
 extern "C" int eb_debug_marks_stretch(long long* out_host);
 extern "C" int eb_debug_marks_swap(long long* out_host);
+extern "C" int eb_debug_marks_swap_global(unsigned long long* mn, unsigned long long* mx, int reset);
+extern "C" int eb_debug_marks_stretch_global(unsigned long long* mn, unsigned long long* mx, int reset);
+#endif
 
 #define CK(x)                                                                         \
   do {                                                                                \
@@ -127,7 +131,7 @@ int main(int argc, char** argv) {
   eb_like like{EB_LIKE_GAUSSIAN, 0, D + D * D, 0, lk};
   EB(eb_eval_state(&st, &prior, &like, s));
   eb_stretch_rng sr; std::memset(&sr, 0, sizeof(sr));
-  sr.mode = EB_RNG_PHILOX; sr.randomize_split = 1; sr.seed = 7; sr.iter_dev = &ctrl->iter;
+  sr.mode = EB_RNG_PHILOX; sr.randomize_split = 1; sr.seed = 7; sr.iter_dev = &ctrl->iter_next; sr.pdl_chain = 1;
   eb_swap_rng wr; std::memset(&wr, 0, sizeof(wr));
   wr.mode = EB_RNG_PHILOX; wr.permute = 1; wr.seed = 7; wr.iter_dev = &ctrl->iter;
   eb_adapt ad{1, -1, 10000.0, 100.0};
@@ -135,6 +139,7 @@ int main(int argc, char** argv) {
   gr.mode = EB_RNG_PHILOX; gr.cov_kind = 0; gr.scale = 0.1; gr.seed = 7; gr.iter_dev = &ctrl->iter;
 
   std::printf("eb_stretch_step (both halves)   : %.2f us/launch\n", time_graph(s, N, [&] { EB(eb_stretch_step(&st, &prior, &like, 2.0, &sr, acc, cnt, s)); }));
+  std::printf("eb_stretch_step, no count buffer: %.2f us/launch\n", time_graph(s, N, [&] { EB(eb_stretch_step(&st, &prior, &like, 2.0, &sr, acc, nullptr, s)); }));
   eb_stretch_rng sr0 = sr; sr0.randomize_split = 0;
   std::printf("eb_stretch_step no-randomize    : %.2f us/launch\n", time_graph(s, N, [&] { EB(eb_stretch_step(&st, &prior, &like, 2.0, &sr0, acc, cnt, s)); }));
   std::printf("eb_gaussian_step                : %.2f us/launch\n", time_graph(s, N, [&] { EB(eb_gaussian_step(&st, &prior, &like, &gr, acc, cnt, s)); }));
@@ -145,21 +150,80 @@ int main(int argc, char** argv) {
     EB(eb_pt_swap(&st, &wr, &ad, ctrl, s));
   }));
 
+  // ---- the sharded pass on ONE GPU (world = 1: publish to self, every row rewritten into the alternate buffers) -------
+  {
+    double *coords2, *logl2, *logp2, *logl_all, *betas_all;
+    unsigned long long* flags;
+    CK(cudaMalloc(&coords2, n * D * 8)); CK(cudaMalloc(&logl2, n * 8)); CK(cudaMalloc(&logp2, n * 8));
+    CK(cudaMalloc(&logl_all, n * 8)); CK(cudaMalloc(&betas_all, T * 8)); CK(cudaMalloc(&flags, 16 * 8));
+    CK(cudaMemset(flags, 0, 16 * 8));
+    CK(cudaMemcpy(betas_all, hb.data(), T * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctrl, 0, sizeof(eb_ctrl)));
+    eb_state cur = st, alt = st;
+    alt.coords = coords2; alt.logl = logl2; alt.logp = logp2;
+    cur.betas = betas_all; alt.betas = betas_all;
+    eb_swap_rng wr2 = wr;
+    auto one = [&](bool with_publish) {
+      eb_publish pb; std::memset(&pb, 0, sizeof(pb));
+      pb.rank = 0; pb.world = 1; pb.ntemps_total = T; pb.nwalkers = W; pb.temp_begin[0] = 0; pb.temp_begin[1] = T;
+      pb.logl_local = cur.logl; pb.logl_all_peer[0] = logl_all; pb.flags_peer[0] = (uint64_t*)flags;
+      if (with_publish) EB(eb_publish_logl(&pb, ctrl, s));
+      eb_shard sh; std::memset(&sh, 0, sizeof(sh));
+      sh.rank = 0; sh.world = 1; sh.ntemps_total = T; sh.temp_begin[0] = 0; sh.temp_begin[1] = T;
+      sh.coords_src[0] = cur.coords; sh.logp_src[0] = cur.logp; sh.logl_all = with_publish ? logl_all : cur.logl;
+      sh.betas_all = betas_all; sh.flags = with_publish ? (const uint64_t*)flags : nullptr;
+      EB(eb_pt_swap_sharded(&sh, &alt, &wr2, &ad, ctrl, s));
+      std::swap(cur, alt);
+    };
+    // an even number of iterations per graph so that the buffers are back in place at every replay
+    std::printf("sharded swap, world=1, no publish : %.2f us/launch\n", time_graph(s, N, [&] { one(false); }));
+    std::printf("publish alone                     : %.2f us/launch\n", time_graph(s, N, [&] {
+      eb_publish pb; std::memset(&pb, 0, sizeof(pb));
+      pb.rank = 0; pb.world = 1; pb.ntemps_total = T; pb.nwalkers = W; pb.temp_begin[0] = 0; pb.temp_begin[1] = T;
+      pb.logl_local = cur.logl; pb.logl_all_peer[0] = logl_all; pb.flags_peer[0] = (uint64_t*)flags;
+      EB(eb_publish_logl(&pb, ctrl, s));
+    }));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaMemset(ctrl, 0, sizeof(eb_ctrl))); CK(cudaMemset(flags, 0, 16 * 8));   // flag words count publish CTAs since iteration 0
+    std::printf("publish + sharded swap, world=1   : %.2f us/pair\n", time_graph(s, N, [&] { one(true); }));
+  }
+#ifndef NO_MARKS
+  // ---- globaltimer spread of the marks over all CTAs of ONE launch (ns relative to the first CTA's first mark) ------
+  {
+    unsigned long long mn[64], mx[64];
+    CK(cudaStreamSynchronize(s));
+    eb_debug_marks_swap_global(mn, mx, 1);
+    EB(eb_pt_swap(&st, &wr, &ad, ctrl, s));
+    CK(cudaStreamSynchronize(s));
+    if (eb_debug_marks_swap_global(mn, mx, 0) == 0) {
+      std::printf("swap marks, ns since CTA 0 start [CTA 0 .. adapt CTA]:");
+      for (int i = 16; i <= 25; ++i) if (i != 22) std::printf(" m%d=%llu", i, mn[i] - mn[16]);
+      std::printf(" adapt-CTA-end=%llu", mx[23] - mn[16]);
+      std::printf("\n");
+    }
+    eb_debug_marks_stretch_global(mn, mx, 1);
+    EB(eb_stretch_step(&st, &prior, &like, 2.0, &sr, acc, cnt, s));
+    CK(cudaStreamSynchronize(s));
+    if (eb_debug_marks_stretch_global(mn, mx, 0) == 0) {
+      std::printf("stretch marks (both launches), ns since first CTA start [first .. last]:");
+      for (int i = 0; i <= 7; ++i) if (i != 5) std::printf(" m%d=[%llu..%llu]", i, mn[i] - mn[0], mx[i] - mn[0]);
+      std::printf("\n");
+    }
+  }
   // ---- phase marks (profiling build) ---------------------------------------------------------------
   long long m[64];
   EB(eb_stretch_step(&st, &prior, &like, 2.0, &sr, acc, cnt, s));
   EB(eb_pt_swap(&st, &wr, &ad, ctrl, s));
   CK(cudaStreamSynchronize(s));
   if (eb_debug_marks_stretch(m) == 0) {
-    const char* sn[] = {"start", "rng-init", "prepare x2", "stage params", "finish half 0", "(loop)", "cluster barrier", "finish half 1"};
-    std::printf("stretch CTA(0,0) cycles: ");
-    for (int i = 1; i < 8; ++i) std::printf("%s=%lld ", sn[i], m[i] - m[i - 1]);
-    std::printf(" total=%lld\n", m[7] - m[0]);
+    std::printf("stretch CTA(0,0) thread 0 (split 0) cycles: rng-init=%lld prepare=%lld stage params=%lld finish=%lld barrier=%lld total=%lld\n",
+                m[1] - m[0], m[2] - m[1], m[3] - m[2], m[6] - m[4], m[7] - m[6], m[7] - m[0]);
     EB(eb_debug_marks_swap(m));
     const char* wn[] = {"start", "phase0 keys", "phase1 pos/logl/logu", "phase2 cascade", "counts", "phase3 rows", "tail-last"};
     std::printf("swap    CTA 0 cycles   : ");
     for (int i = 17; i <= 22; ++i) std::printf("%s=%lld ", wn[i - 16], m[i] - m[i - 1]);
     std::printf(" total=%lld\n", m[22] - m[16]);
   }
+#endif
   return 0;
 }
