@@ -44,12 +44,13 @@ def corr_prec(d, seed=99):
 def workload(name, ngpus=1):
     """returns dict(T, W, d, lo, hi, like=('gauss'|'rosen'|'gmix', params...), moves, weights, label)"""
     if name == "c2":
-        T, W, d = 16, 4096 * ngpus, 8
+        # N > 1: weak scaling along the sharded axis — every GPU owns 16 temperatures of 4096 walkers
+        T, W, d = 16 * ngpus, 4096, 8
         return dict(T=T, W=W, d=d, lo=-10.0, hi=10.0, like=("gauss", np.zeros(d), corr_prec(d)),
                     moves=[dict(kind="stretch", a=2.0)], weights=[1.0],
                     label=f"C2: {T} temps x {W} walkers x {d}-d correlated Gaussian, StretchMove + PT swaps")
     if name == "c3":
-        T, W, d = 16, 4096 * ngpus, 8
+        T, W, d = 16 * ngpus, 4096, 8
         return dict(T=T, W=W, d=d, lo=-10.0, hi=10.0, like=("rosen",),
                     moves=[dict(kind="stretch", a=2.0), dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.1))],
                     weights=[0.5, 0.5],
@@ -197,19 +198,26 @@ def run_gpu(args):
         res = run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=ClockSampler, comm=args.comm)
         if rank == 0:
             peak, peak_src = measured_peak_gbs()
+            roof = None
+            if res.get("k1_us"):
+                b = (24 * d + 41) * res["local_temps"] * W
+                a = b / (res["k1_us"] * 1e-6) / 1e9
+                roof = dict(bound="hbm", kernel="stretch_step_kernel (rank 0's temperatures, both launches of one step)",
+                            achieved=round(a, 1), peak=peak, unit="GB/s", frac=round(a / peak, 4), traffic=None,
+                            peak_source=peak_src, algorithmic_bytes_per_launch=b, avg_launch_us=round(res["k1_us"], 3))
             out = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                        ms_per_step=res["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
                        dtype="f64", data="synthetic",
                        config=dict(workload=wl["label"], ntemps=T, nwalkers=W, ndim=d, rng="philox",
                                    parallelism=f"temperature-sharded x{world} (temp_begin={res['temp_begin']}), "
-                                               f"walkers grow with N (4096 per GPU-equivalent)",
+                                               f"weak scaling: 16 temperatures x 4096 walkers per GPU",
                                    comm=("NVLink peer stores + flag words, no NCCL on the data path" if res["comm"] == "p2p"
                                          else "NCCL all_gather of logl + NVLink peer row pulls"),
                                    l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
                                    step="one iteration = move kernel + publish kernel + sharded swap/adapt kernel"
                                         + (" (CUDA graph replay)" if res["graph"] else "")),
                        clocks=res["clocks"], e2e=dict(unit=UNIT, **res["e2e"]), gpu_launches=res["launches"],
-                       roofline=None, cpu_baseline=None,
+                       roofline=roof, cpu_baseline=None,
                        extra=dict(ms_per_step_resident_no_flush=res["resident_ms"],
                                   value_resident_no_flush=T * W / (res["resident_ms"] * 1e-3),
                                   betas_cold_hot=res["betas"], swaps_accepted_last=res["swaps"],
@@ -289,31 +297,61 @@ def run_gpu(args):
     value = T * W * args.steps / (total_ms * 1e-3)
     resident_ms = e0.elapsed_time(e1) / args.steps
 
-    # ---- roofline of the dominant kernel: fused stretch half step ---------------------------------------
-    nrep = 100
+    # ---- roofline of the dominant kernel: the fused stretch step (two launches: red half, blue half) ------------------
+    def stretch_us(ctx_, ds_, cnt_, nrep):
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            ctx_.stretch_step(ds_, 2.0, accepted_count=cnt_)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gk, stream=stream):
+                for r in range(nrep):
+                    ctx_.stretch_step(ds_, 2.0, accepted_count=cnt_)
+            gk.replay()
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            gk.replay()
+            k1.record(stream)
+            torch.cuda.synchronize()
+        return k0.elapsed_time(k1) * 1e3 / nrep
+
     st_move = [m for m in moves if isinstance(m, StretchMove)][0]
     cnt = st_move._count_buffer(ctx, T, W)
-    gk = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(stream):
-        with torch.cuda.graph(gk, stream=stream):
-            for r in range(nrep):
-                ctx.stretch_step(ds, 2.0, accepted_count=cnt)
-        gk.replay()
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record(stream)
-        gk.replay()
-        k1.record(stream)
-        torch.cuda.synchronize()
-    k_us = k0.elapsed_time(k1) * 1e3 / nrep
+    k_us = stretch_us(ctx, ds, cnt, 100)
     D = d
-    alg_bytes = (24 * D + 41) * T * W  # 24*D+41 B per walker-update; one launch updates all T*W walkers
+    alg_bytes = (24 * D + 41) * T * W  # 24*D+41 B per walker-update; one step updates all T*W walkers
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (k_us * 1e-6) / 1e9
-    roofline = dict(bound="hbm", kernel="stretch_step_kernel", achieved=round(achieved, 1), peak=peak, unit="GB/s",
-                    frac=round(achieved / peak, 4), traffic=None, peak_source=peak_src,
+    traffic = None  # DRAM bytes per stretch step from the committed ncu --set full capture of this workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.workload]
+        traffic = tr["launches_per_step"] * (tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"])
+    except Exception:
+        pass
+    roofline = dict(bound="hbm", kernel="stretch_step_kernel (both red/blue launches of one step)", achieved=round(achieved, 1),
+                    peak=peak, unit="GB/s", frac=round(achieved / peak, 4), traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes, avg_launch_us=round(k_us, 3),
-                    note="state (4.3 MB at C2) is L2-resident across launches; back-to-back launches in one graph")
+                    note="per stretch step = 2 launches; state (4.7 MB at C2) is L2-resident across launches, so this is an "
+                         "algorithmic-bytes rate against the HBM peak, limited by launch/dependency latency at this size; "
+                         "extra.roofline_c4 is the same kernel on the HBM-sized config-4 working set")
+    # the same kernel where the working set exceeds what one launch can hide behind latency: BASELINE config 4 on one GPU
+    roofline_c4 = None
+    if not args.profile:
+        wl4 = workload("c4")
+        pri4 = ProbDistContainer({i: uniform_dist(wl4["lo"], wl4["hi"]) for i in range(wl4["d"])})
+        ctx4 = DeviceContext(pri4, device_like(wl4), device=dev, rng="philox", seed=7)
+        tc4 = TemperatureControl(wl4["d"], wl4["W"], ntemps=wl4["T"])
+        tc4.bind(ctx4)
+        ds4 = ctx4.upload(State(initial_coords(wl4)), betas=tc4.betas_dev)
+        ctx4.eval_state(ds4)
+        cnt4 = torch.zeros((wl4["T"], wl4["W"]), dtype=torch.int32, device=dev)
+        k4_us = stretch_us(ctx4, ds4, cnt4, 20)
+        b4 = (24 * wl4["d"] + 41) * wl4["T"] * wl4["W"]
+        a4 = b4 / (k4_us * 1e-6) / 1e9
+        roofline_c4 = dict(workload=wl4["label"], kernel="stretch_step_kernel", achieved=round(a4, 1), peak=peak, unit="GB/s",
+                           frac=round(a4 / peak, 4), algorithmic_bytes_per_launch=b4, avg_launch_us=round(k4_us, 2),
+                           walker_updates_per_s=wl4["T"] * wl4["W"] / (k4_us * 1e-6))
+        del ds4, ctx4, cnt4
 
     # ---- e2e: C-ABI call with HOST buffers, one iteration per call ------------------------------------------
     lib = _lib.load()
@@ -358,10 +396,10 @@ def run_gpu(args):
                dtype="f64", data="synthetic",
                config=dict(workload=wl["label"], ntemps=T, nwalkers=W, ndim=d, rng="philox",
                            l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
-                           step="one iteration = 1 fused stretch kernel (both red/blue halves) + 1 swap/adapt kernel (CUDA graph replay)"),
+                           step="one iteration = stretch step (red launch + blue launch chained by programmatic dependent launch) + 1 swap/adapt kernel (CUDA graph replay)"),
                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                extra=dict(ms_per_step_resident_no_flush=resident_ms,
-                          value_resident_no_flush=T * W / (resident_ms * 1e-3),
+                          value_resident_no_flush=T * W / (resident_ms * 1e-3), roofline_c4=roofline_c4,
                           wall_s_timed_region=t_wall, betas_cold_hot=[float(tc.betas[0]), float(tc.betas[-1])],
                           swaps_accepted_last=tc.swaps_accepted.tolist()[:4]))
     print(json.dumps(out))

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "liberyn_b200.so")
+LIB_PATH = os.environ.get("ERYN_B200_LIB") or os.path.join(HERE, "lib", "liberyn_b200.so")  # override: profiling build
 
 EB_MAX_TEMPS = 128
 EB_MAX_ROW = 32

@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const SwapArgs p)
     __syncthreads();
     if (!s_ok) return;
   }
+  EB_MARK(26);
   for (int r = tid; r < T; r += blockDim.x) {   // the ladder is adapted by the previous pass: read after the wait
     const double b = p.betas[r];
     s_betas[r] = b;

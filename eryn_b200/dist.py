@@ -417,6 +417,25 @@ def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm
         torch.cuda.synchronize()
         dist.barrier()
     run.check()
+    # the dominant kernel alone (this rank's temperatures): back-to-back stretch steps in one graph
+    st_moves = [m for m in moves if isinstance(m, StretchMove)]
+    k1_us = None
+    if st_moves:
+        nrep = 50
+        cnt = st_moves[0]._count_buffer(ctx, run.t_hi - run.t_lo, W)
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(gk, stream=stream):
+                for _ in range(nrep):
+                    ctx.stretch_step(run.current, 2.0, accepted_count=cnt)
+            gk.replay()
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            gk.replay()
+            k1.record(stream)
+            torch.cuda.synchronize()
+        k1_us = k0.elapsed_time(k1) * 1e3 / nrep
     clocks = clk.summary() if clk is not None else None
     total_ms = float(sum(a.elapsed_time(b) for a, b in evs))
     resident_ms = e0.elapsed_time(e1)
@@ -459,6 +478,6 @@ def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm
                             d2h_bytes_per_step=int(shard_bytes * world),
                             api="per rank: pinned host shard -> H2D -> move + publish + sharded swap -> D2H, every step"),
                    swaps=swaps, betas=[float(betas[0]), float(betas[-1])], temp_begin=run.temp_begin, comm=comm,
-                   graph=use_graph)
+                   graph=use_graph, k1_us=k1_us, local_temps=run.t_hi - run.t_lo)
     run.close()
     return out

@@ -1,5 +1,2 @@
-mkdir -p gpurun_out
-timeout 120 tools/_build/microbench_prod 16 8192 8 | grep -E "shape|sharded|publish|eb_pt_swap"
-timeout 600 python -m pytest tests/test_mgpu.py -m gpu -x -q 2>&1 | tail -3
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/shard_breakdown.py 2>&1 | grep "rank"
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 200 --warmup 10 2>/dev/null | cut -c1-300

@@ -27,7 +27,7 @@ def main():
     from eryn_b200.likelihood import GaussianLikelihood
     from eryn_b200.moves import StretchMove
     from eryn_b200.prior import ProbDistContainer, uniform_dist
-    T, W, d = 16, 4096 * world, 8
+    T, W, d = 16 * world, 4096, 8
     A = np.random.RandomState(99).randn(d, d)
     P = np.linalg.inv(A @ A.T / d + np.eye(d))
     pri = ProbDistContainer({i: uniform_dist(-10.0, 10.0) for i in range(d)})
@@ -74,6 +74,15 @@ def main():
         print(f"[{comm}] rank {rank}: move {np.median(seg[:, 0]):.1f} us, publish/all-gather {np.median(seg[:, 1]):.1f} us, "
               f"sharded swap (incl. wait for peers) {np.median(seg[:, 2]):.1f} us; iteration-to-iteration {np.median(tot):.1f} us "
               f"(host-paced, no graph)", flush=True)
+        if os.environ.get("ERYN_B200_LIB"):
+            import ctypes
+            mn = (ctypes.c_uint64 * 64)()
+            mx = (ctypes.c_uint64 * 64)()
+            if run.lib.eb_debug_marks_swap_global(mn, mx, 0) == 0:
+                base = mn[16]
+                print(f"[{comm}] rank {rank} last swap kernel, CTA 0, ns since its start: " +
+                      " ".join(f"m{i}={mn[i] - base}" for i in (17, 26, 18, 19, 20, 24, 25, 21)) +
+                      f" adapt-CTA-end={mx[23] - base}", flush=True)
         dist.barrier()
         run.close()
     dist.destroy_process_group()
