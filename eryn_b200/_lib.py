@@ -24,7 +24,7 @@ vp = C.c_void_p
 
 class eb_state(C.Structure):
     _fields_ = [("ntemps", C.c_int32), ("nwalkers", C.c_int32), ("nleaves", C.c_int32), ("ndim", C.c_int32),
-                ("temp_offset", C.c_int32), ("_pad", C.c_int32),
+                ("temp_offset", C.c_int32), ("inds_stride", C.c_int32),
                 ("coords", vp), ("logl", vp), ("logp", vp), ("inds", vp), ("betas", vp)]
 
 
@@ -90,6 +90,39 @@ class eb_publish(C.Structure):
                 ("logl_local", vp), ("logl_all_peer", vp * EB_MAX_RANKS), ("flags_peer", vp * EB_MAX_RANKS)]
 
 
+EB_MAX_BRANCHES = 4
+EB_PULSE_GAUSS, EB_PULSE_SINE = 0, 1
+_i4 = C.c_int32 * EB_MAX_BRANCHES
+
+
+class eb_mb_layout(C.Structure):
+    _fields_ = [("nbranches", C.c_int32), ("nfriends", C.c_int32), ("nleaves", _i4), ("ndim", _i4), ("nleaves_min", _i4),
+                ("kind", _i4), ("friend_key", _i4)]
+
+
+class eb_mb_state(C.Structure):
+    _fields_ = [("ntemps", C.c_int32), ("nwalkers", C.c_int32), ("temp_offset", C.c_int32), ("_pad", C.c_int32),
+                ("coords", vp), ("logl", vp), ("logp", vp), ("aux", vp), ("betas", vp)]
+
+
+class eb_pulse_data(C.Structure):
+    _fields_ = [("nt", C.c_int32), ("_pad", C.c_int32), ("sigma", C.c_double), ("t", vp), ("y", vp)]
+
+
+class eb_mb_friends(C.Structure):
+    _fields_ = [("nfr", _i4), ("coords", vp * EB_MAX_BRANCHES), ("keys", vp * EB_MAX_BRANCHES)]
+
+
+class eb_mb_group_rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("_pad", C.c_int32), ("pick", vp), ("u_z", vp), ("u_acc", vp),
+                ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+
+
+class eb_mb_rj_rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("_pad", C.c_int32), ("change", vp), ("leaf", vp), ("birth", vp * EB_MAX_BRANCHES),
+                ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+
+
 # every symbol include/eryn_b200.h declares: name -> (restype, argtypes)
 P = C.POINTER
 SYMBOLS = {
@@ -109,6 +142,13 @@ SYMBOLS = {
     "eb_ipc_export": (C.c_int, [vp, vp]),
     "eb_ipc_open": (C.c_int, [vp, P(vp)]),
     "eb_ipc_close": (C.c_int, [vp]),
+    "eb_mb_eval_state": (C.c_int, [P(eb_mb_layout), P(eb_mb_state), P(eb_prior), P(eb_pulse_data), vp]),
+    "eb_mb_friends_update": (C.c_int, [P(eb_mb_layout), P(eb_mb_state), P(eb_mb_friends), C.c_int32, vp]),
+    "eb_mb_group_stretch": (C.c_int, [P(eb_mb_layout), P(eb_mb_state), P(eb_prior), P(eb_pulse_data), P(eb_mb_friends),
+                                      C.c_double, P(eb_mb_group_rng), vp, vp, vp]),
+    "eb_mb_rj_step": (C.c_int, [P(eb_mb_layout), P(eb_mb_state), P(eb_prior), P(eb_pulse_data), P(eb_mb_rj_rng), vp, vp,
+                                vp]),
+    "eb_mb_aux_stride": (C.c_int32, [P(eb_mb_layout)]),
     "eb_advance_iter": (C.c_int, [vp, vp]),
     "eb_stretch_propose": (C.c_int, [P(eb_state), C.c_double, C.c_int32, P(eb_stretch_rng), vp, vp, vp, vp]),
     "eb_accept_update": (C.c_int, [P(eb_state), vp, C.c_int32, vp, vp, vp, vp, C.c_int32, P(eb_stretch_rng),
@@ -118,7 +158,7 @@ SYMBOLS = {
 }
 
 STRUCTS = [eb_state, eb_prior, eb_like, eb_stretch_rng, eb_gauss_rng, eb_swap_rng, eb_ctrl, eb_adapt, eb_host_job,
-           eb_shard, eb_publish]
+           eb_shard, eb_publish, eb_mb_layout, eb_mb_state, eb_pulse_data, eb_mb_friends, eb_mb_group_rng, eb_mb_rj_rng]
 
 _lib = None
 

@@ -24,6 +24,7 @@ class Backend(object):
         self.iteration = 0
         self.accepted = np.zeros((self.ntemps, self.nwalkers), dtype=int)
         self.swaps_accepted = np.zeros((self.ntemps - 1,), dtype=int)
+        self.rj_accepted = np.zeros((self.ntemps, self.nwalkers), dtype=int) if rj else None
         self.chain = {n: np.empty((0, self.ntemps, self.nwalkers, self.nleaves_max[n], self.ndims[n]))
                       for n in self.branch_names}
         self.inds = {n: np.empty((0, self.ntemps, self.nwalkers, self.nleaves_max[n]), dtype=bool)
@@ -67,6 +68,8 @@ class Backend(object):
         self.accepted += np.asarray(accepted).astype(int)
         if swaps_accepted is not None:
             self.swaps_accepted += np.asarray(swaps_accepted).astype(int)
+        if rj_accepted is not None and self.rj_accepted is not None:
+            self.rj_accepted += np.asarray(rj_accepted).astype(int)
         if moves_accepted_fraction is not None:
             for k, v in moves_accepted_fraction.items():
                 self.move_info[k]["acceptance_fraction"][:] = v
@@ -81,6 +84,10 @@ class Backend(object):
 
     def get_inds(self, thin=1, discard=0):
         return {n: self._get(self.inds[n], thin, discard) for n in self.branch_names}
+
+    def get_nleaves(self, thin=1, discard=0):
+        """backend.py:590-614: number of active leaves per walker"""
+        return {n: v.sum(axis=-1) for n, v in self.get_inds(thin, discard).items()}
 
     def get_log_like(self, thin=1, discard=0):
         return self._get(self.log_like, thin, discard)

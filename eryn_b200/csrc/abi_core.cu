@@ -77,6 +77,7 @@ int fill_common(Common& c, const eb_state* st, const eb_prior* prior, const eb_l
   c.inds = const_cast<uint8_t*>(st->inds); c.betas = st->betas;
   c.T = st->ntemps; c.W = st->nwalkers; c.L = st->nleaves; c.D = st->ndim; c.LD = st->nleaves * st->ndim;
   c.t0 = st->temp_offset;
+  c.Lb = st->inds_stride > 0 ? st->inds_stride : st->nleaves;
   c.lo = c.hi = c.lpdf = nullptr; c.like_params = nullptr; c.like_nparams = 0; c.like_ncomp = 0;
   if (prior) { c.lo = prior->lo; c.hi = prior->hi; c.lpdf = prior->logpdf; }
   c.like_kind = -1;
@@ -138,6 +139,12 @@ size_t eb_struct_size(int which) {
     case 8: return sizeof(eb_host_job);
     case 9: return sizeof(eb_shard);
     case 10: return sizeof(eb_publish);
+    case 11: return sizeof(eb_mb_layout);
+    case 12: return sizeof(eb_mb_state);
+    case 13: return sizeof(eb_pulse_data);
+    case 14: return sizeof(eb_mb_friends);
+    case 15: return sizeof(eb_mb_group_rng);
+    case 16: return sizeof(eb_mb_rj_rng);
     default: return 0;
   }
 }

@@ -77,6 +77,7 @@ static __device__ unsigned long long eb_dbg_gmin[64], eb_dbg_gmax[64];   // glob
 struct Common {
   double* coords; double* logl; double* logp; uint8_t* inds; double* betas;
   int T, W, L, D, LD;
+  int Lb;  // bytes per walker of `inds` (leaf flags, or flags + friend table of a multi-branch state)
   int t0;  // global index of local temperature 0 (random-stream keying)
   const double* lo; const double* hi; const double* lpdf;
   const double* like_params; int like_nparams, like_ncomp, like_kind;

@@ -86,6 +86,15 @@ __device__ __forceinline__ int swap_source(unsigned long long lo, unsigned long 
   return o;
 }
 
+// the per-walker byte payload that travels with a row (leaf flags, friend table): word copies when aligned
+__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int n) {
+  if (((n | (int)(reinterpret_cast<size_t>(dst) | reinterpret_cast<size_t>(src))) & 3) == 0) {
+    for (int i = 0; i < n; i += 4) *reinterpret_cast<uint32_t*>(dst + i) = *reinterpret_cast<const uint32_t*>(src + i);
+  } else {
+    for (int i = 0; i < n; ++i) dst[i] = src[i];
+  }
+}
+
 // copy one row between distinct slots through registers; LD is a runtime value
 __device__ __forceinline__ void copy_row(double* __restrict__ dst, const double* __restrict__ src, int LD) {
   if ((LD & 3) == 0) {
@@ -179,7 +188,7 @@ template <bool PHILOX, bool SHARDED, int CL, int RR, int RPL>
 __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const SwapArgs p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const Common& c = p.c;
-  const int T = p.T, W = c.W, LD = c.LD, L = c.L, cpb = p.cpb;
+  const int T = p.T, W = c.W, LD = c.LD, L = c.Lb, cpb = p.cpb;
   const SwapLayout lay = swap_layout(T, cpb);
   double* s_betas = reinterpret_cast<double*>(smraw + lay.betas);
   double* s_dts = reinterpret_cast<double*>(smraw + lay.dts);
@@ -438,8 +447,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const SwapArgs p)
         const size_t sslot = (size_t)s * W + pos[s], dslot = (size_t)r * W + pos[r];
         copy_row(p.scratch_coords + dslot * LD, c.coords + sslot * LD, LD);
         p.scratch_logp[dslot] = c.logp[sslot];
-        if (c.inds)
-          for (int l = 0; l < L; ++l) p.scratch_inds[dslot * L + l] = c.inds[sslot * L + l];
+        if (c.inds) copy_bytes(p.scratch_inds + dslot * L, c.inds + sslot * L, L);
       }
       __syncwarp();
       for (int r = lane; valid && r < T; r += CL) {
@@ -449,8 +457,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const SwapArgs p)
         copy_row(c.coords + dslot * LD, p.scratch_coords + dslot * LD, LD);
         c.logp[dslot] = p.scratch_logp[dslot];
         c.logl[dslot] = ll[s];
-        if (c.inds)
-          for (int l = 0; l < L; ++l) c.inds[dslot * L + l] = p.scratch_inds[dslot * L + l];
+        if (c.inds) copy_bytes(c.inds + dslot * L, p.scratch_inds + dslot * L, L);
       }
     }
   } else if (valid) {
@@ -467,8 +474,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const SwapArgs p)
       copy_row(c.coords + dslot * LD, p.coords_src[gsrc] + sslot * LD, LD);
       c.logp[dslot] = p.logp_src[gsrc][sslot];
       c.logl[dslot] = ll[s];
-      if (c.inds)
-        for (int l = 0; l < L; ++l) c.inds[dslot * L + l] = p.inds_src[gsrc][sslot * L + l];
+      if (c.inds) copy_bytes(c.inds + dslot * L, p.inds_src[gsrc] + sslot * L, L);
     }
   }
 

@@ -38,7 +38,7 @@ class DeviceState(object):
 
     def c_struct(self):
         T, W, L, D = self.shape
-        st = _lib.eb_state(T, W, L, D, self.temp_offset, 0, _ptr(self.coords), _ptr(self.logl), _ptr(self.logp),
+        st = _lib.eb_state(T, W, L, D, self.temp_offset, getattr(self, "inds_stride", 0), _ptr(self.coords), _ptr(self.logl), _ptr(self.logp),
                            _ptr(self.inds), _ptr(self.betas))
         return st
 
@@ -56,12 +56,7 @@ class DeviceContext(object):
                           consume them (bit-identical accept masks to the reference)."""
 
     def __init__(self, priors, log_like_fn, device=None, rng="philox", seed=0, branch_name="model_0"):
-        self.lib = _lib.require_device()
-        if rng not in ("philox", "numpy-replay"):
-            raise ValueError("rng must be 'philox' or 'numpy-replay'")
-        self.rng = rng
-        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._init_common(device, rng, seed)
         self.branch_name = branch_name
         if isinstance(priors, dict):
             priors = priors[branch_name]
@@ -84,6 +79,14 @@ class DeviceContext(object):
             self.fused = False
         else:
             raise ValueError("log_like_fn must be a DeviceLikelihood or a callable on CUDA tensors")
+
+    def _init_common(self, device, rng, seed):
+        self.lib = _lib.require_device()
+        if rng not in ("philox", "numpy-replay"):
+            raise ValueError("rng must be 'philox' or 'numpy-replay'")
+        self.rng = rng
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.ctrl = torch.zeros(self.lib.eb_ctrl_size(), dtype=torch.uint8, device=self.device)
         self._scratch = {}
         self.launches = 0  # kernels launched through this context (bench.py reports it)
@@ -313,7 +316,7 @@ class DeviceContext(object):
             r.row_scratch = _ptr(self.scratch("swap_rows", (T, W, L, D), torch.float64))
             r.logp_scratch = _ptr(self.scratch("swap_logp", (T, W), torch.float64))
             if d.inds is not None:
-                r.inds_scratch = _ptr(self.scratch("swap_inds", (T, W, L), torch.uint8))
+                r.inds_scratch = _ptr(self.scratch("swap_inds", (T, W, getattr(d, "inds_stride", 0) or L), torch.uint8))
         ad = None
         if adapt is not None:
             ad = _lib.eb_adapt(int(adapt["adaptive"]), int(adapt["stop_adaptation"]), float(adapt["adaptation_lag"]),

@@ -55,8 +55,7 @@ class EnsembleSampler(object):
                  fill_zero_leaves_val=-1e300, num_repeats_in_model=1, track_moves=True, info={},
                  rng="philox", seed=None, device=None):
         for name, val in (("provide_groups", provide_groups), ("provide_supplemental", provide_supplemental),
-                          ("pool", pool), ("rj_moves", rj_moves), ("periodic", periodic), ("args", args),
-                          ("kwargs", kwargs)):
+                          ("pool", pool), ("periodic", periodic), ("args", args), ("kwargs", kwargs)):
             if val:
                 raise NotImplementedError(f"{name} is outside the device hot path built so far (DESIGN.md §7)")
         if fill_zero_leaves_val != -1e300:
@@ -64,38 +63,46 @@ class EnsembleSampler(object):
         if isinstance(ndims, dict):
             branch_names = list(ndims.keys()) if branch_names is None else branch_names
         if branch_names is None:
-            branch_names = ["model_0"]
-        if len(branch_names) != 1 or nbranches != 1:
-            raise NotImplementedError("the device hot path covers one branch per sampler in this build")
+            branch_names = ["model_0"] if nbranches == 1 else [f"model_{i}" for i in range(nbranches)]
         self.branch_names = list(branch_names)
+        nb = len(self.branch_names)
+        as_dict = lambda v: dict(v) if isinstance(v, dict) else {n: int(v) for n in self.branch_names}
+        self.ndims = as_dict(ndims)
+        self.nleaves_max = as_dict(nleaves_max)
+        self.nleaves_min = as_dict(nleaves_min if nleaves_min is not None else 0)
+        self.nbranches = nb
+        self.has_reversible_jump = bool(rj_moves)
+        # several branches, several leaves or reversible jump: the multi-branch device path
+        self._mb = nb > 1 or max(self.nleaves_max.values()) > 1 or self.has_reversible_jump
+        if isinstance(priors, ProbDistContainer):
+            priors = {self.branch_names[0]: priors}
+        elif isinstance(priors, dict) and not all(n in priors for n in self.branch_names):
+            priors = {self.branch_names[0]: ProbDistContainer(priors)}
+        priors = {n: (p if isinstance(p, ProbDistContainer) else ProbDistContainer(p)) for n, p in priors.items()}
         name = self.branch_names[0]
-        self.ndims = ndims if isinstance(ndims, dict) else {name: int(ndims)}
-        self.nleaves_max = nleaves_max if isinstance(nleaves_max, dict) else {name: int(nleaves_max)}
-        self.nbranches = 1
-        self.has_reversible_jump = False
-        if isinstance(priors, dict) and name not in priors:
-            priors = {name: ProbDistContainer(priors)}
-        elif isinstance(priors, ProbDistContainer):
-            priors = {name: priors}
         self.priors = priors
-        self.key_order = {name: priors[name].key_order}
+        self.key_order = {n: priors[n].key_order for n in self.branch_names}
         self.nwalkers = int(nwalkers)
         self.num_repeats_in_model = int(num_repeats_in_model)
+        self.num_repeats_rj = 1
         self.track_moves = track_moves
         self.update_fn, self.update_iterations = update_fn, update_iterations
         self.stopping_fn, self.stopping_iterations = stopping_fn, stopping_iterations
 
-        # tempering (ensemble.py:321-334)
+        # tempering (ensemble.py:321-334): effective dimension = sum over branches of nleaves_max * ndim
         if tempering_kwargs == {}:
             self.ntemps = 1
             self.temperature_control = None
         else:
-            total_ndim = self.nleaves_max[name] * self.ndims[name]
+            total_ndim = sum(self.nleaves_max[n] * self.ndims[n] for n in self.branch_names)
             self.temperature_control = TemperatureControl(total_ndim, nwalkers, **tempering_kwargs)
             self.ntemps = self.temperature_control.ntemps
 
         # move schedule (ensemble.py:349-378)
         if moves is None:
+            if self._mb:
+                raise NotImplementedError("several branches / leaves need an in-model move that handles them on the device: "
+                                          "pass moves=GroupStretchMove(nfriends=...)")
             self.moves = [StretchMove(temperature_control=self.temperature_control, a=2.0)]
             self.weights = [1.0]
         elif isinstance(moves, Iterable):
@@ -117,11 +124,37 @@ class EnsembleSampler(object):
         if seed is None:
             seed = int(state[1][0]) | (int(state[1][1]) << 32)
 
-        self.ctx = DeviceContext(priors[name], log_like_fn, device=device, rng=rng, seed=seed, branch_name=name)
+        if self._mb:
+            from .moves import DistributionGenerateRJ, GroupStretchMove
+            from .multibranch import MBContext
+            groups = [m for m in self.moves if isinstance(m, GroupStretchMove)]
+            if len(groups) != len(self.moves):
+                raise NotImplementedError("in-model moves of a multi-branch sampler: GroupStretchMove")
+            if len({(m.nfriends, str(m.friend_key)) for m in groups}) != 1:
+                raise ValueError("all GroupStretchMoves of one sampler share one friend table (nfriends, friend_key)")
+            self.ctx = MBContext(priors, log_like_fn, self.branch_names, self.ndims, self.nleaves_max, self.nleaves_min,
+                                 nfriends=groups[0].nfriends, friend_key=groups[0].friend_key, device=device, rng=rng,
+                                 seed=seed)
+            # rj move schedule (ensemble.py:380-507): True / "together" = one DistributionGenerateRJ over all branches
+            self.rj_moves, self.rj_weights = None, None
+            if self.has_reversible_jump:
+                if rj_moves is True or rj_moves == "together":
+                    self.rj_moves = [DistributionGenerateRJ(priors, nleaves_max=self.nleaves_max,
+                                                            nleaves_min=self.nleaves_min,
+                                                            temperature_control=self.temperature_control)]
+                elif isinstance(rj_moves, str):
+                    raise NotImplementedError("rj_moves='iterate_branches' / 'separate_branches' need Gibbs splits "
+                                              "(DESIGN.md §7); use rj_moves=True")
+                else:
+                    self.rj_moves = list(rj_moves) if isinstance(rj_moves, Iterable) else [rj_moves]
+                self.rj_weights = np.ones(len(self.rj_moves)) / len(self.rj_moves)
+        else:
+            self.rj_moves, self.rj_weights = None, None
+            self.ctx = DeviceContext(priors[name], log_like_fn, device=device, rng=rng, seed=seed, branch_name=name)
         self.log_like_fn = self.ctx.like
         if self.temperature_control is not None:
             self.temperature_control.bind(self.ctx)
-        for move in self.moves:
+        for move in self.moves + (self.rj_moves or []):
             if self.temperature_control is not None and move.temperature_control is None:
                 move.temperature_control = self.temperature_control  # ensemble.py:516-525
             move.bind(self.ctx)
@@ -131,7 +164,7 @@ class EnsembleSampler(object):
         self.all_moves = {}
         if self.track_moves:
             counts = {}
-            for move in self.moves:
+            for move in self.moves + (self.rj_moves or []):
                 mn = move.__class__.__name__
                 counts[mn] = counts.get(mn, -1) + 1
                 self.all_moves[f"{mn}_{counts[mn]}"] = move  # ensemble.py:563-583
@@ -141,7 +174,7 @@ class EnsembleSampler(object):
         self._previous_state = None
         if not self.backend.initialized:
             self.backend.reset(self.nwalkers, self.ndims, nleaves_max=self.nleaves_max, ntemps=self.ntemps,
-                               branch_names=self.branch_names, rj=False, moves=self.move_keys,
+                               branch_names=self.branch_names, rj=self.has_reversible_jump, moves=self.move_keys,
                                key_order=self.key_order, **info)
         self._dstate = None
 
@@ -164,6 +197,12 @@ class EnsembleSampler(object):
     def get_log_like(self, **kwargs):
         return self.backend.get_log_like(**kwargs)
 
+    def get_nleaves(self, **kwargs):
+        return self.backend.get_nleaves(**kwargs)
+
+    def get_inds(self, **kwargs):
+        return self.backend.get_inds(**kwargs)
+
     def get_log_prior(self, **kwargs):
         return self.backend.get_log_prior(**kwargs)
 
@@ -178,8 +217,17 @@ class EnsembleSampler(object):
         return Model(self.log_like_fn, self.compute_log_like, self.compute_log_prior, self.temperature_control, map,
                      self._random)
 
+    def _mb_eval(self, coords, inds):
+        st = State({n: np.asarray(coords[n], dtype=np.float64) for n in self.branch_names},
+                   inds=None if inds is None else {n: inds[n] for n in self.branch_names})
+        d = self.ctx.upload(st)
+        self.ctx.eval_state(d)
+        return d.logp.cpu().numpy(), d.logl.cpu().numpy()
+
     def compute_log_prior(self, coords, inds=None, supps=None, branch_supps=None):
         """ensemble.py:1127 — evaluated on the device; returns an ndarray [ntemps, nwalkers]."""
+        if self._mb:
+            return self._mb_eval(coords, inds)[0]
         name = self.branch_names[0]
         c = coords[name] if isinstance(coords, dict) else coords
         T, W, L, D = c.shape
@@ -194,6 +242,8 @@ class EnsembleSampler(object):
 
     def compute_log_like(self, coords, inds=None, logp=None, supps=None, branch_supps=None):
         """ensemble.py:1219 — evaluated on the device; returns (ndarray [ntemps, nwalkers], None)."""
+        if self._mb:
+            return self._mb_eval(coords, inds)[1], None
         name = self.branch_names[0]
         c = coords[name] if isinstance(coords, dict) else coords
         if np.any(np.isinf(c)):
@@ -257,10 +307,12 @@ class EnsembleSampler(object):
         model = self.get_model()
         self._dstate = d
         acc_total = torch.zeros((self.ntemps, self.nwalkers), dtype=torch.int32, device=self.ctx.device)
+        rj_total = torch.zeros((self.ntemps, self.nwalkers), dtype=torch.int32, device=self.ctx.device)
+        in_model_swaps = None
         i = 0
         it_range = iter(int, 1) if iterations is None else range(iterations)
         for _ in it_range:
-            for _ in range(thin_by):
+            for inner in range(thin_by):
                 acc_total.zero_()  # ensemble.py:968: `accepted` restarts every inner iteration
                 for repeat in range(self.num_repeats_in_model):
                     mi = self._random.choice(len(self.moves), p=self.weights)  # ensemble.py:971 (1 uniform)
@@ -269,13 +321,24 @@ class EnsembleSampler(object):
                     acc_total += acc
                     if tune:
                         move.tune(d, acc)
+                if self.has_reversible_jump:  # ensemble.py:986-1006
+                    if store and inner == thin_by - 1 and tc is not None and self.ntemps > 1:
+                        in_model_swaps = tc.swaps_accepted  # ensemble.py:977: read before the rj move swaps again
+                    rj_total.zero_()
+                    for repeat in range(self.num_repeats_rj):
+                        ri = self._random.choice(len(self.rj_moves), p=self.rj_weights)  # ensemble.py:990
+                        d, racc = self.rj_moves[ri].propose(model, d)
+                        rj_total += racc
                 i += 1
             # ---- yield point: materialise a host State (ensemble.py:1013-1045)
             host = self.ctx.download(d, random_state=self.random_state)
             if store:
                 maf = {k: m.acceptance_fraction for k, m in self.all_moves.items()} if self.track_moves else None
                 swaps = tc.swaps_accepted if (tc is not None and self.ntemps > 1) else None
+                if self.has_reversible_jump:
+                    swaps = in_model_swaps
                 self.backend.save_step(host, acc_total.cpu().numpy(), swaps_accepted=swaps,
+                                       rj_accepted=rj_total.cpu().numpy() if self.has_reversible_jump else None,
                                        moves_accepted_fraction=maf)
             if self.update_iterations > 0 and self.update_fn is not None and i % self.update_iterations == 0:
                 self.update_fn(i, host, self)

@@ -1,6 +1,9 @@
 from .gaussian import GaussianMove
+from .group import GroupStretchMove
+from .rj import DistributionGenerateRJ, ReversibleJumpMove
 from .move import Move
 from .stretch import StretchMove
 from .tempering import TemperatureControl, make_ladder
 
-__all__ = ["Move", "StretchMove", "GaussianMove", "TemperatureControl", "make_ladder"]
+__all__ = ["Move", "StretchMove", "GaussianMove", "GroupStretchMove", "ReversibleJumpMove", "DistributionGenerateRJ",
+           "TemperatureControl", "make_ladder"]

@@ -65,7 +65,8 @@ typedef struct {
   int32_t temp_offset; /* index of local temperature 0 in the full ladder (temperature-sharded runs; else 0):
                           the random streams are keyed by the GLOBAL temperature, so a sharded run
                           reproduces the single-GPU chain */
-  int32_t _pad;
+  int32_t inds_stride; /* bytes per walker of `inds` when it carries more than the leaf flags (multi-branch states:
+                          flags + friend table, eb_mb_state.aux); 0 = nleaves.  Only the swap pass looks at it. */
   double* coords;      /* [T][W][L][D] */
   double* logl;        /* [T][W]  State.log_like  */
   double* logp;        /* [T][W]  State.log_prior */
@@ -175,7 +176,8 @@ EB_API int eb_device_count(void);
 EB_API size_t eb_ctrl_size(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 eb_state, 1 eb_prior, 2 eb_like,
  * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job, 9 eb_shard,
- * 10 eb_publish */
+ * 10 eb_publish, 11 eb_mb_layout, 12 eb_mb_state, 13 eb_pulse_data, 14 eb_mb_friends, 15 eb_mb_group_rng,
+ * 16 eb_mb_rj_rng */
 EB_API size_t eb_struct_size(int which);
 
 /* ---- probability evaluation:  EnsembleSampler.compute_log_prior (ensemble.py:1127) and
@@ -253,6 +255,94 @@ EB_API int eb_dev_free(void* p);
 EB_API int eb_ipc_export(const void* dev_ptr, uint8_t* handle64);
 EB_API int eb_ipc_open(const uint8_t* handle64, void** out);
 EB_API int eb_ipc_close(void* p);
+
+
+/* ======================================================================================================
+ * Reversible jump + group stretch over several branches (BASELINE config 5).
+ *
+ * A walker owns, per branch b, up to nleaves[b] leaves of ndim[b] parameters (state.py:330 Branch); `inds` says
+ * which leaves exist.  On the device the branches of a walker are stored back to back:
+ *   coords [T][W][row]      row = sum_b nleaves[b]*ndim[b]; branch b starts at sum_{b'<b} nleaves[b']*ndim[b']
+ *   aux    [T][W][stride]   leaf flags (sum_b nleaves[b] bytes, padded to a multiple of 4), then the friend table
+ *                           int32 [sum_b nleaves[b]][nfriends] of the group move (the reference keeps it in a
+ *                           BranchSupplemental, which the swap pass moves with the walker, tempering.py:351-482)
+ * and the swap pass is eb_pt_swap on eb_state{nleaves = 1, ndim = row, inds = aux, inds_stride = stride}.
+ * ====================================================================================================== */
+#define EB_MAX_BRANCHES 4
+#define EB_MB_MAX_ROW 128    /* doubles per walker */
+#define EB_MB_MAX_LEAVES 64  /* leaves per walker, all branches */
+
+typedef struct {
+  int32_t nbranches;
+  int32_t nfriends;                       /* width of the friend table, 0 = none */
+  int32_t nleaves[EB_MAX_BRANCHES];       /* = nleaves_max */
+  int32_t ndim[EB_MAX_BRANCHES];
+  int32_t nleaves_min[EB_MAX_BRANCHES];   /* rj.py:33-58 */
+  int32_t kind[EB_MAX_BRANCHES];          /* eb_pulse_kind of the branch's template */
+  int32_t friend_key[EB_MAX_BRANCHES];    /* parameter the friends are sorted by (tests/test_eryn.py:822: index 1) */
+} eb_mb_layout;
+
+typedef struct {
+  int32_t ntemps, nwalkers, temp_offset, _pad;
+  double* coords;  /* [T][W][row] */
+  double* logl;    /* [T][W] */
+  double* logp;    /* [T][W] */
+  uint8_t* aux;    /* [T][W][stride] */
+  double* betas;   /* [T] or NULL */
+} eb_mb_state;
+
+/* log L = -1/2 sum_i ((template(t_i) - y_i)/sigma)^2, template = sum of the active leaves' pulses — the reference
+ * test's likelihood (tests/test_eryn.py:38-92).  Walkers without any active leaf or with logp = -inf are not
+ * evaluated and get -1e300 (ensemble.py:1279-1282, :1486-1513). */
+typedef enum { EB_PULSE_GAUSS = 0 /* a exp(-(t-b)^2/(2c^2)) */, EB_PULSE_SINE = 1 /* a sin(2 pi b t + c) */ } eb_pulse_kind;
+typedef struct {
+  int32_t nt, _pad;
+  double sigma;
+  const double* t;  /* [nt] device */
+  const double* y;  /* [nt] device */
+} eb_pulse_data;
+
+/* stationary friends of the group move (group.py:50-95; rule of tests/test_eryn.py:813-907): per branch the cold
+ * chain's active leaves sorted by their key parameter, built on the host every n_iter_update iterations */
+typedef struct {
+  int32_t nfr[EB_MAX_BRANCHES];
+  const double* coords[EB_MAX_BRANCHES]; /* [nfr][ndim] device */
+  const double* keys[EB_MAX_BRANCHES];   /* [nfr] device, ascending */
+} eb_mb_friends;
+
+typedef struct {
+  int32_t mode, _pad;      /* eb_rng_mode */
+  const int32_t* pick;     /* replay [T][W][sum nleaves]: column of the friend table (fixture's randint) */
+  const double* u_z;       /* replay [T][W]  stretch.py:131 */
+  const double* u_acc;     /* replay [T][W]  group.py:254 */
+  uint64_t seed; const uint64_t* iter_dev; uint64_t iter;
+} eb_mb_group_rng;
+
+typedef struct {
+  int32_t mode, _pad;
+  const int32_t* change;   /* replay [B][T][W] +1 / -1 / 0 after the edge fix-up (distgenrj.py:61-71) */
+  const int32_t* leaf;     /* replay [B][T][W] leaf that is born or dies (distgenrj.py:97,111) */
+  const double* birth[EB_MAX_BRANCHES]; /* replay [T][W][ndim_b] prior draws for the births (prior.py:56-71) */
+  const double* u_acc;     /* replay [T][W]  rj.py:332 */
+  uint64_t seed; const uint64_t* iter_dev; uint64_t iter;
+} eb_mb_rj_rng;
+
+/* compute_log_prior + compute_log_like of the whole state (ensemble.py:898-912) */
+EB_API int eb_mb_eval_state(const eb_mb_layout* lay, const eb_mb_state* st, const eb_prior* prior,
+                            const eb_pulse_data* data, void* stream);
+/* friend table: mode 0 = every active leaf gets its nfriends nearest friends, inactive leaves -1 (fixture
+ * setup_friends); mode 1 = only active leaves whose row is all -1 (fix_friends) */
+EB_API int eb_mb_friends_update(const eb_mb_layout* lay, const eb_mb_state* st, const eb_mb_friends* fr, int32_t mode,
+                                void* stream);
+/* GroupStretchMove.propose without the tempering tail: group.py:122-270 + groupstretch.py:34-120 */
+EB_API int eb_mb_group_stretch(const eb_mb_layout* lay, const eb_mb_state* st, const eb_prior* prior,
+                               const eb_pulse_data* data, const eb_mb_friends* fr, double a, const eb_mb_group_rng* rng,
+                               uint8_t* accepted, uint32_t* accepted_count, void* stream);
+/* DistributionGenerateRJ.propose without the tempering tail: rj.py:145-343 + distgenrj.py:35-222 */
+EB_API int eb_mb_rj_step(const eb_mb_layout* lay, const eb_mb_state* st, const eb_prior* prior, const eb_pulse_data* data,
+                         const eb_mb_rj_rng* rng, uint8_t* accepted, uint32_t* accepted_count, void* stream);
+/* bytes per walker of the aux array for a layout */
+EB_API int32_t eb_mb_aux_stride(const eb_mb_layout* lay);
 
 /* iteration counter tick for untempered runs (no swap pass) */
 EB_API int eb_advance_iter(eb_ctrl* ctrl, void* stream);
