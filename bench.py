@@ -110,12 +110,17 @@ def run_cpu(wl, steps, warmup, budget_s=None):
 
 
 def cpu_threads():
+    """threads the NumPy port actually computes with: its work is elementwise / einsum-without-BLAS / fancy indexing,
+    all single-threaded in NumPy (the BLAS pool, if any, stays idle on this path)"""
+    return 1
+
+
+def blas_pool():
     try:
         from threadpoolctl import threadpool_info
-        n = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
-        n = 1
-    return n
+        return 1
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -389,7 +394,7 @@ def run_gpu(args):
     cpu_v, cpu_s, cpu_n = run_cpu(wl, steps=10 ** 6, warmup=1, budget_s=0.5 if args.profile else 12.0)
     cpu = dict(value=cpu_v, unit=UNIT, cores=cpu_threads(), kind="port",
                sample=f"{cpu_n} iterations of the same workload ({cpu_s * 1e3:.1f} ms/iteration), NumPy oracle port, "
-                      f"os.cpu_count()={os.cpu_count()}")
+                      f"os.cpu_count()={os.cpu_count()}, BLAS pool {blas_pool()} (idle: the path is single-threaded NumPy, like the reference)")
 
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -413,7 +418,9 @@ def run_reference(args):
     wl = workload(args.workload, max(1, args.gpus))
     v, s, n = run_cpu(wl, steps=args.steps, warmup=args.warmup, budget_s=150.0)
     cpu = dict(value=v, unit=UNIT, cores=cpu_threads(), kind="port",
-               sample=f"{n} iterations, {s * 1e3:.1f} ms/iteration, os.cpu_count()={os.cpu_count()}")
+               sample=f"{n} iterations, {s * 1e3:.1f} ms/iteration, os.cpu_count()={os.cpu_count()}, BLAS pool {blas_pool()} "
+                      f"(idle: the reference path is single-process, single-threaded NumPy; its only multi-core "
+                      f"facility is pool.map over per-walker likelihood calls, slower than vectorising)")
     print(json.dumps(dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=n,
                           warmup=args.warmup, ms_per_step=s * 1e3, higher_is_better=True, scaling="weak",
                           vs_baseline=None, dtype="f64", data="synthetic",

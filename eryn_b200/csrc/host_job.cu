@@ -64,7 +64,7 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   if (cx.coords.ensure(bc) || cx.logl.ensure(bs) || cx.logp.ensure(bs) || cx.betas.ensure(T * sizeof(double)) ||
       cx.prior.ensure(3 * D * sizeof(double)) || cx.like.ensure((job->like_nparams + 1) * sizeof(double)) ||
       cx.acc.ensure(n) || cx.acc_cnt.ensure(n * sizeof(uint32_t)) || cx.ctrl.ensure(sizeof(eb_ctrl)) ||
-      (T > 64 && (cx.row_scratch.ensure(bc) || cx.logp_scratch.ensure(bs))))
+      (T > 32 && (cx.row_scratch.ensure(bc) || cx.logp_scratch.ensure(bs))))
     return EB_ERR_CUDA;
 
   // ---- host -> device -------------------------------------------------------------------------
@@ -112,7 +112,7 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   eb_swap_rng wrng;
   std::memset(&wrng, 0, sizeof(wrng));
   wrng.mode = EB_RNG_PHILOX; wrng.permute = job->permute; wrng.seed = job->seed; wrng.iter_dev = &dctrl->iter;
-  if (T > 64) { wrng.row_scratch = (double*)cx.row_scratch.p; wrng.logp_scratch = (double*)cx.logp_scratch.p; }
+  if (T > 32) { wrng.row_scratch = (double*)cx.row_scratch.p; wrng.logp_scratch = (double*)cx.logp_scratch.p; }
   for (int it = 0; it < niter; ++it) {
     const int mv = job->move_schedule_host ? job->move_schedule_host[it] : 0;
     int rc;

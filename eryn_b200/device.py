@@ -312,7 +312,7 @@ class DeviceContext(object):
             r.mode = _lib.EB_RNG_REPLAY
             r.iperm, r.i1perm, r.u, r.next_pos, r.u_at = [_ptr(t) for t in keep]
             self.launches += 1 if T > 1 else 0
-        if d.inds is not None or L * D > 32 or T > 64:  # rows move through staging buffers (eb_swap_rng.row_scratch)
+        if d.inds is not None or L * D > 32 or T > 32:  # shapes whose rows move through staging buffers (k_swap.cu)
             r.row_scratch = _ptr(self.scratch("swap_rows", (T, W, L, D), torch.float64))
             r.logp_scratch = _ptr(self.scratch("swap_logp", (T, W), torch.float64))
             if d.inds is not None:

@@ -137,7 +137,7 @@ typedef struct {
   int32_t* next_pos;      /* replay scratch [T][W] int32 */
   double* u_at;           /* replay scratch [T][W] */
   double* row_scratch;    /* [T][W][L][D] staging of moved rows; needed when rows are longer than 32 doubles, the state
-                             has leaf flags, or T > 64 (else may be NULL) */
+                             has leaf flags, T > 64, or T > 32 with rows longer than 8 doubles (else may be NULL) */
   double* logp_scratch;   /* [T][W], with row_scratch */
   uint8_t* inds_scratch;  /* [T][W][L], with row_scratch when the state has leaf flags */
   uint64_t seed;

@@ -139,6 +139,16 @@ PHILOX_CASES = {
     "d13": (2, 64, 13, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 8, -5, 5),
     "d18": (2, 64, 18, lambda d: orc.RosenbrockLike(), [dict(kind="stretch", a=2.0)], [1.0], 8, -5, 5),
     "d30": (2, 128, 30, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -10, 10),
+    # ladder lengths that exercise every swap-kernel shape: 8/16/32 lanes per chain, two rungs per lane (T = 40),
+    # the staging-buffer path (T = 70, and rows longer than 32 doubles cannot occur in the fused kernels), T = 128
+    "T8": (8, 64, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 6, -5, 5),
+    "T24": (24, 64, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 6, -5, 5),
+    "T40": (40, 48, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 6, -5, 5),
+    "T40_d20": (40, 48, 20, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 4, -10, 10),
+    "T70": (70, 32, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 5, -5, 5),
+    "T128": (128, 32, 8, c2_like, [dict(kind="stretch", a=2.0)], [1.0], 4, -10, 10),
+    "W_small": (3, 16, 3, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 10, -5, 5),
+    "W_257": (2, 257, 5, lambda d: orc.RosenbrockLike(), [dict(kind="stretch", a=2.0)], [1.0], 6, -5, 5),
 }
 
 
