@@ -160,22 +160,45 @@ struct Like<1> {  // EB_LIKE_ROSENBROCK
 
 template <>
 struct Like<2> {  // EB_LIKE_GMIX: params logc[K], hinv[K], mu[K*D]
+  static constexpr int KREG = 4;   // components whose exponents are kept in registers (two-pass log-sum-exp)
+  template <int DMAX, bool EXACT>
+  static __device__ __forceinline__ double comp(const double (&x)[DMAX], int D, const double* __restrict__ mu) {
+    // |x - mu|^2 with explicit FMAs on four accumulators (short dependent chains)
+    double r[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if (EXACT || j < D) {
+        const double dd = x[j] - mu[j];
+        r[j & 3] = fma(dd, dd, r[j & 3]);
+      }
+    return (r[0] + r[1]) + (r[2] + r[3]);
+  }
   template <int DMAX, bool EXACT>
   static __device__ __forceinline__ double eval(const double (&x)[DMAX], int D_, const double* __restrict__ sp, int K) {
     const int D = EXACT ? DMAX : D_;
     const double* logc = sp;
     const double* hinv = sp + K;
     const double* mu = sp + 2 * K;
+    if (K <= KREG) {
+      double e[KREG];
+      double m = neg_inf();
+#pragma unroll
+      for (int k = 0; k < KREG; ++k) {
+        e[k] = neg_inf();
+        if (k < K) {
+          e[k] = logc[k] - comp<DMAX, EXACT>(x, D, mu + k * D) * hinv[k];
+          m = e[k] > m ? e[k] : m;
+        }
+      }
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < KREG; ++k)
+        if (k < K) s += exp(e[k] - m);
+      return m + log(s);
+    }
     double m = neg_inf(), s = 0.0;
     for (int k = 0; k < K; ++k) {
-      double r2 = 0.0;
-#pragma unroll
-      for (int j = 0; j < DMAX; ++j)
-        if (EXACT || j < D) {
-          const double dd = x[j] - mu[k * D + j];
-          r2 += dd * dd;
-        }
-      const double e = logc[k] - r2 * hinv[k];
+      const double e = logc[k] - comp<DMAX, EXACT>(x, D, mu + k * D) * hinv[k];
       if (e > m) {  // online log-sum-exp
         s = s * exp(m - e) + 1.0;
         m = e;

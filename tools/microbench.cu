@@ -100,10 +100,11 @@ static void launch_empty(cudaStream_t s, int gx, int gy, int threads, int cluste
 
 int main(int argc, char** argv) {
   const int T = argc > 1 ? std::atoi(argv[1]) : 16, W = argc > 2 ? std::atoi(argv[2]) : 4096, D = argc > 3 ? std::atoi(argv[3]) : 8;
+  const int LK = argc > 4 ? std::atoi(argv[4]) : 0;   // 0 Gaussian, 1 Rosenbrock, 2 mixture of 4 Gaussians
   const int N = 50;
   cudaStream_t s;
   CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  std::printf("shape T=%d W=%d D=%d\n", T, W, D);
+  std::printf("shape T=%d W=%d D=%d like=%d\n", T, W, D, LK);
   std::printf("empty plain   grid 128x256      : %.2f us/launch\n", time_graph(s, N, [&] { launch_empty(s, 128, 1, 256, 1, false); }));
   std::printf("empty plain   grid (8,16)x256   : %.2f us/launch\n", time_graph(s, N, [&] { launch_empty(s, 8, 16, 256, 1, false); }));
   std::printf("empty cluster8 grid (8,16)x256  : %.2f us/launch\n", time_graph(s, N, [&] { launch_empty(s, 8, 16, 256, 8, false); }));
@@ -112,23 +113,26 @@ int main(int argc, char** argv) {
 
   // ---- state -------------------------------------------------------------------------------------
   const size_t n = (size_t)T * W;
-  std::vector<double> hc(n * D), hb(T), hpr(3 * D), hlk(D + D * D, 0.0);
+  const int KM = 4;
+  const int nlk = LK == 0 ? D + D * D : LK == 1 ? 0 : KM * (2 + D);
+  std::vector<double> hc(n * D), hb(T), hpr(3 * D), hlk(nlk + 1, 0.0);
   srand(1);
   for (auto& v : hc) v = 6.0 * rand() / RAND_MAX - 3.0;
   for (int t = 0; t < T; ++t) hb[t] = std::pow(1.5, -t);
-  for (int d = 0; d < D; ++d) { hpr[d] = -10; hpr[D + d] = 10; hpr[2 * D + d] = std::log(1.0 / 20.0); hlk[D + d * D + d] = 1.0; }
+  for (int d = 0; d < D; ++d) { hpr[d] = -10; hpr[D + d] = 10; hpr[2 * D + d] = std::log(1.0 / 20.0); if (LK == 0) hlk[D + d * D + d] = 1.0; }
+  if (LK == 2) for (int k = 0; k < KM; ++k) { hlk[k] = -1.0 - 0.1 * k; hlk[KM + k] = 0.5 / (1.0 + 0.2 * k); for (int d = 0; d < D; ++d) hlk[2 * KM + k * D + d] = 4.0 * rand() / RAND_MAX - 2.0; }
   double *coords, *logl, *logp, *betas, *pr, *lk;
   uint8_t* acc; uint32_t* cnt; eb_ctrl* ctrl;
   CK(cudaMalloc(&coords, n * D * 8)); CK(cudaMalloc(&logl, n * 8)); CK(cudaMalloc(&logp, n * 8)); CK(cudaMalloc(&betas, T * 8));
-  CK(cudaMalloc(&pr, 3 * D * 8)); CK(cudaMalloc(&lk, (D + D * D) * 8)); CK(cudaMalloc(&acc, n)); CK(cudaMalloc(&cnt, n * 4));
+  CK(cudaMalloc(&pr, 3 * D * 8)); CK(cudaMalloc(&lk, (nlk + 1) * 8)); CK(cudaMalloc(&acc, n)); CK(cudaMalloc(&cnt, n * 4));
   CK(cudaMalloc(&ctrl, sizeof(eb_ctrl)));
   CK(cudaMemcpy(coords, hc.data(), n * D * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(betas, hb.data(), T * 8, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(pr, hpr.data(), 3 * D * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(lk, hlk.data(), (D + D * D) * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pr, hpr.data(), 3 * D * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(lk, hlk.data(), (nlk + 1) * 8, cudaMemcpyHostToDevice));
   CK(cudaMemset(ctrl, 0, sizeof(eb_ctrl))); CK(cudaMemset(cnt, 0, n * 4));
   eb_state st; std::memset(&st, 0, sizeof(st));
   st.ntemps = T; st.nwalkers = W; st.nleaves = 1; st.ndim = D; st.coords = coords; st.logl = logl; st.logp = logp; st.betas = betas;
   eb_prior prior{pr, pr + D, pr + 2 * D};
-  eb_like like{EB_LIKE_GAUSSIAN, 0, D + D * D, 0, lk};
+  eb_like like{LK, LK == 2 ? KM : 0, nlk, 0, lk};
   EB(eb_eval_state(&st, &prior, &like, s));
   eb_stretch_rng sr; std::memset(&sr, 0, sizeof(sr));
   sr.mode = EB_RNG_PHILOX; sr.randomize_split = 1; sr.seed = 7; sr.iter_dev = &ctrl->iter_next; sr.pdl_chain = 1;
