@@ -29,7 +29,7 @@ class eb_state(C.Structure):
 
 
 class eb_prior(C.Structure):
-    _fields_ = [("lo", vp), ("hi", vp), ("logpdf", vp)]
+    _fields_ = [("lo", vp), ("hi", vp), ("logpdf", vp), ("period", vp)]
 
 
 class eb_like(C.Structure):
@@ -150,7 +150,7 @@ SYMBOLS = {
                                 vp]),
     "eb_mb_aux_stride": (C.c_int32, [P(eb_mb_layout)]),
     "eb_advance_iter": (C.c_int, [vp, vp]),
-    "eb_stretch_propose": (C.c_int, [P(eb_state), C.c_double, C.c_int32, P(eb_stretch_rng), vp, vp, vp, vp]),
+    "eb_stretch_propose": (C.c_int, [P(eb_state), C.c_double, C.c_int32, P(eb_stretch_rng), vp, vp, vp, vp, vp]),
     "eb_accept_update": (C.c_int, [P(eb_state), vp, C.c_int32, vp, vp, vp, vp, C.c_int32, P(eb_stretch_rng),
                                    vp, vp, vp]),
     "eb_box_log_prior": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, P(eb_prior), vp, vp]),
@@ -181,7 +181,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.eb_abi_version() != 2:
+    if lib.eb_abi_version() != 3:
         raise ErynB200Error("liberyn_b200.so ABI version mismatch; rebuild")
     for i, st in enumerate(STRUCTS):
         if lib.eb_struct_size(i) != C.sizeof(st):

@@ -78,8 +78,8 @@ int fill_common(Common& c, const eb_state* st, const eb_prior* prior, const eb_l
   c.T = st->ntemps; c.W = st->nwalkers; c.L = st->nleaves; c.D = st->ndim; c.LD = st->nleaves * st->ndim;
   c.t0 = st->temp_offset;
   c.Lb = st->inds_stride > 0 ? st->inds_stride : st->nleaves;
-  c.lo = c.hi = c.lpdf = nullptr; c.like_params = nullptr; c.like_nparams = 0; c.like_ncomp = 0;
-  if (prior) { c.lo = prior->lo; c.hi = prior->hi; c.lpdf = prior->logpdf; }
+  c.lo = c.hi = c.lpdf = nullptr; c.per = nullptr; c.like_params = nullptr; c.like_nparams = 0; c.like_ncomp = 0;
+  if (prior) { c.lo = prior->lo; c.hi = prior->hi; c.lpdf = prior->logpdf; c.per = prior->period; }
   c.like_kind = -1;
   if (like) { c.like_params = like->params; c.like_nparams = like->nparams; c.like_ncomp = like->ncomp; c.like_kind = like->kind; }
   if (need_fused) {

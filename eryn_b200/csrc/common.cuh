@@ -79,7 +79,7 @@ struct Common {
   int T, W, L, D, LD;
   int Lb;  // bytes per walker of `inds` (leaf flags, or flags + friend table of a multi-branch state)
   int t0;  // global index of local temperature 0 (random-stream keying)
-  const double* lo; const double* hi; const double* lpdf;
+  const double* lo; const double* hi; const double* lpdf; const double* per;
   const double* like_params; int like_nparams, like_ncomp, like_kind;
 };
 
@@ -88,7 +88,8 @@ struct Common {
 // Two steps so that the global-load latency hides behind other work: `stage_load` issues the loads of this thread's
 // (first) element into registers, `stage_store` writes them to shared memory and copies whatever exceeds one element
 // per thread; the caller synchronises the block afterwards.
-struct Staged { double lo, hi, lpdf, p0, p1, p2; };
+struct Staged { double lo, hi, lpdf, per, p0, p1, p2; };
+constexpr int PRIOR_ROWS = 4;   // shared-memory rows of D doubles in front of the likelihood block: lo, hi, lpdf, period
 
 __device__ __forceinline__ void stage_store_gauss(double* sp, int D, int e, double pij, double pji) {
   const int i = e / D, j = e - i * D;
@@ -98,7 +99,7 @@ __device__ __forceinline__ void stage_store_gauss(double* sp, int D, int e, doub
 
 __device__ __forceinline__ void stage_load(const Common& c, Staged& r) {
   const int D = c.D, tid = threadIdx.x;
-  if (tid < D) { r.lo = c.lo[tid]; r.hi = c.hi[tid]; r.lpdf = c.lpdf[tid]; }
+  if (tid < D) { r.lo = c.lo[tid]; r.hi = c.hi[tid]; r.lpdf = c.lpdf[tid]; r.per = c.per ? c.per[tid] : 0.0; }
   if (c.like_kind == EB_LIKE_GAUSSIAN) {
     if (tid < D) r.p0 = c.like_params[tid];
     if (tid < D * D) {
@@ -114,9 +115,11 @@ __device__ __forceinline__ void stage_load(const Common& c, Staged& r) {
 
 __device__ __forceinline__ void stage_store(const Common& c, const Staged& r, double* sm) {
   const int D = c.D, tid = threadIdx.x, nt = blockDim.x;
-  if (tid < D) { sm[tid] = r.lo; sm[D + tid] = r.hi; sm[2 * D + tid] = r.lpdf; }
-  for (int i = tid + nt; i < D; i += nt) { sm[i] = c.lo[i]; sm[D + i] = c.hi[i]; sm[2 * D + i] = c.lpdf[i]; }
-  double* sp = sm + 3 * D;
+  if (tid < D) { sm[tid] = r.lo; sm[D + tid] = r.hi; sm[2 * D + tid] = r.lpdf; sm[3 * D + tid] = r.per; }
+  for (int i = tid + nt; i < D; i += nt) {
+    sm[i] = c.lo[i]; sm[D + i] = c.hi[i]; sm[2 * D + i] = c.lpdf[i]; sm[3 * D + i] = c.per ? c.per[i] : 0.0;
+  }
+  double* sp = sm + PRIOR_ROWS * D;
   if (c.like_kind == EB_LIKE_GAUSSIAN) {
     const double* P = c.like_params + D;
     if (tid < D) sp[tid] = r.p0;
@@ -148,15 +151,26 @@ __device__ __forceinline__ void eval_point(const double (&q)[DMAX], const Common
   if (isinf(lp) || !leaf_active) {
     ll = FILL_LOGL;  // ensemble.py:1279-1282, :1486 / fill_zero_leaves_val :1499
   } else {
-    ll = Like<LIKE>::template eval<DMAX, EXACT>(q, D, sm + 3 * D, c.like_ncomp);
+    ll = Like<LIKE>::template eval<DMAX, EXACT>(q, D, sm + PRIOR_ROWS * D, c.like_ncomp);
     if (ll != ll) ll = FILL_LOGL;  // red_blue.py:279-281
   }
+}
+
+// NumPy's float `%` (npy_divmod): fmod, then the sign of the divisor
+__device__ __forceinline__ double np_mod(double a, double b) {
+  double m = fmod(a, b);
+  if (m != 0.0) {
+    if ((b < 0.0) != (m < 0.0)) m += b;
+  } else {
+    m = copysign(0.0, b);
+  }
+  return m;
 }
 
 int fill_common(Common& c, const eb_state* st, const eb_prior* prior, const eb_like* like, bool need_fused);
 
 static inline size_t smem_bytes(const Common& c, int extra = 0) {
-  return sizeof(double) * (size_t)(3 * c.D + c.like_nparams + extra);
+  return sizeof(double) * (size_t)(PRIOR_ROWS * c.D + c.like_nparams + extra);
 }
 
 static inline int bucket(int LD) { return LD <= 8 ? 8 : LD <= 16 ? 16 : LD <= 24 ? 24 : 32; }

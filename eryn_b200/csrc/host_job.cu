@@ -97,7 +97,7 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   st.ntemps = T; st.nwalkers = W; st.nleaves = L; st.ndim = D; st.temp_offset = 0; st.inds_stride = 0;
   st.coords = (double*)cx.coords.p; st.logl = (double*)cx.logl.p; st.logp = (double*)cx.logp.p;
   st.inds = nullptr; st.betas = job->betas_host ? (double*)cx.betas.p : nullptr;
-  eb_prior prior{(const double*)cx.prior.p, (const double*)cx.prior.p + D, (const double*)cx.prior.p + 2 * D};
+  eb_prior prior{(const double*)cx.prior.p, (const double*)cx.prior.p + D, (const double*)cx.prior.p + 2 * D, nullptr};
   eb_like like{job->like_kind, job->like_ncomp, job->like_nparams, 0, (const double*)cx.like.p};
   eb_ctrl* dctrl = (eb_ctrl*)cx.ctrl.p;
   eb_stretch_rng srng;

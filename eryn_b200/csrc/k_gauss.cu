@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
   const Common& c = p.c;
   stage_params(c, sm);
   const int D = EXACT ? DMAX : c.D;
-  double* s_chol = sm + 3 * D + c.like_nparams;
+  double* s_chol = sm + PRIOR_ROWS * D + c.like_nparams;
   if (PHILOX && p.cov_kind == 1) {
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) s_chol[i] = p.chol[i];
     __syncthreads();
@@ -76,6 +76,11 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
         if (EXACT || j < D) q[j] = q[j] + dl[j];
     }
     u_acc = p.u_acc[tid];
+  }
+  if (c.per && active) {                                                     // gaussian.py:111-129
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if ((EXACT || j < D) && sm[3 * D + j] > 0.0) q[j] = np_mod(q[j], sm[3 * D + j]);
   }
   const double ll0 = c.logl[tid], lp0 = c.logp[tid];
   const bool tempered = c.betas != nullptr;

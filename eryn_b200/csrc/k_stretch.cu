@@ -106,9 +106,28 @@ __device__ __forceinline__ void job_finish(const StretchArgs& p, const double* s
   double cc[DMAX];
   load_row<DMAX>(c.coords + ((size_t)t * c.W + j.wc) * LD, LD, cc);          // c_temp (stretch.py:100)
   const bool tempered = c.betas != nullptr;
+  if (c.per) {
+    // periodic parameters (single leaf: LD == D): the distance from s to c goes through the boundary when that is
+    // shorter (utils/periodic.py:49-117), the proposal is wrapped into [0, period) (:119-151)
+    const double* per = sm + 3 * LD;
 #pragma unroll
-  for (int d = 0; d < DMAX; ++d)
-    if (EXACT || d < LD) j.q[d] = cc[d] - (cc[d] - j.q[d]) * j.zz;           // stretch.py:143-145
+    for (int d = 0; d < DMAX; ++d)
+      if (EXACT || d < LD) {
+        const double P = per[d], s0 = j.q[d];
+        double diff = cc[d] - s0;
+        if (P > 0.0 && fabs(diff) > P / 2.0) {
+          const double new_s = diff < 0.0 ? -(P - s0) : (P + s0);
+          diff = cc[d] - new_s;
+        }
+        double v = cc[d] - diff * j.zz;                                       // stretch.py:145
+        if (P > 0.0) v = np_mod(v, P);
+        j.q[d] = v;
+      }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d)
+      if (EXACT || d < LD) j.q[d] = cc[d] - (cc[d] - j.q[d]) * j.zz;         // stretch.py:143-145
+  }
   double lp, ll;
   eval_point<DMAX, LIKE, EXACT>(j.q, c, sm, j.active, lp, ll);               // red_blue.py:260,270
   const double logP = log_posterior(ll, lp, j.beta, tempered);               // red_blue.py:283
@@ -213,7 +232,14 @@ __global__ void __launch_bounds__(BLOCK) stretch_propose_kernel(const StretchArg
   const double* sr = c.coords + ((size_t)t * c.W + w) * c.LD;
   const double* cr = c.coords + ((size_t)t * c.W + wc) * c.LD;
   double* q = p.q_out + (size_t)tid * c.LD;
-  for (int j = 0; j < c.LD; ++j) q[j] = cr[j] - (cr[j] - sr[j]) * zz;
+  for (int j = 0; j < c.LD; ++j) {
+    const double P = c.per ? c.per[j % c.D] : 0.0;
+    double diff = cr[j] - sr[j];
+    if (P > 0.0 && fabs(diff) > P / 2.0) diff = cr[j] - (diff < 0.0 ? -(P - sr[j]) : (P + sr[j]));
+    double v = cr[j] - diff * zz;
+    if (P > 0.0) v = np_mod(v, P);
+    q[j] = v;
+  }
   p.factors_out[tid] = ((double)c.LD - 1.0) * log(zz);
   p.sub_out[tid] = w;
 }
@@ -403,11 +429,12 @@ int eb_stretch_step(const eb_state* st, const eb_prior* prior, const eb_like* li
   return check_launch("stretch_step");
 }
 
-int eb_stretch_propose(const eb_state* st, double a, int32_t split, const eb_stretch_rng* rng, double* q,
-                       double* factors, int32_t* sub_out, void* stream) {
+int eb_stretch_propose(const eb_state* st, double a, int32_t split, const eb_stretch_rng* rng, const double* period,
+                       double* q, double* factors, int32_t* sub_out, void* stream) {
   StretchArgs args;
   int rc = fill_common(args.c, st, nullptr, nullptr, false);
   if (rc) return rc;
+  args.c.per = period;
   rc = fill_stretch_args(args, st, a, rng, false);
   if (rc) return rc;
   if (split != 0 && split != 1) return fail(EB_ERR_INVALID, "split must be 0 or 1 (nsplits == 2)");

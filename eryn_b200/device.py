@@ -55,7 +55,7 @@ class DeviceContext(object):
     rng = "numpy-replay" parity: the host draws NumPy randoms in the reference's order and the kernels
                           consume them (bit-identical accept masks to the reference)."""
 
-    def __init__(self, priors, log_like_fn, device=None, rng="philox", seed=0, branch_name="model_0"):
+    def __init__(self, priors, log_like_fn, device=None, rng="philox", seed=0, branch_name="model_0", periodic=None):
         self._init_common(device, rng, seed)
         self.branch_name = branch_name
         if isinstance(priors, dict):
@@ -63,8 +63,17 @@ class DeviceContext(object):
         self.priors = priors
         lo, hi, lp = priors.arrays()
         self.ndim = len(lo)
-        self._prior_dev = torch.from_numpy(np.stack([lo, hi, lp])).to(self.device)
-        self._prior_c = _lib.eb_prior(_ptr(self._prior_dev[0]), _ptr(self._prior_dev[1]), _ptr(self._prior_dev[2]))
+        # periodic parameters: {index: period} (utils/periodic.py:16-47), a dense [ndim] array on the device (0 = none)
+        per = np.zeros(self.ndim)
+        if periodic:
+            for idx, period in periodic.items():
+                if not isinstance(idx, (int, np.integer)):
+                    raise ValueError("If providing str values for the variable names, must provide key_order argument.")
+                per[int(idx)] = float(period)
+        self.periods = per if per.any() else None
+        self._prior_dev = torch.from_numpy(np.stack([lo, hi, lp, per])).to(self.device)
+        self._prior_c = _lib.eb_prior(_ptr(self._prior_dev[0]), _ptr(self._prior_dev[1]), _ptr(self._prior_dev[2]),
+                                      _ptr(self._prior_dev[3]) if self.periods is not None else None)
         self.like = log_like_fn
         if isinstance(log_like_fn, DeviceLikelihood):
             p = np.ascontiguousarray(log_like_fn.params(), dtype=np.float64)
@@ -254,8 +263,10 @@ class DeviceContext(object):
             q = torch.empty((T * Ns, L, D), dtype=torch.float64, device=self.device)
             factors = torch.empty(T * Ns, dtype=torch.float64, device=self.device)
             sub = torch.empty(T * Ns, dtype=torch.int32, device=self.device)
-            _lib.check(self.lib.eb_stretch_propose(C.byref(st), float(a), int(split), C.byref(r), _ptr(q),
-                                                   _ptr(factors), _ptr(sub), self.stream()), "eb_stretch_propose")
+            _lib.check(self.lib.eb_stretch_propose(C.byref(st), float(a), int(split), C.byref(r),
+                                                   _ptr(self._prior_dev[3]) if self.periods is not None else None,
+                                                   _ptr(q), _ptr(factors), _ptr(sub), self.stream()),
+                       "eb_stretch_propose")
             inds_sub = None
             if d.inds is not None:
                 inds_sub = torch.gather(d.inds, 1, sub.view(T, Ns, 1).long().expand(T, Ns, L)).reshape(T * Ns, L).contiguous()

@@ -55,7 +55,7 @@ class EnsembleSampler(object):
                  fill_zero_leaves_val=-1e300, num_repeats_in_model=1, track_moves=True, info={},
                  rng="philox", seed=None, device=None):
         for name, val in (("provide_groups", provide_groups), ("provide_supplemental", provide_supplemental),
-                          ("pool", pool), ("periodic", periodic), ("args", args), ("kwargs", kwargs)):
+                          ("pool", pool), ("args", args), ("kwargs", kwargs)):
             if val:
                 raise NotImplementedError(f"{name} is outside the device hot path built so far (DESIGN.md §7)")
         if fill_zero_leaves_val != -1e300:
@@ -124,6 +124,8 @@ class EnsembleSampler(object):
         if seed is None:
             seed = int(state[1][0]) | (int(state[1][1]) << 32)
 
+        if self._mb and periodic is not None:
+            raise NotImplementedError("periodic parameters are handled by the single-branch kernels (DESIGN.md §7)")
         if self._mb:
             from .moves import DistributionGenerateRJ, GroupStretchMove
             from .multibranch import MBContext
@@ -150,7 +152,13 @@ class EnsembleSampler(object):
                 self.rj_weights = np.ones(len(self.rj_moves)) / len(self.rj_moves)
         else:
             self.rj_moves, self.rj_weights = None, None
-            self.ctx = DeviceContext(priors[name], log_like_fn, device=device, rng=rng, seed=seed, branch_name=name)
+            per = None
+            if periodic is not None:  # ensemble.py:338-347
+                if not isinstance(periodic, dict):
+                    raise ValueError("periodic must be PeriodicContainer or dict if not None.")
+                per = periodic.get(name)
+            self.ctx = DeviceContext(priors[name], log_like_fn, device=device, rng=rng, seed=seed, branch_name=name,
+                                     periodic=per)
         self.log_like_fn = self.ctx.like
         if self.temperature_control is not None:
             self.temperature_control.bind(self.ctx)
@@ -158,6 +166,8 @@ class EnsembleSampler(object):
             if self.temperature_control is not None and move.temperature_control is None:
                 move.temperature_control = self.temperature_control  # ensemble.py:516-525
             move.bind(self.ctx)
+            if periodic is not None and move.periodic is None:
+                move.periodic = periodic  # ensemble.py:528-536
             move.accepted = np.zeros((self.ntemps, self.nwalkers))  # ensemble.py:539-540
 
         self.backend = Backend() if backend is None else backend

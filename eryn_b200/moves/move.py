@@ -8,11 +8,9 @@ __all__ = ["Move"]
 
 class Move(object):
     def __init__(self, temperature_control=None, periodic=None, ctx=None, **kwargs):
-        if periodic is not None:
-            raise NotImplementedError("periodic parameters are a 'next' row (SURVEY.md §8f) of the device path")
         if kwargs:
             raise NotImplementedError(f"unsupported Move kwargs on the device path: {sorted(kwargs)}")
-        self.periodic = None
+        self.periodic = periodic  # applied inside the kernels through the DeviceContext (utils/periodic.py)
         self._accepted = None
         self._accepted_dev = None
         self.num_proposals = 0

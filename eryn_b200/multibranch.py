@@ -106,7 +106,8 @@ class MBContext(DeviceContext):
         self.priors = {n: priors[n] for n in branch_names}
         lo, hi, lp = [np.concatenate([self.priors[n].arrays()[k] for n in branch_names]) for k in range(3)]
         self._prior_dev = torch.from_numpy(np.stack([lo, hi, lp])).to(self.device)
-        self._prior_c = _lib.eb_prior(_ptr(self._prior_dev[0]), _ptr(self._prior_dev[1]), _ptr(self._prior_dev[2]))
+        self._prior_c = _lib.eb_prior(_ptr(self._prior_dev[0]), _ptr(self._prior_dev[1]), _ptr(self._prior_dev[2]), None)
+        self.periods = None
         self._t_dev, self._y_dev = self.to_dev(like.t), self.to_dev(like.y)
         self._data_c = _lib.eb_pulse_data(len(like.t), 0, like.sigma, _ptr(self._t_dev), _ptr(self._y_dev))
         if self.lib.eb_mb_aux_stride(C.byref(self.layout.c)) != self.layout.aux_stride:

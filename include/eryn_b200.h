@@ -32,7 +32,7 @@ extern "C" {
 #define EB_API
 #endif
 
-#define EB_ABI_VERSION 2
+#define EB_ABI_VERSION 3
 #define EB_MAX_TEMPS 128
 #define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
 #define EB_MAX_RANKS 16 /* GPUs of one temperature-sharded run */
@@ -79,6 +79,10 @@ typedef struct {
   const double* lo;     /* [D] */
   const double* hi;     /* [D] */
   const double* logpdf; /* [D] log(1/(hi-lo)) as the host computed it (prior.py:40-41) */
+  const double* period; /* [D] period of each parameter, 0 = not periodic; NULL = no periodic parameters.  The stretch
+                           proposal then takes the distance through the boundary when that is shorter and wraps the
+                           proposal into [0, period) (utils/periodic.py:49-151, stretch.py:136-153); the Gaussian
+                           proposal wraps (gaussian.py:111-129).  Single-branch kernels only. */
 } eb_prior;
 
 typedef struct {
@@ -352,6 +356,7 @@ EB_API int eb_advance_iter(eb_ctrl* ctrl, void* stream);
  *      (red_blue.py:283-323, move.py:472).  q [T][Ns][L][D], factors [T][Ns],
  *      sub_out [T][Ns] int32 = walker ids the rows of q belong to. */
 EB_API int eb_stretch_propose(const eb_state* st, double a, int32_t split, const eb_stretch_rng* rng,
+                       const double* period /* [D] as eb_prior.period, or NULL */,
                        double* q, double* factors, int32_t* sub_out, void* stream);
 EB_API int eb_accept_update(const eb_state* st, const int32_t* sub, int32_t nsub, const double* q,
                      const double* factors, const double* logl_new, const double* logp_new,

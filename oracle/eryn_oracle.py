@@ -200,7 +200,28 @@ def update_subset(state, sub, q, new_logl, new_logp, keep):
 # ----------------------------------------------------------------------------------
 # moves
 # ----------------------------------------------------------------------------------
-def stretch_half_step(state, sub, comp, rint, u_z, u_acc, a, betas, prior, like):
+def periodic_distance(s, c, periods):
+    """utils/periodic.py:49-117 with p1 = s, p2 = c (stretch.py:136-141): c - s, through the boundary when that is
+    shorter.  periods [D]: period of each parameter, 0 = not periodic."""
+    diff = c - s
+    for d in np.nonzero(periods)[0]:
+        P = periods[d]
+        dp = diff[..., d].copy()
+        fix = np.abs(dp) > P / 2.0
+        new_s = -(P - s[..., d]) * (dp < 0.0) + (P + s[..., d]) * (dp >= 0.0)
+        dp[fix] = c[..., d][fix] - new_s[fix]
+        diff[..., d] = dp
+    return diff
+
+
+def periodic_wrap(q, periods):
+    """utils/periodic.py:119-151: q % period on the periodic parameters (in place)."""
+    for d in np.nonzero(periods)[0]:
+        q[..., d] = q[..., d] % periods[d]
+    return q
+
+
+def stretch_half_step(state, sub, comp, rint, u_z, u_acc, a, betas, prior, like, periods=None):
     """One red/blue half step (red_blue.py:148-323 + stretch.py:74-231).
 
     sub [T,Ns] / comp [T,Nc]: walker ids of the moving subset / the complement, in the order
@@ -210,7 +231,10 @@ def stretch_half_step(state, sub, comp, rint, u_z, u_acc, a, betas, prior, like)
     c = np.take_along_axis(state.coords, comp[:, :, None, None], axis=1)
     c_temp = np.take_along_axis(c, rint[:, :, None, None], axis=1)  # stretch.py:100
     zz = ((a - 1.0) * u_z + 1) ** 2.0 / a  # stretch.py:129-132
-    q = c_temp - (c_temp - s) * zz[:, :, None, None]  # stretch.py:143-145
+    if periods is not None:
+        q = periodic_wrap(c_temp - periodic_distance(s, c_temp, periods) * zz[:, :, None, None], periods)  # :136-153
+    else:
+        q = c_temp - (c_temp - s) * zz[:, :, None, None]  # stretch.py:143-145
     factors = (L * D - 1.0) * np.log(zz)  # stretch.py:223
     new_inds = np.take_along_axis(state.inds, sub[:, :, None], axis=1)
     logp = box_log_prior(prior, q, new_inds)  # red_blue.py:260
@@ -226,7 +250,7 @@ def stretch_half_step(state, sub, comp, rint, u_z, u_acc, a, betas, prior, like)
     return keep, dict(q=q, logl=logl, logp=logp, zz=zz, lnpdiff=lnpdiff)
 
 
-def gaussian_step(state, delta, u_acc, betas, prior, like):
+def gaussian_step(state, delta, u_acc, betas, prior, like, periods=None):
     """MH step with an additive proposal (mh.py:56-193, gaussian.py:68-131).
 
     delta [T,W,L,D] is the proposal increment (scale*randn or multivariate_normal draw) for
@@ -234,6 +258,8 @@ def gaussian_step(state, delta, u_acc, betas, prior, like):
     T, W, L, D = state.coords.shape
     q = state.coords.copy()
     q[state.inds] = (state.coords + delta)[state.inds]  # gaussian.py:99-108
+    if periods is not None:
+        periodic_wrap(q, periods)  # gaussian.py:111-129
     logp = box_log_prior(prior, q, state.inds)
     logl = log_like(like, q, state.inds, logp)
     logP = tempered_log_posterior(logl, logp, betas)
@@ -425,7 +451,8 @@ class OracleSampler:
     betas None means no TemperatureControl (tempering_kwargs == {})."""
 
     def __init__(self, prior, like, moves, weights, streams, betas=None, adaptive=True,
-                 adaptation_lag=10000, adaptation_time=100, stop_adaptation=-1, permute=True):
+                 adaptation_lag=10000, adaptation_time=100, stop_adaptation=-1, permute=True, periods=None):
+        self.periods = None if periods is None else np.asarray(periods, dtype=np.float64)
         self.prior, self.like = prior, like
         self.moves = moves
         w = np.atleast_1d(np.asarray(weights, dtype=float))
@@ -464,12 +491,12 @@ class OracleSampler:
                     flat = (np.arange(T)[:, None] * W + sub).astype(np.uint32)
                     u_acc = st.accept_for(it, split, flat)
                 keep, _ = stretch_half_step(state, sub, comp, rint, u_z, u_acc, move.get("a", 2.0),
-                                            self.betas, self.prior, self.like)
+                                            self.betas, self.prior, self.like, self.periods)
                 np.put_along_axis(accepted, sub, keep, axis=1)
         elif move["kind"] == "gaussian":
             delta = st.gauss_increment(it, state.inds, D, move["proposal"])
             u_acc = st.accept_uniforms(it, 0, T, W)
-            keep, _ = gaussian_step(state, delta, u_acc, self.betas, self.prior, self.like)
+            keep, _ = gaussian_step(state, delta, u_acc, self.betas, self.prior, self.like, self.periods)
             accepted = keep
         else:
             raise ValueError(move["kind"])

@@ -30,6 +30,10 @@ CASES = {
     "gauss_matrix": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                          moves=[dict(kind="gaussian", proposal=dict(kind="matrix", cov=COV3))]),
     "odd_walkers": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), moves=[dict(kind="stretch", a=1.5)]),
+    "periodic_mix": dict(like=lambda d: orc.GaussianLike(np.array([0.2, 6.1, 3.0]), np.eye(3) / 0.49),
+                         moves=[dict(kind="stretch", a=2.0),
+                                dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.25)))],
+                         weights=[0.5, 0.5], periods=np.array([2 * np.pi, 2 * np.pi, 0.0])),
     "noadapt_noperm": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                            moves=[dict(kind="stretch", a=2.0)], adaptive=False, permute=False),
 }

@@ -77,7 +77,7 @@ def corr_prec(d, seed=99):
 
 
 def run_case(name, seed, ndim, nwalkers, ntemps, nits, like, like_args, vectorize, lo, hi,
-             moves_factory=None, tempering_kwargs=None):
+             moves_factory=None, tempering_kwargs=None, periodic=None):
     np.random.seed(seed)
     priors = ProbDistContainer({i: uniform_dist(lo, hi) for i in range(ndim)})
     tk = {} if ntemps is None else dict(ntemps=ntemps)
@@ -85,7 +85,7 @@ def run_case(name, seed, ndim, nwalkers, ntemps, nits, like, like_args, vectoriz
         tk.update(tempering_kwargs)
     moves = moves_factory() if moves_factory else None
     sampler = EnsembleSampler(nwalkers, ndim, like, priors, args=like_args, tempering_kwargs=tk,
-                              moves=moves, vectorize=vectorize)
+                              moves=moves, vectorize=vectorize, periodic=periodic)
     T = sampler.ntemps
     x0 = priors.rvs(size=(T, nwalkers))
     rec = dict(coords=[], logl=[], logp=[], accepted=[], swaps=[], betas=[], move=[])
@@ -133,6 +133,13 @@ def run_case(name, seed, ndim, nwalkers, ntemps, nits, like, like_args, vectoriz
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "periodic":
+        mu3 = np.array([0.2, 6.1, 3.0])
+        per = {"model_0": {0: 2 * np.pi, 1: 2 * np.pi}}
+        # walkers start uniform over [0, 2 pi): the periodic distance (|c - s| > pi) and the wrap are exercised constantly
+        run_case("periodic_mix", 21, 3, 24, 3, 40, ll_gauss_vec, [mu3, np.eye(3) / 0.49], True, 0.0, 2 * np.pi,
+                 moves_factory=lambda: [(StretchMove(), 0.5), (GaussianMove({"model_0": 0.25}), 0.5)], periodic=per)
+        sys.exit(0)
     run_case("c1_kat1", 42, 5, 32, None, 100, ll_single, [np.zeros(5), np.eye(5)], False, -5.0, 5.0)
     run_case("pt_kat2", 42, 3, 16, 4, 50, ll_single, [np.zeros(3), np.eye(3)], False, -5.0, 5.0)
     P8 = corr_prec(8)

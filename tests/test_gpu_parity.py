@@ -61,8 +61,11 @@ def test_replay_matches_reference_golden(name):
         tk = dict(ntemps=T, adaptive=c.get("adaptive", True), permute=c.get("permute", True))
     moves = dev_moves(c["moves"])
     w = c.get("weights", [1.0] * len(moves))
+    periodic = None
+    if c.get("periods") is not None:
+        periodic = {"model_0": {i: float(p) for i, p in enumerate(c["periods"]) if p > 0}}
     sampler = EnsembleSampler(W, d, dev_like(c["like"](d)), priors, tempering_kwargs=tk,
-                              moves=list(zip(moves, w)), rng="numpy-replay")
+                              moves=list(zip(moves, w)), rng="numpy-replay", periodic=periodic)
     x0 = priors.rvs(size=(T, W))
     assert np.array_equal(x0, g["x0"])
     prev = [np.zeros((T, W)) for _ in moves]
@@ -152,14 +155,16 @@ PHILOX_CASES = {
 }
 
 
-def run_philox_case(T, W, d, like_f, moves, weights, nits, lo, hi, seed=2024, untempered=False, check_every=1):
+def run_philox_case(T, W, d, like_f, moves, weights, nits, lo, hi, seed=2024, untempered=False, check_every=1,
+                    periods=None):
     from eryn_b200 import EnsembleSampler
     from eryn_b200.prior import ProbDistContainer, uniform_dist
     olike = like_f(d)
     prior = orc.BoxPrior(np.full(d, float(lo)), np.full(d, float(hi)))
     betas = None if untempered else (orc.make_ladder_default(d, T) if T > 1 else np.array([1.0]))
     sched = np.random.RandomState(7)
-    osmp = orc.OracleSampler(prior, olike, moves, weights, orc.PhiloxStreams(seed, schedule_random=sched), betas=betas)
+    osmp = orc.OracleSampler(prior, olike, moves, weights, orc.PhiloxStreams(seed, schedule_random=sched), betas=betas,
+                             periods=periods)
     x0 = np.random.RandomState(1).uniform(max(lo, -3), min(hi, 3), size=(T, W, d))
     ost = osmp.initialise(orc.OState(x0))
 
@@ -167,8 +172,9 @@ def run_philox_case(T, W, d, like_f, moves, weights, nits, lo, hi, seed=2024, un
     priors = ProbDistContainer({i: uniform_dist(float(lo), float(hi)) for i in range(d)})
     tk = {} if untempered else dict(ntemps=T)
     dm = dev_moves(moves)
+    periodic = None if periods is None else {"model_0": {i: float(p) for i, p in enumerate(periods) if p > 0}}
     smp = EnsembleSampler(W, d, dev_like(olike), priors, tempering_kwargs=tk, moves=list(zip(dm, weights)),
-                          rng="philox", seed=seed)
+                          rng="philox", seed=seed, periodic=periodic)
     n_acc = 0
     for it, state in enumerate(smp.sample(x0, iterations=nits, store=False)):
         acc_o = osmp.iterate(ost)
@@ -190,6 +196,18 @@ def run_philox_case(T, W, d, like_f, moves, weights, nits, lo, hi, seed=2024, un
 @pytest.mark.parametrize("name", list(PHILOX_CASES))
 def test_philox_matches_oracle(name):
     run_philox_case(*PHILOX_CASES[name])
+
+
+def test_philox_periodic_matches_oracle():
+    """periodic parameters (utils/periodic.py) in the fused kernels, production streams, D = 8 (exact-length kernel) and
+    D = 5 (padded kernel); walkers start uniform over the period so distances through the boundary are common"""
+    for d, T, W in ((8, 4, 256), (5, 3, 64)):
+        periods = np.zeros(d)
+        periods[[0, 2, d - 1]] = [3.0, 2 * np.pi, 1.5]
+        mu = np.linspace(0.1, 1.4, d)
+        run_philox_case(T, W, d, lambda dd: orc.GaussianLike(mu, np.eye(dd) / 0.3),
+                        [dict(kind="stretch", a=2.0), dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.3))],
+                        [0.5, 0.5], 12, 0.0, 7.0, periods=periods)
 
 
 def test_philox_untempered_matches_oracle():

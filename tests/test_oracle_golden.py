@@ -19,7 +19,8 @@ def make_oracle(name, g, streams):
     if bool(g["tempered"]):
         betas = orc.make_ladder_default(d, T) if T > 1 else np.array([1.0])
     return orc.OracleSampler(prior, c["like"](d), c["moves"], c.get("weights", [1.0]), streams, betas=betas,
-                             adaptive=c.get("adaptive", True), permute=c.get("permute", True)), prior
+                             adaptive=c.get("adaptive", True), permute=c.get("permute", True),
+                             periods=c.get("periods")), prior
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))

@@ -131,7 +131,7 @@ int main(int argc, char** argv) {
   CK(cudaMemset(ctrl, 0, sizeof(eb_ctrl))); CK(cudaMemset(cnt, 0, n * 4));
   eb_state st; std::memset(&st, 0, sizeof(st));
   st.ntemps = T; st.nwalkers = W; st.nleaves = 1; st.ndim = D; st.coords = coords; st.logl = logl; st.logp = logp; st.betas = betas;
-  eb_prior prior{pr, pr + D, pr + 2 * D};
+  eb_prior prior{pr, pr + D, pr + 2 * D, nullptr};
   eb_like like{LK, LK == 2 ? KM : 0, nlk, 0, lk};
   EB(eb_eval_state(&st, &prior, &like, s));
   eb_stretch_rng sr; std::memset(&sr, 0, sizeof(sr));
