@@ -32,7 +32,26 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
   load_row<DMAX>(c.coords + (size_t)tid * D, D, q);
   const bool active = c.inds ? (c.inds[tid] != 0) : true;
   double u_acc;
-  if (PHILOX) {
+  double factors = 0.0;                                                      // gaussian.py:131
+  if (p.cov_kind == 2 && active)                                             // distgen.py:96: + log q(old)
+    factors += +1.0 * box_logpdf_leaf<DMAX, EXACT>(q, D, sm, sm + D, sm + 2 * D);
+  if (PHILOX && p.cov_kind == 2) {
+    // DistributionGenerate: every active leaf is redrawn from the (uniform) priors, distgen.py:99 / prior.py:66
+    const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
+    const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
+#pragma unroll
+    for (int j = 0; j < DMAX; j += 2) {
+      if (EXACT || j < D) {
+        const uint4 r = stream(key, TAG_GAUSS, (uint32_t)(tid + c.t0 * c.W), (uint32_t)(j >> 1));
+        if (active) {
+          q[j] = u01_52(r.x, r.y) * (sm[D + j] - sm[j]) + sm[j];
+          if (j + 1 < DMAX && (EXACT || j + 1 < D)) q[j + 1] = u01_52(r.z, r.w) * (sm[D + j + 1] - sm[j + 1]) + sm[j + 1];
+        }
+      }
+    }
+    const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)(tid + c.t0 * c.W), 0u);
+    u_acc = u01_52(ra.x, ra.y);
+  } else if (PHILOX) {
     const unsigned long long it = p.iter_dev ? *p.iter_dev : p.iter;
     const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
     double z[DMAX];
@@ -73,11 +92,11 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
     if (active) {
 #pragma unroll
       for (int j = 0; j < DMAX; ++j)
-        if (EXACT || j < D) q[j] = q[j] + dl[j];
+        if (EXACT || j < D) q[j] = p.cov_kind == 2 ? dl[j] : q[j] + dl[j];   // distgen: dl is the new point itself
     }
     u_acc = p.u_acc[tid];
   }
-  if (c.per && active) {                                                     // gaussian.py:111-129
+  if (c.per && active && p.cov_kind != 2) {                                  // gaussian.py:111-129 (distgen.py does not wrap)
 #pragma unroll
     for (int j = 0; j < DMAX; ++j)
       if ((EXACT || j < D) && sm[3 * D + j] > 0.0) q[j] = np_mod(q[j], sm[3 * D + j]);
@@ -89,7 +108,9 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
   eval_point<DMAX, LIKE, EXACT>(q, c, sm, active, lp, ll);                          // mh.py:134-148
   const double logP = log_posterior(ll, lp, beta, tempered);
   const double prevP = log_posterior(ll0, lp0, beta, tempered);
-  const bool keep = (0.0 + logP - prevP) > log(u_acc);                       // mh.py:168-171
+  if (p.cov_kind == 2 && active)                                             // distgen.py:102: - log q(new)
+    factors += -1.0 * box_logpdf_leaf<DMAX, EXACT>(q, D, sm, sm + D, sm + 2 * D);
+  const bool keep = (factors + logP - prevP) > log(u_acc);                   // mh.py:168-171
   if (keep) {
     store_row<DMAX>(c.coords + (size_t)tid * D, D, q);
     c.logl[tid] = ll;
@@ -162,7 +183,7 @@ int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* l
   args.accepted = accepted; args.accepted_count = accepted_count;
   if (args.philox) {
     if (rng->cov_kind == 1 && !rng->chol) return fail(EB_ERR_INVALID, "matrix proposal needs the Cholesky factor");
-    if (rng->cov_kind != 0 && rng->cov_kind != 1) return fail(EB_ERR_INVALID, "Invalid proposal scale dimensions");
+    if (rng->cov_kind < 0 || rng->cov_kind > 2) return fail(EB_ERR_INVALID, "Invalid proposal scale dimensions");
   } else if (rng->mode == EB_RNG_REPLAY) {
     if (!rng->delta || !rng->u_acc) return fail(EB_ERR_INVALID, "replay mode needs delta and u_acc");
   } else {

@@ -291,6 +291,8 @@ class DeviceContext(object):
             r.iter_dev = self.iter_ptr
             if proposal["kind"] == "scalar":
                 r.cov_kind, r.scale = 0, float(proposal["scale"])
+            elif proposal["kind"] == "prior":
+                r.cov_kind = 2
             else:
                 keep = self.to_dev(proposal["chol"], np.float64)
                 r.cov_kind, r.chol = 1, _ptr(keep)
@@ -298,6 +300,7 @@ class DeviceContext(object):
             delta, u_acc = replay
             keep = (self.to_dev(delta, np.float64), self.to_dev(u_acc, np.float64))
             r.mode = _lib.EB_RNG_REPLAY
+            r.cov_kind = 2 if proposal["kind"] == "prior" else 0
             r.delta, r.u_acc = _ptr(keep[0]), _ptr(keep[1])
         acc = self.accepted_mask(T, W)
         _lib.check(self.lib.eb_gaussian_step(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c), C.byref(r),

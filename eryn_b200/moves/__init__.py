@@ -1,3 +1,4 @@
+from .distgen import DistributionGenerate
 from .gaussian import GaussianMove
 from .group import GroupStretchMove
 from .rj import DistributionGenerateRJ, ReversibleJumpMove
@@ -5,5 +6,5 @@ from .move import Move
 from .stretch import StretchMove
 from .tempering import TemperatureControl, make_ladder
 
-__all__ = ["Move", "StretchMove", "GaussianMove", "GroupStretchMove", "ReversibleJumpMove", "DistributionGenerateRJ",
+__all__ = ["Move", "StretchMove", "GaussianMove", "GroupStretchMove", "ReversibleJumpMove", "DistributionGenerateRJ", "DistributionGenerate",
            "TemperatureControl", "make_ladder"]

@@ -121,7 +121,9 @@ typedef struct {
 /* Random inputs of one Gaussian Metropolis step (gaussian.py:68-195, mh.py:171). */
 typedef struct {
   int32_t mode;
-  int32_t cov_kind;       /* 0 scalar (gaussian.py:166), 1 full matrix via Cholesky factor (gaussian.py:192) */
+  int32_t cov_kind;       /* 0 scalar (gaussian.py:166), 1 full matrix via Cholesky factor (gaussian.py:192),
+                             2 DistributionGenerate: every active leaf redrawn from the priors, factors =
+                             log q(old) - log q(new) (distgen.py:34-104); replay: `delta` holds the new points */
   double scale;           /* sqrt(cov) for cov_kind 0 */
   const double* chol;     /* [D][D] lower Cholesky factor for cov_kind 1 (philox mode) */
   const double* delta;    /* replay [T][W][L][D] proposal increment drawn on the host */

@@ -271,6 +271,28 @@ def gaussian_step(state, delta, u_acc, betas, prior, like, periods=None):
     return keep, dict(q=q, logl=logl, logp=logp, lnpdiff=lnpdiff)
 
 
+def distgen_step(state, new_points, u_acc, betas, prior, like):
+    """MH step that redraws every active leaf from `generate_dist` = the priors (mh.py:56-193 with
+    distgen.py:34-104): factors = +log q(old) - log q(new).  new_points [T,W,L,D]: the draws (0 where inactive)."""
+    T, W, L, D = state.coords.shape
+    q = state.coords.copy()
+    factors = np.zeros((T, W))
+    old = state.coords[state.inds]
+    tw = np.where(state.inds)[:2]
+    factors[tw] += +1 * prior.logpdf(old)  # distgen.py:96
+    q[state.inds] = new_points[state.inds]
+    factors[tw] += -1 * prior.logpdf(q[state.inds])  # distgen.py:102
+    logp = box_log_prior(prior, q, state.inds)
+    logl = log_like(like, q, state.inds, logp)
+    logP = tempered_log_posterior(logl, logp, betas)
+    prev_logP = tempered_log_posterior(state.logl, state.logp, betas)
+    lnpdiff = factors + logP - prev_logP  # mh.py:168
+    keep = lnpdiff > np.log(u_acc)  # mh.py:171
+    sub = np.tile(np.arange(W), (T, 1))
+    update_subset(state, sub, q, logl, logp, keep)
+    return keep, dict(q=q, logl=logl, logp=logp, lnpdiff=lnpdiff)
+
+
 # ----------------------------------------------------------------------------------
 # parallel tempering
 # ----------------------------------------------------------------------------------
@@ -363,6 +385,12 @@ class NumpyStreams:
         delta[inds] = d
         return delta
 
+    def prior_draws(self, it, inds, prior):
+        """distgen.py:99: generate_dist.rvs(size=n) -> one global rand(n) per parameter (prior.py:56-71, :432-497)"""
+        out = np.zeros(inds.shape + (len(prior.lo),))
+        out[inds] = prior.rvs(int(inds.sum()), self.glob)
+        return out
+
     def accept_uniforms(self, it, slot, T, W):
         return self.private.rand(T, W)  # mh.py:171
 
@@ -423,6 +451,20 @@ class PhiloxStreams:
         delta = d.reshape(T, W, L, D)
         delta[~inds] = 0.0
         return delta
+
+    def prior_draws(self, it, inds, prior):
+        """uniform u of (flat leaf, parameter d): TAG_GAUSS block (flat, d // 2), word pair d % 2 (k_gauss.cu)"""
+        T, W, L = inds.shape
+        D = len(prior.lo)
+        flat = np.arange(T * W * L, dtype=np.uint32) + np.uint32(self.t0 * W * L)
+        out = np.zeros((T * W * L, D))
+        for d in range(D):
+            r = px._stream(px.TAG_GAUSS, it, self.seed, flat, np.uint32(d // 2))
+            u = px.u01_52(r[2], r[3]) if d % 2 else px.u01_52(r[0], r[1])
+            out[:, d] = u * (prior.hi[d] - prior.lo[d]) + prior.lo[d]
+        out = out.reshape(T, W, L, D)
+        out[~inds] = 0.0
+        return out
 
     def accept_uniforms(self, it, slot, T, W):
         flat = np.arange(T * W, dtype=np.uint32) + np.uint32(self.t0 * W)
@@ -497,6 +539,11 @@ class OracleSampler:
             delta = st.gauss_increment(it, state.inds, D, move["proposal"])
             u_acc = st.accept_uniforms(it, 0, T, W)
             keep, _ = gaussian_step(state, delta, u_acc, self.betas, self.prior, self.like, self.periods)
+            accepted = keep
+        elif move["kind"] == "distgen":
+            new_points = st.prior_draws(it, state.inds, self.prior)
+            u_acc = st.accept_uniforms(it, 0, T, W)
+            keep, _ = distgen_step(state, new_points, u_acc, self.betas, self.prior, self.like)
             accepted = keep
         else:
             raise ValueError(move["kind"])

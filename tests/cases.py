@@ -34,6 +34,8 @@ CASES = {
                          moves=[dict(kind="stretch", a=2.0),
                                 dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.25)))],
                          weights=[0.5, 0.5], periods=np.array([2 * np.pi, 2 * np.pi, 0.0])),
+    "distgen_mix": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                        moves=[dict(kind="stretch", a=2.0), dict(kind="distgen")], weights=[0.5, 0.5]),
     "noadapt_noperm": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                            moves=[dict(kind="stretch", a=2.0)], adaptive=False, permute=False),
 }

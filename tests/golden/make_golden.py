@@ -48,7 +48,7 @@ import warnings  # noqa: E402
 
 warnings.filterwarnings("ignore")
 from eryn.ensemble import EnsembleSampler  # noqa: E402
-from eryn.moves import GaussianMove, StretchMove  # noqa: E402
+from eryn.moves import DistributionGenerate, GaussianMove, StretchMove  # noqa: E402
 from eryn.prior import ProbDistContainer, uniform_dist  # noqa: E402
 from eryn.state import State  # noqa: E402
 
@@ -80,6 +80,7 @@ def run_case(name, seed, ndim, nwalkers, ntemps, nits, like, like_args, vectoriz
              moves_factory=None, tempering_kwargs=None, periodic=None):
     np.random.seed(seed)
     priors = ProbDistContainer({i: uniform_dist(lo, hi) for i in range(ndim)})
+    run_case.priors = priors
     tk = {} if ntemps is None else dict(ntemps=ntemps)
     if tempering_kwargs:
         tk.update(tempering_kwargs)
@@ -139,6 +140,12 @@ if __name__ == "__main__":
         # walkers start uniform over [0, 2 pi): the periodic distance (|c - s| > pi) and the wrap are exercised constantly
         run_case("periodic_mix", 21, 3, 24, 3, 40, ll_gauss_vec, [mu3, np.eye(3) / 0.49], True, 0.0, 2 * np.pi,
                  moves_factory=lambda: [(StretchMove(), 0.5), (GaussianMove({"model_0": 0.25}), 0.5)], periodic=per)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "distgen":
+        # prior-draw Metropolis move (distgen.py) mixed with the stretch move; narrow box so that prior draws get accepted
+        run_case("distgen_mix", 33, 3, 24, 3, 40, ll_gauss_vec, [np.zeros(3), np.eye(3)], True, -2.0, 2.0,
+                 moves_factory=lambda: [(StretchMove(), 0.5),
+                                        (DistributionGenerate({"model_0": run_case.priors}), 0.5)])
         sys.exit(0)
     run_case("c1_kat1", 42, 5, 32, None, 100, ll_single, [np.zeros(5), np.eye(5)], False, -5.0, 5.0)
     run_case("pt_kat2", 42, 3, 16, 4, 50, ll_single, [np.zeros(3), np.eye(3)], False, -5.0, 5.0)

@@ -28,12 +28,14 @@ def dev_like(olike):
     return lk.GaussianMixtureLikelihood(olike.mus, olike.sigmas, olike.weights)
 
 
-def dev_moves(moves):
-    from eryn_b200.moves import GaussianMove, StretchMove
+def dev_moves(moves, priors=None):
+    from eryn_b200.moves import DistributionGenerate, GaussianMove, StretchMove
     out = []
     for m in moves:
         if m["kind"] == "stretch":
             out.append(StretchMove(a=m.get("a", 2.0)))
+        elif m["kind"] == "distgen":
+            out.append(DistributionGenerate({"model_0": priors}))
         else:
             p = m["proposal"]
             out.append(GaussianMove({"model_0": p["scale"] ** 2 if p["kind"] == "scalar" else p["cov"]}))
@@ -59,7 +61,7 @@ def test_replay_matches_reference_golden(name):
     tk = {}
     if bool(g["tempered"]):
         tk = dict(ntemps=T, adaptive=c.get("adaptive", True), permute=c.get("permute", True))
-    moves = dev_moves(c["moves"])
+    moves = dev_moves(c["moves"], priors)
     w = c.get("weights", [1.0] * len(moves))
     periodic = None
     if c.get("periods") is not None:
@@ -139,6 +141,9 @@ PHILOX_CASES = {
                      [dict(kind="gaussian", proposal=dict(kind="matrix", cov=cases.COV3,
                                                           chol=np.linalg.cholesky(cases.COV3)))], [1.0], 15, -5, 5),
     "c4_slice": (8, 1024, 20, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 5, -10, 10),
+    "distgen": (3, 64, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                [dict(kind="stretch", a=2.0), dict(kind="distgen")], [0.5, 0.5], 12, -2, 2),
+    "distgen_d8": (2, 128, 8, c2_like, [dict(kind="distgen")], [1.0], 6, -1, 1),
     "d13": (2, 64, 13, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 8, -5, 5),
     "d18": (2, 64, 18, lambda d: orc.RosenbrockLike(), [dict(kind="stretch", a=2.0)], [1.0], 8, -5, 5),
     "d30": (2, 128, 30, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -10, 10),
@@ -171,7 +176,7 @@ def run_philox_case(T, W, d, like_f, moves, weights, nits, lo, hi, seed=2024, un
     np.random.seed(7)  # the sampler's private stream (move schedule) = copy of the global state
     priors = ProbDistContainer({i: uniform_dist(float(lo), float(hi)) for i in range(d)})
     tk = {} if untempered else dict(ntemps=T)
-    dm = dev_moves(moves)
+    dm = dev_moves(moves, priors)
     periodic = None if periods is None else {"model_0": {i: float(p) for i, p in enumerate(periods) if p > 0}}
     smp = EnsembleSampler(W, d, dev_like(olike), priors, tempering_kwargs=tk, moves=list(zip(dm, weights)),
                           rng="philox", seed=seed, periodic=periodic)
