@@ -216,10 +216,14 @@ def run_gpu(args):
                        config=dict(workload=wl["label"], ntemps=T, nwalkers=W, ndim=d, rng="philox",
                                    parallelism=f"temperature-sharded x{world} (temp_begin={res['temp_begin']}), "
                                                f"weak scaling: 16 temperatures x 4096 walkers per GPU",
-                                   comm=("NVLink peer stores + flag words, no NCCL on the data path" if res["comm"] == "p2p"
-                                         else "NCCL all_gather of logl + NVLink peer row pulls"),
+                                   comm={"fused": "logl all-gather as NVLink peer stores + iteration flags inside the swap kernel "
+                                                  "(no separate publish launch, no NCCL on the data path)",
+                                         "p2p": "publish kernel: NVLink peer stores + flag words, no NCCL on the data path",
+                                         "nccl": "NCCL all_gather of logl + NVLink peer row pulls"}[res["comm"]],
                                    l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
-                                   step="one iteration = move kernel + publish kernel + sharded swap/adapt kernel"
+                                   step=("one iteration = 2 stretch launches + 1 sharded publish/swap/adapt kernel, chained by "
+                                         "programmatic dependent launch" if res["comm"] == "fused" else
+                                         "one iteration = move kernel + publish kernel + sharded swap/adapt kernel")
                                         + (" (CUDA graph replay)" if res["graph"] else "")),
                        clocks=res["clocks"], e2e=dict(unit=UNIT, **res["e2e"]), gpu_launches=res["launches"],
                        roofline=roof, cpu_baseline=None,
@@ -437,7 +441,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="multi-GPU logl exchange (N > 1)")
+    ap.add_argument("--comm", default="fused", choices=["fused", "p2p", "nccl"], help="multi-GPU logl exchange (N > 1)")
     ap.add_argument("--profile", action="store_true", help="shorten the CPU-baseline leg (for runs under ncu)")
     a = ap.parse_args()
     if a.warmup < 3:

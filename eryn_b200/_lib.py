@@ -81,7 +81,8 @@ class eb_shard(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ntemps_total", C.c_int32),
                 ("temp_begin", C.c_int32 * (EB_MAX_RANKS + 1)),
                 ("coords_src", vp * EB_MAX_RANKS), ("logp_src", vp * EB_MAX_RANKS), ("inds_src", vp * EB_MAX_RANKS),
-                ("logl_all", vp), ("betas_all", vp), ("flags", vp)]
+                ("logl_all", vp), ("betas_all", vp), ("flags", vp),
+                ("pub_src", vp), ("pub_logl_all", vp * EB_MAX_RANKS), ("pub_flags", vp * EB_MAX_RANKS), ("pub_elect", vp)]
 
 
 class eb_publish(C.Structure):
@@ -181,7 +182,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.eb_abi_version() != 3:
+    if lib.eb_abi_version() != 4:
         raise ErynB200Error("liberyn_b200.so ABI version mismatch; rebuild")
     for i, st in enumerate(STRUCTS):
         if lib.eb_struct_size(i) != C.sizeof(st):

@@ -134,7 +134,7 @@ __device__ __forceinline__ void mb_accept(const MBArgs& p, WarpSm& ws, size_t sl
   if (lane == 0) p.accepted[slot] = keep ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(MB_THREADS) mb_eval_kernel(const MBArgs p) {
+__global__ void __launch_bounds__(MB_THREADS) mb_eval_kernel(const __grid_constant__ MBArgs p) {
   __shared__ WarpSm sm[MB_WARPS];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slot = (size_t)blockIdx.x * MB_WARPS + wid;
@@ -164,7 +164,7 @@ __device__ __forceinline__ void nearest_friends(const double* __restrict__ keys,
   }
 }
 
-__global__ void __launch_bounds__(MB_THREADS) mb_friends_kernel(const MBArgs p) {
+__global__ void __launch_bounds__(MB_THREADS) mb_friends_kernel(const __grid_constant__ MBArgs p) {
   const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n = (size_t)p.T * p.W * p.Ltot;
   if (id >= n) return;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(MB_THREADS) mb_friends_kernel(const MBArgs p) 
   nearest_friends(p.fkeys[b], p.nfr[b], v, p.nfriends, tab);
 }
 
-__global__ void __launch_bounds__(MB_THREADS) mb_group_stretch_kernel(const MBArgs p) {
+__global__ void __launch_bounds__(MB_THREADS) mb_group_stretch_kernel(const __grid_constant__ MBArgs p) {
   __shared__ WarpSm sm[MB_WARPS];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slot = (size_t)blockIdx.x * MB_WARPS + wid;
@@ -250,7 +250,7 @@ __device__ __forceinline__ double leaf_logpdf(const MBArgs& p, int b, const doub
   return s;
 }
 
-__global__ void __launch_bounds__(MB_THREADS) mb_rj_kernel(const MBArgs p) {
+__global__ void __launch_bounds__(MB_THREADS) mb_rj_kernel(const __grid_constant__ MBArgs p) {
   __shared__ WarpSm sm[MB_WARPS];
   __shared__ double s_factors[MB_WARPS];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -24,7 +24,7 @@ __host__ __device__ inline int publish_grid(size_t ndoubles) {
 // stores, coalesced); after a block barrier its thread 0 issues one system-scope release fence and ADDS 1 to this
 // rank's flag word on every rank (NVLink atomics).  A flag word therefore counts publishing CTAs: a reader of iteration
 // `it` waits for (it + 1) * publish_grid(rows of that rank).  No ticket, no last-block election, no host.
-__global__ void __launch_bounds__(256) publish_logl_kernel(const PublishArgs p) {
+__global__ void __launch_bounds__(256) publish_logl_kernel(const __grid_constant__ PublishArgs p) {
   const size_t n = (size_t)p.nrows * p.W;                   // doubles to publish
   const size_t off = (size_t)p.t_lo * p.W;
   const size_t n2 = n >> 1;

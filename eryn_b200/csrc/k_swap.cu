@@ -33,6 +33,10 @@ struct SwapArgs {
   int temp_begin[EB_MAX_RANKS + 1];
   const double* coords_src[EB_MAX_RANKS]; const double* logp_src[EB_MAX_RANKS]; const uint8_t* inds_src[EB_MAX_RANKS];
   const unsigned long long* flags;                // sharded: local flag words raised by every rank's publish kernel
+  // fused publish (eb_shard.pub_*): the pass itself all-gathers logl; flags then count published iterations
+  int rank;
+  const double* pub_src; double* pub_dst[EB_MAX_RANKS]; unsigned long long* pub_flags[EB_MAX_RANKS];
+  unsigned long long* pub_elect;
   int philox, permute, cpb;                       // cpb = chains per block
   double* scratch_coords; double* scratch_logp; uint8_t* scratch_inds;   // staging of moved rows (RR == 0 path)
   const int32_t* next_pos; const double* u_at;  // replay pair map [T][W]
@@ -46,6 +50,12 @@ struct SwapArgs {
 __host__ __device__ inline int publish_grid(size_t ndoubles) {
   size_t g = (ndoubles / 2 + 255) / 256;
   return g < 1 ? 1 : g > 148 ? 148 : (int)g;
+}
+
+// CTAs of a swap pass that take part in the fused publish of `ndoubles` of logl (grid of `nreal` chain CTAs)
+__host__ __device__ inline int publish_ctas(size_t ndoubles, int nreal) {
+  const int g = publish_grid(ndoubles) > 128 ? 128 : publish_grid(ndoubles);
+  return g < nreal ? g : nreal;
 }
 
 struct SwapLayout {  // byte offsets into dynamic shared memory
@@ -185,7 +195,7 @@ constexpr int SWAP_THREADS = 256;
 // RR > 0: rows of up to RR doubles move through registers (needs T <= RPL*CL and no leaf flags); RR == 0: through the
 // global staging buffers.
 template <bool PHILOX, bool SHARDED, int CL, int RR, int RPL>
-__global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const SwapArgs p) {
+__global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_constant__ SwapArgs p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const Common& c = p.c;
   const int T = p.T, W = c.W, LD = c.LD, L = c.Lb, cpb = p.cpb;
@@ -249,17 +259,55 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const SwapArgs p)
   }
   pdl_wait();                 // the move kernel has completed; its writes are visible
   pdl_launch_dependents();    // the next move kernel may begin its draws
+  if (SHARDED && p.pub_src) {
+    // Fused publish: the first `npub` CTAs all-gather this rank's logl rows (final now: the move kernel completed) into
+    // logl_all of EVERY rank with coalesced 16-byte peer stores.  Per CTA: block barrier, one system-scope release fence
+    // by thread 0 (cumulative over the block's stores), +1 on the local election word; the CTA that completes the count
+    // stores iter+1 into this rank's flag word on every rank.  The publishing CTAs are the lowest block indices, which
+    // are dispatched first, so they never wait behind spinning CTAs of their own grid; the spin below is bounded anyway.
+    const int npub = publish_ctas((size_t)(p.t_hi - p.t_lo) * W, nreal);
+    if ((int)blockIdx.x < npub) {
+      const size_t n = (size_t)(p.t_hi - p.t_lo) * W, off = (size_t)p.t_lo * W;
+      const size_t stride = (size_t)npub * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + tid;
+      if ((off & 1) == 0) {
+        const double2* src = reinterpret_cast<const double2*>(p.pub_src);
+        for (size_t i = i0; i < (n >> 1); i += stride) {
+          const double2 v = src[i];
+          for (int gr = 0; gr < p.world; ++gr) reinterpret_cast<double2*>(p.pub_dst[gr] + off)[i] = v;
+        }
+        if ((n & 1) && i0 == 0)
+          for (int gr = 0; gr < p.world; ++gr) p.pub_dst[gr][off + n - 1] = p.pub_src[n - 1];
+      } else {
+        for (size_t i = i0; i < n; i += stride) {
+          const double v = p.pub_src[i];
+          for (int gr = 0; gr < p.world; ++gr) p.pub_dst[gr][off + i] = v;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        const unsigned long long prev = atomicAdd(p.pub_elect, 1ull);
+        if (prev + 1ull == (it + 1ull) * (unsigned long long)npub) {
+          asm volatile("fence.acq_rel.sys;" ::: "memory");
+          for (int gr = 0; gr < p.world; ++gr)
+            *reinterpret_cast<volatile unsigned long long*>(p.pub_flags[gr] + p.rank) = it + 1ull;
+        }
+      }
+    }
+  }
+  EB_MARK(27);
   if (SHARDED && p.flags) {
-    // every rank's logl rows of THIS iteration must have landed in logl_in (eb_publish_logl): bounded spin on
-    // the local flag words, one thread per CTA
+    // every rank's logl rows of THIS iteration must have landed in logl_in: bounded spin on the local flag words, one
+    // thread per CTA
     __shared__ bool s_ok;
     if (tid == 0) {
       bool ok = *reinterpret_cast<volatile unsigned int*>(&ctrl->error) == 0u;
-      // flag word g counts the CTAs of rank g's publish kernels so far (k_shard.cu)
       const long long t_start = clock64();
       for (int gr = 0; ok && gr < p.world; ++gr) {
         const size_t rows = (size_t)(p.temp_begin[gr + 1] - p.temp_begin[gr]) * W;
-        const unsigned long long target = (it + 1ull) * (unsigned long long)publish_grid(rows);
+        // separate publish kernel: flag word g counts the CTAs of rank g's publish kernels so far (k_shard.cu);
+        // fused publish: it holds the number of iterations rank g has published
+        const unsigned long long target = p.pub_src ? it + 1ull : (it + 1ull) * (unsigned long long)publish_grid(rows);
         const volatile unsigned long long* f = p.flags + gr;
         while (*f < target)
           if (clock64() - t_start > SPIN_TIMEOUT_CYCLES) { ok = false; break; }
@@ -646,6 +694,17 @@ int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rn
     return fail(EB_ERR_INVALID, "destination state must hold this rank's temperatures [%d, %d)", args.t_lo, args.t_hi);
   args.T = T; args.logl_in = sh->logl_all; args.betas = sh->betas_all;
   args.flags = (const unsigned long long*)sh->flags;
+  args.rank = sh->rank;
+  if (sh->pub_src) {
+    if (!sh->flags || !sh->pub_elect) return fail(EB_ERR_INVALID, "fused publish needs flags and pub_elect");
+    for (int g = 0; g < sh->world; ++g) {
+      if (!sh->pub_logl_all[g] || !sh->pub_flags[g]) return fail(EB_ERR_INVALID, "publish pointers of rank %d are NULL", g);
+      args.pub_dst[g] = sh->pub_logl_all[g];
+      args.pub_flags[g] = (unsigned long long*)sh->pub_flags[g];
+    }
+    args.pub_src = sh->pub_src;
+    args.pub_elect = (unsigned long long*)sh->pub_elect;
+  }
   if (T < 2) return eb_advance_iter(ctrl, stream);
   return launch_swap<true>(args, (cudaStream_t)stream);
 }

@@ -80,7 +80,9 @@ class ArenaLayout(object):
         self.logp = [take(n * 8) for _ in range(2)]
         self.logl_all = [take(T * self.W * 8) for _ in range(2)]
         self.betas_all = take(T * 8)
-        self.flags = take(16 * 8)
+        # 64 words: [0,16) CTA-count flags of the separate publish kernel, [16,32) iteration flags of the fused
+        # publish, [32] the local election word of the fused publish
+        self.flags = take(64 * 8)
         self.total = o
 
 
@@ -126,13 +128,13 @@ class ShardedRun(object):
     """One rank of a temperature-sharded run: the shared arena, the peer mappings and the two
     (current, alternate) DeviceStates."""
 
-    def __init__(self, ctx, ntemps, nwalkers, nleaves=1, group=None, comm="p2p"):
+    def __init__(self, ctx, ntemps, nwalkers, nleaves=1, group=None, comm="fused"):
         import torch
         import torch.distributed as dist
         from . import _lib
         from .device import DeviceState
-        if comm not in ("p2p", "nccl"):
-            raise ValueError("comm must be 'p2p' or 'nccl'")
+        if comm not in ("fused", "p2p", "nccl"):
+            raise ValueError("comm must be 'fused', 'p2p' or 'nccl'")
         if ctx.rng != "philox":
             raise ValueError("temperature-sharded runs use the philox streams (replay mode is single-GPU)")
         self.ctx, self.group, self.comm = ctx, group, comm
@@ -167,7 +169,7 @@ class ShardedRun(object):
         dev = ctx.device
         Tg = self.t_hi - self.t_lo
         self.betas_all = _tensor_at(self.base + lay.betas_all, (self.T,), "<f8", dev)
-        self.flags = _tensor_at(self.base + lay.flags, (16,), "<i8", dev)
+        self.flags = _tensor_at(self.base + lay.flags, (64,), "<i8", dev)
         self.logl_all = [_tensor_at(self.base + lay.logl_all[p], (self.T, self.W), "<f8", dev) for p in range(2)]
         self.states = []
         for p in range(2):
@@ -197,6 +199,13 @@ class ShardedRun(object):
             sh.logl_all = self.base + lay.logl_all[p]
             sh.betas_all = self.base + lay.betas_all
             sh.flags = (self.base + lay.flags) if comm == "p2p" else None
+            if comm == "fused":  # the swap kernel publishes itself (eb_shard.pub_*): iteration flags + election word
+                sh.flags = self.base + lay.flags + 16 * 8
+                sh.pub_src = self.base + lay.logl[p]
+                sh.pub_elect = self.base + lay.flags + 32 * 8
+                for g in range(self.world):
+                    sh.pub_logl_all[g] = self.bases[g] + self.layouts[g].logl_all[p]
+                    sh.pub_flags[g] = self.bases[g] + self.layouts[g].flags + 16 * 8
             pb.logl_local = self.base + lay.logl[p]
             self._shard.append(sh)
             self._pub.append(pb)
@@ -249,7 +258,7 @@ class ShardedRun(object):
             _lib.check(self.lib.eb_publish_logl(C.byref(self._pub[p]), C.c_void_p(ctx.ctrl.data_ptr()), ctx.stream()),
                        "eb_publish_logl")
             ctx.launches += 1
-        else:
+        elif self.comm == "nccl":
             dist.all_gather_into_tensor(self.logl_all[p], self.states[p].logl, group=self.group)
         r = _lib.eb_swap_rng()
         r.mode, r.permute, r.seed, r.iter_dev = _lib.EB_RNG_PHILOX, int(bool(permute)), ctx.seed, ctx.iter_ptr
@@ -322,7 +331,7 @@ def __getattr__(name):
 # ------------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
 # ------------------------------------------------------------------------------------------------------
-def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm="p2p"):
+def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm="fused"):
     """Weak-scaling step of bench.py: the walker count grows with the number of GPUs (wl["W"]), the ladder is
     sharded by temperature.  Returns the JSON dict on rank 0 (None elsewhere)."""
     import time
@@ -359,7 +368,7 @@ def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm
     # one iteration = move + publish + swap; the buffers flip every iteration, so a graph is captured per
     # (move kind, parity) and replayed according to the schedule
     graphs = {}
-    use_graph = comm == "p2p"
+    use_graph = comm != "nccl"
     with torch.cuda.stream(stream):
         for mv in moves:  # warm-up outside capture, an even number of iterations (parity returns to 0)
             for _ in range(2):

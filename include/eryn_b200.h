@@ -32,7 +32,7 @@ extern "C" {
 #define EB_API
 #endif
 
-#define EB_ABI_VERSION 3
+#define EB_ABI_VERSION 4
 #define EB_MAX_TEMPS 128
 #define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
 #define EB_MAX_RANKS 16 /* GPUs of one temperature-sharded run */
@@ -238,6 +238,17 @@ typedef struct {
   double* betas_all;                       /* [T] local copy of the full ladder; adapted in place */
   const uint64_t* flags;                   /* [EB_MAX_RANKS] local flag words (NULL: caller ordered the ranks itself,
                                               e.g. with an NCCL all-gather of logl) */
+  /* Fused publish (ABI v4; pub_src NULL = the rows were published by eb_publish_logl or by NCCL).  With pub_src set the
+   * swap kernel itself performs the all-gather right after its grid-dependency wait on the move kernel: its first CTAs
+   * copy this rank's logl rows into pub_logl_all[g] of every rank (coalesced 16-byte NVLink peer stores), each issues one
+   * system-scope release fence and bumps the LOCAL election word; the last of them stores iter+1 into word `rank` of
+   * pub_flags[g] on every rank.  `flags` then counts published ITERATIONS (word g >= iter+1), not publishing CTAs, and
+   * must be a different word array from the one eb_publish_logl raises.  One kernel per swap pass, no separate publish
+   * launch, and the pass stays a programmatic dependent of the move kernel (its draws overlap the move). */
+  const double* pub_src;                   /* [T_rank][W] this rank's current logl rows */
+  double* pub_logl_all[EB_MAX_RANKS];      /* peer-mapped logl_all (this parity) of every rank; entry `rank` local */
+  uint64_t* pub_flags[EB_MAX_RANKS];       /* peer-mapped iteration-flag arrays of every rank */
+  uint64_t* pub_elect;                     /* local election word, zero when ctrl->iter is 0 */
 } eb_shard;
 EB_API int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rng* rng,
                        const eb_adapt* adapt, eb_ctrl* ctrl, void* stream);

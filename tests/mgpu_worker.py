@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
-    ap.add_argument("--comm", default="p2p")
+    ap.add_argument("--comm", default="fused")
     ap.add_argument("--ntemps", type=int, default=4)
     ap.add_argument("--nwalkers", type=int, default=256)
     ap.add_argument("--ndim", type=int, default=8)

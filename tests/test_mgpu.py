@@ -50,8 +50,9 @@ def _oracle(T, W, d, nit, seed, mix):
     return smp, st, acc
 
 
-@pytest.mark.parametrize("comm,T,W,mix", [("p2p", 4, 256, 0), ("nccl", 4, 256, 0), ("p2p", 5, 99, 1), ("p2p", 16, 4096, 0), ("p2p", 72, 64, 0),
-                                                ("p2p", 128, 48, 0)])
+@pytest.mark.parametrize("comm,T,W,mix", [("fused", 4, 256, 0), ("p2p", 4, 256, 0), ("nccl", 4, 256, 0), ("fused", 5, 99, 1),
+                                                ("fused", 16, 4096, 0), ("p2p", 16, 4096, 0), ("fused", 72, 64, 0),
+                                                ("fused", 128, 48, 0), ("fused", 32, 16384, 0)])
 def test_sharded_run_matches_unsharded_oracle(tmp_path, comm, T, W, mix):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")

@@ -1,10 +1,14 @@
-"""Per-stage device time of the temperature-sharded iteration (run under torch.distributed.run, one rank per GPU).
+"""Where the time of a temperature-sharded iteration goes (run under torch.distributed.run, one rank per GPU).
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/shard_breakdown.py
 
-Stages are bracketed by CUDA events on every rank (no graph): move kernels, publish kernel, sharded swap kernel.
-The swap stage contains the in-kernel wait for the peers' flags, so rank skew shows up there."""
-import ctypes as C
+For every comm mode the iteration is captured as a CUDA graph per buffer parity (as bench.py does) and replayed back to
+back, so the ranks pace each other on the device; the per-iteration time is the CUDA-event time of the whole run / n.
+With the profiling build (ERYN_B200_LIB=tools/_build/liberyn_b200_prof.so) the in-kernel phase marks of the LAST
+iteration are printed as a timeline in ns (globaltimer of that GPU) relative to the start of the second stretch launch:
+  K1b start/end (CTA 0) | swap: start, keys, [wait for K1b], publish issued, flags seen, logl gathered, cascade done,
+  counts published, rows moved (CTA 0), adapt CTA done, last CTA rows moved."""
+import ctypes
 import os
 import sys
 
@@ -21,7 +25,6 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     world, rank = dist.get_world_size(), dist.get_rank()
-    from eryn_b200 import _lib
     from eryn_b200 import dist as ed
     from eryn_b200.device import DeviceContext
     from eryn_b200.likelihood import GaussianLikelihood
@@ -31,58 +34,55 @@ def main():
     A = np.random.RandomState(99).randn(d, d)
     P = np.linalg.inv(A @ A.T / d + np.eye(d))
     pri = ProbDistContainer({i: uniform_dist(-10.0, 10.0) for i in range(d)})
-    for comm in ("p2p", "nccl"):
+    prof = bool(os.environ.get("ERYN_B200_LIB"))
+    modes = os.environ.get("EB_BREAKDOWN_MODES", "fused,p2p").split(",")
+    for comm in modes:
         ctx = DeviceContext(pri, GaussianLikelihood(np.zeros(d), P), rng="philox", seed=1)
         run = ed.ShardedRun(ctx, T, W, comm=comm)
         tc = ed.ShardedTemperatureControl(run, d, W)
         mv = StretchMove(a=2.0)
         mv.temperature_control = tc
         mv.bind(ctx)
-        cnt = mv._count_buffer(ctx, run.t_hi - run.t_lo, W)
+        mv.accepted = np.zeros((run.t_hi - run.t_lo, W))
         run.load(np.random.RandomState(1).uniform(-3, 3, size=(T, W, 1, d)), tc._betas_host)
-        n = 200
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n)]
-        ad = dict(adaptive=True, stop_adaptation=-1, adaptation_lag=10000, adaptation_time=100)
-        for it in range(20):
-            ctx.stretch_step(run.current, 2.0, accepted_count=cnt)
-            run.swap(adapt=ad)
-        torch.cuda.synchronize()
-        dist.barrier()
-        for it in range(n):
-            ev[it][0].record()
-            ctx.stretch_step(run.current, 2.0, accepted_count=cnt)
-            ev[it][1].record()
-            p = run.parity
-            if comm == "p2p":
-                _lib.check(run.lib.eb_publish_logl(C.byref(run._pub[p]), C.c_void_p(ctx.ctrl.data_ptr()), ctx.stream()), "pub")
-            else:
-                dist.all_gather_into_tensor(run.logl_all[p], run.states[p].logl)
-            ev[it][2].record()
-            # swap without the publish: call the second half of run.swap by hand
-            r = _lib.eb_swap_rng()
-            r.mode, r.permute, r.seed, r.iter_dev = _lib.EB_RNG_PHILOX, 1, ctx.seed, ctx.iter_ptr
-            a = _lib.eb_adapt(1, -1, 10000.0, 100.0)
-            dst = run.states[1 - p].c_struct()
-            _lib.check(run.lib.eb_pt_swap_sharded(C.byref(run._shard[p]), C.byref(dst), C.byref(r), C.byref(a),
-                                                  C.c_void_p(ctx.ctrl.data_ptr()), ctx.stream()), "swap")
-            run.parity = 1 - p
-            ev[it][3].record()
-        torch.cuda.synchronize()
+        stream = torch.cuda.Stream()
+        graphs = []
+        with torch.cuda.stream(stream):
+            for _ in range(4):
+                mv.propose(None, run.current)
+            torch.cuda.synchronize()
+            dist.barrier()
+            for par in range(2):
+                run.parity = par
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    mv.propose(None, run.current)
+                graphs.append(g)
+            run.parity = 0
+            torch.cuda.synchronize()
+            dist.barrier()
+            n = 400
+            for rep in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for i in range(n):
+                    graphs[i & 1].replay()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                dist.barrier()
+            us = e0.elapsed_time(e1) * 1e3 / n
         run.check()
-        seg = np.array([[e[i].elapsed_time(e[i + 1]) * 1e3 for i in range(3)] for e in ev])
-        tot = np.array([ev[i][0].elapsed_time(ev[i + 1][0]) * 1e3 for i in range(n - 1)])
-        print(f"[{comm}] rank {rank}: move {np.median(seg[:, 0]):.1f} us, publish/all-gather {np.median(seg[:, 1]):.1f} us, "
-              f"sharded swap (incl. wait for peers) {np.median(seg[:, 2]):.1f} us; iteration-to-iteration {np.median(tot):.1f} us "
-              f"(host-paced, no graph)", flush=True)
-        if os.environ.get("ERYN_B200_LIB"):
-            import ctypes
-            mn = (ctypes.c_uint64 * 64)()
-            mx = (ctypes.c_uint64 * 64)()
-            if run.lib.eb_debug_marks_swap_global(mn, mx, 0) == 0:
-                base = mn[16]
-                print(f"[{comm}] rank {rank} last swap kernel, CTA 0, ns since its start: " +
-                      " ".join(f"m{i}={mn[i] - base}" for i in (17, 26, 18, 19, 20, 24, 25, 21)) +
-                      f" adapt-CTA-end={mx[23] - base}", flush=True)
+        print(f"[{comm}] rank {rank}: {us:.1f} us per iteration (graph replays back to back, T={T}, W={W})", flush=True)
+        if prof:
+            mn, mx = (ctypes.c_uint64 * 64)(), (ctypes.c_uint64 * 64)()
+            sn, sx = (ctypes.c_uint64 * 64)(), (ctypes.c_uint64 * 64)()
+            if run.lib.eb_debug_marks_swap_global(mn, mx, 0) == 0 and run.lib.eb_debug_marks_stretch_global(sn, sx, 0) == 0:
+                base = sn[0]
+                f = lambda v: int(v) - int(base)
+                print(f"[{comm}] rank {rank} timeline ns: K1b start 0 end {f(sn[7])} lastCTA-end {f(sx[7])} | swap start {f(mn[16])} "
+                      f"keys {f(mn[17])} publish-issued {f(mn[27])} flags-seen {f(mn[26])} gathered {f(mn[18])} cascade {f(mn[19])} "
+                      f"counts {f(mn[20])} rows {f(mn[21])} | adaptCTA start {f(mx[16])} flags-seen {f(mx[26])} done {f(mx[23])}",
+                      flush=True)
         dist.barrier()
         run.close()
     dist.destroy_process_group()
