@@ -33,10 +33,9 @@ struct SwapArgs {
   int temp_begin[EB_MAX_RANKS + 1];
   const double* coords_src[EB_MAX_RANKS]; const double* logp_src[EB_MAX_RANKS]; const uint8_t* inds_src[EB_MAX_RANKS];
   const unsigned long long* flags;                // sharded: local flag words raised by every rank's publish kernel
-  // fused publish (eb_shard.pub_*): the pass itself all-gathers logl; flags then count published iterations
-  int rank;
-  const double* pub_src; double* pub_dst[EB_MAX_RANKS]; unsigned long long* pub_flags[EB_MAX_RANKS];
-  unsigned long long* pub_elect;
+  // fused publish (eb_shard.pub_*): the pass itself all-gathers logl as self-validating 16-byte units
+  int rank, pdl;
+  const double* pub_src; uint4* pub_dst[EB_MAX_RANKS]; const uint4* ll_in;
   int philox, permute, cpb;                       // cpb = chains per block
   double* scratch_coords; double* scratch_logp; uint8_t* scratch_inds;   // staging of moved rows (RR == 0 path)
   const int32_t* next_pos; const double* u_at;  // replay pair map [T][W]
@@ -117,6 +116,36 @@ __device__ __forceinline__ void copy_row(double* __restrict__ dst, const double*
     for (int e = 0; e < LD; e += 2) *reinterpret_cast<double2*>(dst + e) = *reinterpret_cast<const double2*>(src + e);
   } else {
     for (int e = 0; e < LD; ++e) dst[e] = src[e];
+  }
+}
+
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ld_volatile_d2(const double* p, double& a, double& b) {
+  asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p) : "memory");
+}
+
+// Fused publish of a sharded pass (eb_shard.pub_*): the first CTAs of the grid write this rank's logl rows into the LL
+// buffer of EVERY rank (own rank included) as 16-byte units {lo32, tag, hi32, tag}, tag = iter+1, with coalesced 16-byte
+// NVLink peer stores.  A unit validates itself (each aligned 8-byte half is written atomically and carries the tag), so
+// there is no release fence, no flag and no wait for store acknowledgements: the latency of the all-gather is one
+// one-way NVLink trip.  Buffers alternate with the iteration parity, so a tag can only be confused with the one written
+// two iterations earlier, which differs.
+__device__ __forceinline__ void publish_ll(const SwapArgs& p, unsigned long long it, int nreal) {
+  const size_t n = (size_t)(p.t_hi - p.t_lo) * p.c.W, off = (size_t)p.t_lo * p.c.W;
+  const int npub = publish_ctas(n, nreal);
+  if ((int)blockIdx.x >= npub) return;
+  const uint32_t tag = (uint32_t)(it + 1ull);
+  const size_t stride = (size_t)npub * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = p.pub_src[i];
+    const uint4 u = make_uint4((uint32_t)__double2loint(v), tag, (uint32_t)__double2hiint(v), tag);
+    for (int gr = 0; gr < p.world; ++gr)
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p.pub_dst[gr] + off + i), "r"(u.x), "r"(u.y), "r"(u.z),
+                   "r"(u.w) : "memory");
   }
 }
 
@@ -227,6 +256,9 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
 
   EB_MARK(16);
+  // Ordinary launch (not a programmatic dependent): the move kernel has completed, so the rows go out first and the
+  // prologue below (positions, log u) runs while they cross NVLink.
+  if (SHARDED && p.pub_src && !p.pdl) publish_ll(p, it, nreal);
   for (int r = tid; r < T; r += blockDim.x) {
     s_cnt[r] = 0;
     if (PHILOX && p.permute) Feistel::make_keys(key, TAG_SWAP_KEY, (uint32_t)r, s_keys + FEISTEL_ROUNDS * r);
@@ -259,55 +291,19 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   }
   pdl_wait();                 // the move kernel has completed; its writes are visible
   pdl_launch_dependents();    // the next move kernel may begin its draws
-  if (SHARDED && p.pub_src) {
-    // Fused publish: the first `npub` CTAs all-gather this rank's logl rows (final now: the move kernel completed) into
-    // logl_all of EVERY rank with coalesced 16-byte peer stores.  Per CTA: block barrier, one system-scope release fence
-    // by thread 0 (cumulative over the block's stores), +1 on the local election word; the CTA that completes the count
-    // stores iter+1 into this rank's flag word on every rank.  The publishing CTAs are the lowest block indices, which
-    // are dispatched first, so they never wait behind spinning CTAs of their own grid; the spin below is bounded anyway.
-    const int npub = publish_ctas((size_t)(p.t_hi - p.t_lo) * W, nreal);
-    if ((int)blockIdx.x < npub) {
-      const size_t n = (size_t)(p.t_hi - p.t_lo) * W, off = (size_t)p.t_lo * W;
-      const size_t stride = (size_t)npub * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + tid;
-      if ((off & 1) == 0) {
-        const double2* src = reinterpret_cast<const double2*>(p.pub_src);
-        for (size_t i = i0; i < (n >> 1); i += stride) {
-          const double2 v = src[i];
-          for (int gr = 0; gr < p.world; ++gr) reinterpret_cast<double2*>(p.pub_dst[gr] + off)[i] = v;
-        }
-        if ((n & 1) && i0 == 0)
-          for (int gr = 0; gr < p.world; ++gr) p.pub_dst[gr][off + n - 1] = p.pub_src[n - 1];
-      } else {
-        for (size_t i = i0; i < n; i += stride) {
-          const double v = p.pub_src[i];
-          for (int gr = 0; gr < p.world; ++gr) p.pub_dst[gr][off + i] = v;
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("fence.acq_rel.sys;" ::: "memory");
-        const unsigned long long prev = atomicAdd(p.pub_elect, 1ull);
-        if (prev + 1ull == (it + 1ull) * (unsigned long long)npub) {
-          asm volatile("fence.acq_rel.sys;" ::: "memory");
-          for (int gr = 0; gr < p.world; ++gr)
-            *reinterpret_cast<volatile unsigned long long*>(p.pub_flags[gr] + p.rank) = it + 1ull;
-        }
-      }
-    }
-  }
+  if (SHARDED && p.pub_src && p.pdl) publish_ll(p, it, nreal);
   EB_MARK(27);
   if (SHARDED && p.flags) {
-    // every rank's logl rows of THIS iteration must have landed in logl_in: bounded spin on the local flag words, one
-    // thread per CTA
+    // separate publish kernel (eb_publish_logl): every rank's logl rows of THIS iteration must have landed in logl_in:
+    // bounded spin on the local flag words, one thread per CTA
     __shared__ bool s_ok;
     if (tid == 0) {
       bool ok = *reinterpret_cast<volatile unsigned int*>(&ctrl->error) == 0u;
       const long long t_start = clock64();
       for (int gr = 0; ok && gr < p.world; ++gr) {
         const size_t rows = (size_t)(p.temp_begin[gr + 1] - p.temp_begin[gr]) * W;
-        // separate publish kernel: flag word g counts the CTAs of rank g's publish kernels so far (k_shard.cu);
-        // fused publish: it holds the number of iterations rank g has published
-        const unsigned long long target = p.pub_src ? it + 1ull : (it + 1ull) * (unsigned long long)publish_grid(rows);
+        // flag word g counts the CTAs of rank g's publish kernels so far (k_shard.cu)
+        const unsigned long long target = (it + 1ull) * (unsigned long long)publish_grid(rows);
         const volatile unsigned long long* f = p.flags + gr;
         while (*f < target)
           if (clock64() - t_start > SPIN_TIMEOUT_CYCLES) { ok = false; break; }
@@ -338,9 +334,68 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     if (valid)
       for (int r = lane; r < T; r += CL) lu[r] = log((r >= 1) ? p.u_at[(size_t)r * W + pos[r]] : 0.5);
   }
-  if (valid)
+  if (SHARDED && p.ll_in) {
+    // fused publish: every logl arrives as a 16-byte unit {lo32, tag, hi32, tag} with tag = iter+1 (publish_ll); a lane
+    // polls the units of its rungs (at most four: T <= 128, CL = 32 beyond 16 rungs) until both tags match.  No fence and
+    // no flag: each 8-byte half is written atomically and validates itself.
+    if (valid) {
+      const uint32_t tag = (uint32_t)(it + 1ull);
+      bool pend[4];
+      uint4 v[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) pend[m] = lane + m * CL < T;
+      bool ok = *reinterpret_cast<volatile unsigned int*>(&ctrl->error) == 0u;   // an earlier timeout: do not spin again
+      const long long t_start = clock64();
+      for (;;) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (pend[m]) {
+            const int r = lane + m * CL;
+            v[m] = ld_volatile_u4(p.ll_in + (size_t)r * W + pos[r]);
+          }
+        bool any = false;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (pend[m]) {
+            if ((v[m].y == tag && v[m].w == tag) || !ok) {
+              ll[lane + m * CL] = __hiloint2double((int)v[m].z, (int)v[m].x);
+              pend[m] = false;
+            } else {
+              any = true;
+            }
+          }
+        if (!any) break;
+        if (clock64() - t_start > SPIN_TIMEOUT_CYCLES) {
+          atomicExch(&ctrl->error, EB_DEVERR_PEER_TIMEOUT);
+          ok = false;
+        }
+      }
+    }
+  } else if (valid) {
     for (int r = lane; r < T; r += CL) ll[r] = p.logl_in[(size_t)r * W + pos[r]];
+  }
   __syncthreads();
+  // Sharded, short rows: the two rows most likely to arrive from a neighbour rank are requested now, so that their NVLink
+  // round trip (~5 us) runs under the cascade and the count publication: the walker just below this rank's rungs (taken
+  // if the swap at rung t_lo is accepted) and the walker just above them (taken if the swap at rung t_hi is accepted and
+  // the one above it is not).  Every unit of this chain was valid above, so every rank has completed its move kernel.
+  constexpr int PF = 8;
+  double pf_row[PF], pf_lp = 0.0;
+  int pf_src = -1;
+  if (SHARDED && valid && LD <= PF && (LD & 1) == 0 && !c.inds) {
+    const int nown = p.t_hi - p.t_lo;
+    if (lane == 0 && p.t_lo >= 1) pf_src = p.t_lo - 1;
+    else if (lane == (nown - 1) % CL && p.t_hi < T) pf_src = p.t_hi;
+    if (pf_src >= 0) {
+      int gsrc = 0;
+      while (gsrc + 1 < p.world && pf_src >= p.temp_begin[gsrc + 1]) ++gsrc;
+      const size_t sslot = (size_t)(pf_src - p.temp_begin[gsrc]) * W + pos[pf_src];
+#pragma unroll
+      for (int e = 0; e < PF; e += 2)
+        if (e < LD) ld_volatile_d2(p.coords_src[gsrc] + sslot * LD + e, pf_row[e], pf_row[e + 1]);
+      pf_lp = *reinterpret_cast<const volatile double*>(p.logp_src[gsrc] + sslot);
+    }
+  }
 
   EB_MARK(18);
   // ---- the cascade, hot -> cold (tempering.py:515-559 restricted to this chain); every lane of the chain runs it
@@ -519,8 +574,15 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
       while (gsrc + 1 < p.world && s >= p.temp_begin[gsrc + 1]) ++gsrc;
       const size_t sslot = (size_t)(s - p.temp_begin[gsrc]) * W + pos[s];
       const size_t dslot = (size_t)(r - p.t_lo) * W + pos[r];
-      copy_row(c.coords + dslot * LD, p.coords_src[gsrc] + sslot * LD, LD);
-      c.logp[dslot] = p.logp_src[gsrc][sslot];
+      if (s == pf_src) {                 // the speculative request above was the right one
+#pragma unroll
+        for (int e = 0; e < PF; e += 2)
+          if (e < LD) *reinterpret_cast<double2*>(c.coords + dslot * LD + e) = make_double2(pf_row[e], pf_row[e + 1]);
+        c.logp[dslot] = pf_lp;
+      } else {
+        copy_row(c.coords + dslot * LD, p.coords_src[gsrc] + sslot * LD, LD);
+        c.logp[dslot] = p.logp_src[gsrc][sslot];
+      }
       c.logl[dslot] = ll[s];
       if (c.inds) copy_bytes(c.inds + dslot * L, p.inds_src[gsrc] + sslot * L, L);
     }
@@ -582,6 +644,7 @@ static int launch_swap_kernel(SwapArgs& args, cudaStream_t s) {
   // programmatic dependent of the move kernel: positions and log(u) are computed while the move still runs
   cudaLaunchAttribute attr[1];
   static const int pdl_mask = getenv("EB_PDL_MASK") ? atoi(getenv("EB_PDL_MASK")) : 5;
+  args.pdl = (pdl_mask & 2) ? 1 : 0;
   if (pdl_mask & 2) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -696,14 +759,14 @@ int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rn
   args.flags = (const unsigned long long*)sh->flags;
   args.rank = sh->rank;
   if (sh->pub_src) {
-    if (!sh->flags || !sh->pub_elect) return fail(EB_ERR_INVALID, "fused publish needs flags and pub_elect");
+    if (sh->flags) return fail(EB_ERR_INVALID, "fused publish validates the data itself: pass flags = NULL");
+    if (!sh->ll_in) return fail(EB_ERR_INVALID, "fused publish needs ll_in");
     for (int g = 0; g < sh->world; ++g) {
-      if (!sh->pub_logl_all[g] || !sh->pub_flags[g]) return fail(EB_ERR_INVALID, "publish pointers of rank %d are NULL", g);
-      args.pub_dst[g] = sh->pub_logl_all[g];
-      args.pub_flags[g] = (unsigned long long*)sh->pub_flags[g];
+      if (!sh->pub_ll[g]) return fail(EB_ERR_INVALID, "LL buffer of rank %d is NULL", g);
+      args.pub_dst[g] = (uint4*)sh->pub_ll[g];
     }
     args.pub_src = sh->pub_src;
-    args.pub_elect = (unsigned long long*)sh->pub_elect;
+    args.ll_in = (const uint4*)sh->ll_in;
   }
   if (T < 2) return eb_advance_iter(ctrl, stream);
   return launch_swap<true>(args, (cudaStream_t)stream);

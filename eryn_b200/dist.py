@@ -80,9 +80,9 @@ class ArenaLayout(object):
         self.logp = [take(n * 8) for _ in range(2)]
         self.logl_all = [take(T * self.W * 8) for _ in range(2)]
         self.betas_all = take(T * 8)
-        # 64 words: [0,16) CTA-count flags of the separate publish kernel, [16,32) iteration flags of the fused
-        # publish, [32] the local election word of the fused publish
-        self.flags = take(64 * 8)
+        self.flags = take(16 * 8)
+        # fused publish: logl of every rank as self-validating 16-byte units (eb_shard.pub_ll / ll_in), per parity
+        self.logl_ll = [take(T * self.W * 16) for _ in range(2)]
         self.total = o
 
 
@@ -169,7 +169,7 @@ class ShardedRun(object):
         dev = ctx.device
         Tg = self.t_hi - self.t_lo
         self.betas_all = _tensor_at(self.base + lay.betas_all, (self.T,), "<f8", dev)
-        self.flags = _tensor_at(self.base + lay.flags, (64,), "<i8", dev)
+        self.flags = _tensor_at(self.base + lay.flags, (16,), "<i8", dev)
         self.logl_all = [_tensor_at(self.base + lay.logl_all[p], (self.T, self.W), "<f8", dev) for p in range(2)]
         self.states = []
         for p in range(2):
@@ -199,13 +199,12 @@ class ShardedRun(object):
             sh.logl_all = self.base + lay.logl_all[p]
             sh.betas_all = self.base + lay.betas_all
             sh.flags = (self.base + lay.flags) if comm == "p2p" else None
-            if comm == "fused":  # the swap kernel publishes itself (eb_shard.pub_*): iteration flags + election word
-                sh.flags = self.base + lay.flags + 16 * 8
+            if comm == "fused":  # the swap kernel publishes itself (eb_shard.pub_*): self-validating units, no flags
+                sh.flags = None
                 sh.pub_src = self.base + lay.logl[p]
-                sh.pub_elect = self.base + lay.flags + 32 * 8
+                sh.ll_in = self.base + lay.logl_ll[p]
                 for g in range(self.world):
-                    sh.pub_logl_all[g] = self.bases[g] + self.layouts[g].logl_all[p]
-                    sh.pub_flags[g] = self.bases[g] + self.layouts[g].flags + 16 * 8
+                    sh.pub_ll[g] = self.bases[g] + self.layouts[g].logl_ll[p]
             pb.logl_local = self.base + lay.logl[p]
             self._shard.append(sh)
             self._pub.append(pb)

@@ -239,16 +239,15 @@ typedef struct {
   const uint64_t* flags;                   /* [EB_MAX_RANKS] local flag words (NULL: caller ordered the ranks itself,
                                               e.g. with an NCCL all-gather of logl) */
   /* Fused publish (ABI v4; pub_src NULL = the rows were published by eb_publish_logl or by NCCL).  With pub_src set the
-   * swap kernel itself performs the all-gather right after its grid-dependency wait on the move kernel: its first CTAs
-   * copy this rank's logl rows into pub_logl_all[g] of every rank (coalesced 16-byte NVLink peer stores), each issues one
-   * system-scope release fence and bumps the LOCAL election word; the last of them stores iter+1 into word `rank` of
-   * pub_flags[g] on every rank.  `flags` then counts published ITERATIONS (word g >= iter+1), not publishing CTAs, and
-   * must be a different word array from the one eb_publish_logl raises.  One kernel per swap pass, no separate publish
-   * launch, and the pass stays a programmatic dependent of the move kernel (its draws overlap the move). */
+   * swap kernel itself performs the all-gather: its first CTAs write this rank's logl rows into the LL buffer of EVERY
+   * rank (own rank included) as self-validating 16-byte units {lo32, tag, hi32, tag}, tag = (uint32_t)(iter+1), with
+   * coalesced NVLink peer stores, and the cascade polls the units it needs in `ll_in` until both tags match.  Each
+   * aligned 8-byte half is written atomically and carries the tag, so the exchange needs no release fence, no flag word
+   * and no wait for store acknowledgements (one one-way NVLink trip instead of three); `flags` must be NULL.  The LL
+   * buffers alternate with the iteration parity like logl_all, and must be zero when ctrl->iter is 0. */
   const double* pub_src;                   /* [T_rank][W] this rank's current logl rows */
-  double* pub_logl_all[EB_MAX_RANKS];      /* peer-mapped logl_all (this parity) of every rank; entry `rank` local */
-  uint64_t* pub_flags[EB_MAX_RANKS];       /* peer-mapped iteration-flag arrays of every rank */
-  uint64_t* pub_elect;                     /* local election word, zero when ctrl->iter is 0 */
+  void* pub_ll[EB_MAX_RANKS];              /* peer-mapped LL buffers (this parity) of every rank: [T][W] 16-byte units */
+  const void* ll_in;                       /* local LL buffer (this parity) */
 } eb_shard;
 EB_API int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rng* rng,
                        const eb_adapt* adapt, eb_ctrl* ctrl, void* stream);
