@@ -82,7 +82,8 @@ class eb_shard(C.Structure):
                 ("temp_begin", C.c_int32 * (EB_MAX_RANKS + 1)),
                 ("coords_src", vp * EB_MAX_RANKS), ("logp_src", vp * EB_MAX_RANKS), ("inds_src", vp * EB_MAX_RANKS),
                 ("logl_all", vp), ("betas_all", vp), ("flags", vp),
-                ("pub_src", vp), ("pub_ll", vp * EB_MAX_RANKS), ("ll_in", vp)]
+                ("pub_src", vp), ("pub_ll", vp * EB_MAX_RANKS), ("ll_in", vp),
+                ("mail_peer", vp * EB_MAX_RANKS), ("mail_in", vp)]
 
 
 class eb_publish(C.Structure):

@@ -74,6 +74,13 @@ static __device__ unsigned long long eb_dbg_gmin[64], eb_dbg_gmax[64];   // glob
 #define EB_DBG_SKIP(bit) false
 #endif
 
+// volatile 64-bit global load as inline PTX: the compiler can neither cache it nor fold it with a parameter read
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const void* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 struct Common {
   double* coords; double* logl; double* logp; uint8_t* inds; double* betas;
   int T, W, L, D, LD;

@@ -199,7 +199,9 @@ __global__ void __launch_bounds__(MB_THREADS) mb_group_stretch_kernel(const __gr
   RngKey key;
   double u_z, u_acc;
   if (p.philox) {
-    const unsigned long long it = p.iter_dev ? *reinterpret_cast<const volatile unsigned long long*>(p.iter_dev) : p.iter;
+    unsigned long long it = p.iter;   // (not a ?: of the two: with a __grid_constant__ parameter block nvcc merges the
+  // arms into ONE global load whose address may then point into parameter space)
+  if (p.iter_dev) it = ld_volatile_u64(p.iter_dev);
     key = make_rng_key(p.seed_lo, p.seed_hi, it);
     const uint4 r = stream(key, TAG_GROUP, fw, 0u);
     u_z = u01_52(r.x, r.y);
@@ -264,7 +266,9 @@ __global__ void __launch_bounds__(MB_THREADS) mb_rj_kernel(const __grid_constant
   RngKey key;
   double u_acc = 0.5;
   if (p.philox) {
-    const unsigned long long it = p.iter_dev ? *reinterpret_cast<const volatile unsigned long long*>(p.iter_dev) : p.iter;
+    unsigned long long it = p.iter;   // (not a ?: of the two: with a __grid_constant__ parameter block nvcc merges the
+  // arms into ONE global load whose address may then point into parameter space)
+  if (p.iter_dev) it = ld_volatile_u64(p.iter_dev);
     key = make_rng_key(p.seed_lo, p.seed_hi, it);
     const uint4 r = stream(key, TAG_RJ, fw, 0u);
     u_acc = u01_52(r.z, r.w);

@@ -36,6 +36,8 @@ struct SwapArgs {
   // fused publish (eb_shard.pub_*): the pass itself all-gathers logl as self-validating 16-byte units
   int rank, pdl;
   const double* pub_src; uint4* pub_dst[EB_MAX_RANKS]; const uint4* ll_in;
+  // row mail (eb_shard.mail_*): rows that change rank are PUSHED by the rank that owns the source rung
+  uint4* mail_dst[EB_MAX_RANKS]; const uint4* mail_in;
   int philox, permute, cpb;                       // cpb = chains per block
   double* scratch_coords; double* scratch_logp; uint8_t* scratch_inds;   // staging of moved rows (RR == 0 path)
   const int32_t* next_pos; const double* u_at;  // replay pair map [T][W]
@@ -124,6 +126,9 @@ __device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_volatile_u4(uint4* p, const uint4 u) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
 __device__ __forceinline__ void ld_volatile_d2(const double* p, double& a, double& b) {
   asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p) : "memory");
 }
@@ -143,9 +148,7 @@ __device__ __forceinline__ void publish_ll(const SwapArgs& p, unsigned long long
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const double v = p.pub_src[i];
     const uint4 u = make_uint4((uint32_t)__double2loint(v), tag, (uint32_t)__double2hiint(v), tag);
-    for (int gr = 0; gr < p.world; ++gr)
-      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p.pub_dst[gr] + off + i), "r"(u.x), "r"(u.y), "r"(u.z),
-                   "r"(u.w) : "memory");
+    for (int gr = 0; gr < p.world; ++gr) st_volatile_u4(p.pub_dst[gr] + off + i, u);
   }
 }
 
@@ -247,7 +250,10 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   if (adapt_cta && tid == 0) time_now = *reinterpret_cast<const volatile long long*>(&ctrl->time);
   // ---- prologue: nothing here reads the walker state, so under programmatic dependent launch it overlaps the move
   //      kernel that precedes this pass.  ctrl->iter is written only by this kernel's own tail.
-  const unsigned long long it = p.iter_dev ? *reinterpret_cast<const volatile unsigned long long*>(p.iter_dev) : p.iter;
+  if (p.pdl == 2) pdl_wait();
+  unsigned long long it = p.iter;   // (not a ?: of the two: with a __grid_constant__ parameter block nvcc merges the
+  // arms into ONE global load whose address may then point into parameter space)
+  if (p.iter_dev) it = ld_volatile_u64(p.iter_dev);
   if (blockIdx.x == 0 && tid == 0) {
     // the next move kernel may start its draws while this pass still runs: it keys them by iter_next
     *reinterpret_cast<volatile unsigned long long*>(&ctrl->iter_next) = it + 1ull;
@@ -256,9 +262,9 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
 
   EB_MARK(16);
-  // Ordinary launch (not a programmatic dependent): the move kernel has completed, so the rows go out first and the
+  // Ordinary launch (or wait-first dependent): the move kernel has completed, so the rows go out first and the
   // prologue below (positions, log u) runs while they cross NVLink.
-  if (SHARDED && p.pub_src && !p.pdl) publish_ll(p, it, nreal);
+  if (SHARDED && p.pub_src && p.pdl != 1) publish_ll(p, it, nreal);
   for (int r = tid; r < T; r += blockDim.x) {
     s_cnt[r] = 0;
     if (PHILOX && p.permute) Feistel::make_keys(key, TAG_SWAP_KEY, (uint32_t)r, s_keys + FEISTEL_ROUNDS * r);
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   }
   pdl_wait();                 // the move kernel has completed; its writes are visible
   pdl_launch_dependents();    // the next move kernel may begin its draws
-  if (SHARDED && p.pub_src && p.pdl) publish_ll(p, it, nreal);
+  if (SHARDED && p.pub_src && p.pdl == 1) publish_ll(p, it, nreal);
   EB_MARK(27);
   if (SHARDED && p.flags) {
     // separate publish kernel (eb_publish_logl): every rank's logl rows of THIS iteration must have landed in logl_in:
@@ -375,58 +381,94 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     for (int r = lane; r < T; r += CL) ll[r] = p.logl_in[(size_t)r * W + pos[r]];
   }
   __syncthreads();
-  // Sharded, short rows: the two rows most likely to arrive from a neighbour rank are requested now, so that their NVLink
-  // round trip (~5 us) runs under the cascade and the count publication: the walker just below this rank's rungs (taken
-  // if the swap at rung t_lo is accepted) and the walker just above them (taken if the swap at rung t_hi is accepted and
-  // the one above it is not).  Every unit of this chain was valid above, so every rank has completed its move kernel.
-  constexpr int PF = 8;
-  double pf_row[PF], pf_lp = 0.0;
-  int pf_src = -1;
-  if (SHARDED && valid && LD <= PF && (LD & 1) == 0 && !c.inds) {
-    const int nown = p.t_hi - p.t_lo;
-    if (lane == 0 && p.t_lo >= 1) pf_src = p.t_lo - 1;
-    else if (lane == (nown - 1) % CL && p.t_hi < T) pf_src = p.t_hi;
-    if (pf_src >= 0) {
-      int gsrc = 0;
-      while (gsrc + 1 < p.world && pf_src >= p.temp_begin[gsrc + 1]) ++gsrc;
-      const size_t sslot = (size_t)(pf_src - p.temp_begin[gsrc]) * W + pos[pf_src];
-#pragma unroll
-      for (int e = 0; e < PF; e += 2)
-        if (e < LD) ld_volatile_d2(p.coords_src[gsrc] + sslot * LD + e, pf_row[e], pf_row[e + 1]);
-      pf_lp = *reinterpret_cast<const volatile double*>(p.logp_src[gsrc] + sslot);
-    }
-  }
-
   EB_MARK(18);
   // ---- the cascade, hot -> cold (tempering.py:515-559 restricted to this chain); every lane of the chain runs it
-  //      (same operands, broadcast reads), so every lane knows all accept bits
+  //      (same operands, broadcast reads), so every lane knows all accept bits.
+  // The carried log-likelihood is always an ORIGINAL value: after a rejected swap at rung i+1 the walker of rung i is
+  // carried on, and its test at rung i, dts[i] * (ll[i] - ll[i-1]) > lu[i], depends on nothing the cascade decides.
+  // Those "fresh" tests are evaluated for all rungs at once, one or a few rungs per lane (same expression, same
+  // rounding), and exchanged by ballot; the sequential walk then needs the dependent DADD -> DMUL -> DSETP chain only
+  // while a walker is carried further than one rung (a run of accepted swaps), and a bit test otherwise.
   unsigned long long sel_lo = 0ull, sel_hi = 0ull;
-  if (valid && !EB_DBG_SKIP(8)) {
-    double carry = ll[T - 1];
-    if (RR > 0) {
-      // short ladders: compile-time trip count, so the operand loads of all rungs are hoisted above the dependent chain
+  {
+    unsigned long long fr_lo = 0ull, fr_hi = 0ull;
+    constexpr int NB = CL == 32 ? 4 : 1;              // T <= 128 with 32 lanes, T <= CL otherwise
+    const int sh = (tid & 31) - lane;                 // first lane of this chain's group within the warp
 #pragma unroll
-      for (int i = CL * RPL - 1; i >= 1; --i) {
-        if (i < T) {
-          const double lower = ll[i - 1];
-          const bool sel = s_dts[i] * (carry - lower) > lu[i];                 // :538, :541  (s_dts[i] = betas[i-1]-betas[i])
+    for (int m = 0; m < NB; ++m) {
+      const int r = lane + m * CL;
+      bool f = false;
+      if (valid && r >= 1 && r < T) f = s_dts[r] * (ll[r] - ll[r - 1]) > lu[r];     // :538, :541  (s_dts[i] = betas[i-1]-betas[i])
+      const unsigned v = __ballot_sync(0xffffffffu, f);
+      if (CL == 32) {                                 // one chain per warp: ballot m holds rungs 32m .. 32m+31
+        if (m == 0) fr_lo |= (unsigned long long)v;
+        if (m == 1) fr_lo |= (unsigned long long)v << 32;
+        if (m == 2) fr_hi |= (unsigned long long)v;
+        if (m == 3) fr_hi |= (unsigned long long)v << 32;
+      } else {                                        // several chains per warp: this chain's CL bits
+        fr_lo = (unsigned long long)((v >> sh) & ((1u << (CL & 31)) - 1u));
+      }
+    }
+    if (valid && !EB_DBG_SKIP(8)) {
+      bool fresh = true;
+      double carry = 0.0;
+      for (int i = T - 1; i >= 1; --i) {
+        if (fresh) {
+          if (sel_bit(fr_lo, fr_hi, i)) {
+            if (i < 64) sel_lo |= 1ull << i;
+            else sel_hi |= 1ull << (i - 64);
+            carry = ll[i];             // carried past rung i-1: from here on the test depends on the cascade
+            fresh = false;
+          }                            // else: the carried walker settles on rung i, rung i-1's walker is carried on
+        } else {
+          const bool sel = s_dts[i] * (carry - ll[i - 1]) > lu[i];
           if (sel) {
             if (i < 64) sel_lo |= 1ull << i;
             else sel_hi |= 1ull << (i - 64);
           } else {
-            carry = lower;               // the carried walker settles on rung i, rung i-1's walker is carried on
+            fresh = true;
           }
         }
       }
-    } else {
-      for (int i = T - 1; i >= 1; --i) {
-        const double lower = ll[i - 1];
-        const bool sel = s_dts[i] * (carry - lower) > lu[i];
-        if (sel) {
-          if (i < 64) sel_lo |= 1ull << i;
-          else sel_hi |= 1ull << (i - 64);
-        } else {
-          carry = lower;
+    }
+  }
+
+  // ---- sharded: rows that change rank leave NOW, before the counts are published, as mail pushed by the rank that
+  //      owns the source rung (every rank has resolved the whole chain, so sender and receiver agree without talking):
+  //      a one-way NVLink trip that runs under the count publication and the local row copies, instead of the round
+  //      trip of a pull.  A mail is LD+1 self-validating units (row, then logp) in the receiver's mailbox, slot
+  //      [direction][chain]; per chain and rank at most one walker arrives from below (into rung t_lo, when the swap at
+  //      t_lo is accepted) and at most one from above (the carried walker, where it settles).  The lanes of the chain
+  //      share the units of a mail (coalesced loads and peer stores).
+  if (SHARDED && p.mail_in && valid) {
+    const int MU = LD + 1;
+    const uint32_t tag = (uint32_t)(it + 1ull);
+    // up: the walker of my top rung moves up to rung t_hi
+    if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {
+      const int sr = p.t_hi - 1;
+      int gd = p.rank;
+      while (gd + 1 < p.world && p.t_hi >= p.temp_begin[gd + 1]) ++gd;
+      const size_t sslot = (size_t)(sr - p.t_lo) * W + pos[sr];
+      uint4* box = p.mail_dst[gd] + ((size_t)0 * W + chain) * MU;
+      for (int e = lane; e < MU; e += CL) {
+        const double v = e < LD ? p.coords_src[p.rank][sslot * LD + e] : p.logp_src[p.rank][sslot];
+        st_volatile_u4(box + e, make_uint4((uint32_t)__double2loint(v), tag, (uint32_t)__double2hiint(v), tag));
+      }
+    }
+    // down: the walker carried across my lower boundary, if it started on one of my rungs
+    if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) {
+      int o = p.t_lo;
+      while (o + 1 < T && sel_bit(sel_lo, sel_hi, o + 1)) ++o;      // rung the carried walker started on
+      if (o < p.t_hi) {
+        int d = p.t_lo - 1;
+        while (d >= 1 && sel_bit(sel_lo, sel_hi, d)) --d;           // rung it settles on
+        int gd = 0;
+        while (gd + 1 < p.world && d >= p.temp_begin[gd + 1]) ++gd;
+        const size_t sslot = (size_t)(o - p.t_lo) * W + pos[o];
+        uint4* box = p.mail_dst[gd] + ((size_t)1 * W + chain) * MU;
+        for (int e = lane; e < MU; e += CL) {
+          const double v = e < LD ? p.coords_src[p.rank][sslot * LD + e] : p.logp_src[p.rank][sslot];
+          st_volatile_u4(box + e, make_uint4((uint32_t)__double2loint(v), tag, (uint32_t)__double2hiint(v), tag));
         }
       }
     }
@@ -568,23 +610,52 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     // from the CURRENT buffers of whichever rank holds the source rung (NVLink peer loads); lanes work on different
     // rungs, so the loads of all owned rungs of the chain are in flight together.  Source and destination buffers
     // are distinct: no staging.
+    const bool mail = p.mail_in != nullptr;
     for (int r = p.t_lo + lane; r < p.t_hi; r += CL) {
       const int s = swap_source(sel_lo, sel_hi, r, T);
       int gsrc = 0;
       while (gsrc + 1 < p.world && s >= p.temp_begin[gsrc + 1]) ++gsrc;
-      const size_t sslot = (size_t)(s - p.temp_begin[gsrc]) * W + pos[s];
       const size_t dslot = (size_t)(r - p.t_lo) * W + pos[r];
-      if (s == pf_src) {                 // the speculative request above was the right one
-#pragma unroll
-        for (int e = 0; e < PF; e += 2)
-          if (e < LD) *reinterpret_cast<double2*>(c.coords + dslot * LD + e) = make_double2(pf_row[e], pf_row[e + 1]);
-        c.logp[dslot] = pf_lp;
-      } else {
-        copy_row(c.coords + dslot * LD, p.coords_src[gsrc] + sslot * LD, LD);
-        c.logp[dslot] = p.logp_src[gsrc][sslot];
-      }
       c.logl[dslot] = ll[s];
+      if (mail && gsrc != p.rank) continue;             // arrives by mail (below)
+      const size_t sslot = (size_t)(s - p.temp_begin[gsrc]) * W + pos[s];
+      copy_row(c.coords + dslot * LD, p.coords_src[gsrc] + sslot * LD, LD);
+      c.logp[dslot] = p.logp_src[gsrc][sslot];
       if (c.inds) copy_bytes(c.inds + dslot * L, p.inds_src[gsrc] + sslot * L, L);
+    }
+    if (mail) {
+      // the mail of this chain, after the local copies were issued: [0] from below into rung t_lo, [1] from above into
+      // the rung where the carried walker settles (if that is one of mine); every lane polls its units and writes them
+      const int MU = LD + 1;
+      const uint32_t tag = (uint32_t)(it + 1ull);
+      int dest[2] = {-1, -1};
+      if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) dest[0] = p.t_lo;
+      if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {
+        int d = p.t_hi - 1;
+        while (d >= 1 && sel_bit(sel_lo, sel_hi, d)) --d;
+        if (d >= p.t_lo) dest[1] = d;
+      }
+      bool ok = *reinterpret_cast<volatile unsigned int*>(&ctrl->error) == 0u;
+      const long long t_start = clock64();
+#pragma unroll
+      for (int dir = 0; dir < 2; ++dir) {
+        if (dest[dir] < 0) continue;
+        const size_t dslot = (size_t)(dest[dir] - p.t_lo) * W + pos[dest[dir]];
+        const uint4* box = p.mail_in + ((size_t)dir * W + chain) * MU;
+        for (int e = lane; e < MU; e += CL) {
+          uint4 v = ld_volatile_u4(box + e);
+          while ((v.y != tag || v.w != tag) && ok) {
+            if (clock64() - t_start > SPIN_TIMEOUT_CYCLES) {
+              atomicExch(&ctrl->error, EB_DEVERR_PEER_TIMEOUT);
+              ok = false;
+            }
+            v = ld_volatile_u4(box + e);
+          }
+          const double x = __hiloint2double((int)v.z, (int)v.x);
+          if (e < LD) c.coords[dslot * LD + e] = x;
+          else c.logp[dslot] = x;
+        }
+      }
     }
   }
 
@@ -644,8 +715,11 @@ static int launch_swap_kernel(SwapArgs& args, cudaStream_t s) {
   // programmatic dependent of the move kernel: positions and log(u) are computed while the move still runs
   cudaLaunchAttribute attr[1];
   static const int pdl_mask = getenv("EB_PDL_MASK") ? atoi(getenv("EB_PDL_MASK")) : 5;
-  args.pdl = (pdl_mask & 2) ? 1 : 0;
-  if (pdl_mask & 2) {
+  // bit 1: programmatic dependent of the move kernel, prologue before the grid-dependency wait; bit 3: programmatic
+  // dependent that waits FIRST (its CTAs are resident when the move kernel retires, no launch gap, and they do not
+  // compete with the move kernel for issue slots)
+  args.pdl = (pdl_mask & 8) ? 2 : (pdl_mask & 2) ? 1 : 0;
+  if (pdl_mask & 10) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
@@ -767,6 +841,15 @@ int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rn
     }
     args.pub_src = sh->pub_src;
     args.ll_in = (const uint4*)sh->ll_in;
+  }
+  if (sh->mail_in) {
+    if (!sh->pub_src) return fail(EB_ERR_INVALID, "row mail rides on the fused publish (set pub_src)");
+    if (dst->inds) return fail(EB_ERR_UNSUPPORTED, "row mail carries coords and logp only (no leaf flags)");
+    for (int g = 0; g < sh->world; ++g) {
+      if (!sh->mail_peer[g]) return fail(EB_ERR_INVALID, "mailbox of rank %d is NULL", g);
+      args.mail_dst[g] = (uint4*)sh->mail_peer[g];
+    }
+    args.mail_in = (const uint4*)sh->mail_in;
   }
   if (T < 2) return eb_advance_iter(ctrl, stream);
   return launch_swap<true>(args, (cudaStream_t)stream);

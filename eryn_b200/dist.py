@@ -83,6 +83,8 @@ class ArenaLayout(object):
         self.flags = take(16 * 8)
         # fused publish: logl of every rank as self-validating 16-byte units (eb_shard.pub_ll / ll_in), per parity
         self.logl_ll = [take(T * self.W * 16) for _ in range(2)]
+        # row mail: [direction][walker chain][L*D + 1] units per parity (eb_shard.mail_peer / mail_in)
+        self.mail = [take(2 * self.W * (self.L * self.D + 1) * 16) for _ in range(2)]
         self.total = o
 
 
@@ -128,7 +130,7 @@ class ShardedRun(object):
     """One rank of a temperature-sharded run: the shared arena, the peer mappings and the two
     (current, alternate) DeviceStates."""
 
-    def __init__(self, ctx, ntemps, nwalkers, nleaves=1, group=None, comm="fused"):
+    def __init__(self, ctx, ntemps, nwalkers, nleaves=1, group=None, comm="fused", mail=True):
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -205,6 +207,10 @@ class ShardedRun(object):
                 sh.ll_in = self.base + lay.logl_ll[p]
                 for g in range(self.world):
                     sh.pub_ll[g] = self.bases[g] + self.layouts[g].logl_ll[p]
+                if mail:
+                    sh.mail_in = self.base + lay.mail[p]
+                    for g in range(self.world):
+                        sh.mail_peer[g] = self.bases[g] + self.layouts[g].mail[p]
             pb.logl_local = self.base + lay.logl[p]
             self._shard.append(sh)
             self._pub.append(pb)

@@ -248,6 +248,15 @@ typedef struct {
   const double* pub_src;                   /* [T_rank][W] this rank's current logl rows */
   void* pub_ll[EB_MAX_RANKS];              /* peer-mapped LL buffers (this parity) of every rank: [T][W] 16-byte units */
   const void* ll_in;                       /* local LL buffer (this parity) */
+  /* Row mail (optional, needs pub_src; NULL = rows that change rank are pulled from *_src of the owning rank).  Every
+   * rank resolves the whole chain, so the rank that owns the SOURCE rung of a walker that changes rank pushes the row
+   * (coords, then logp; logl is known from the exchange) into the mailbox of the receiving rank as nleaves*ndim+1
+   * self-validating 16-byte units, slot [direction][walker chain]: direction 0 = arrives from the colder neighbour into
+   * the receiver's first rung, 1 = the carried walker arriving from hotter rungs.  One one-way NVLink trip, issued
+   * before the swap counts are published, instead of the round trip of a pull.  Mailboxes alternate with the iteration
+   * parity and must be zero when ctrl->iter is 0; [2][nwalkers][nleaves*ndim+1] units each. */
+  void* mail_peer[EB_MAX_RANKS];           /* peer-mapped mailboxes (this parity) of every rank */
+  const void* mail_in;                     /* local mailbox (this parity) */
 } eb_shard;
 EB_API int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rng* rng,
                        const eb_adapt* adapt, eb_ctrl* ctrl, void* stream);

@@ -42,6 +42,8 @@ def main():
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / a.iters
     print(f"device : {dt * 1e3:8.3f} ms/iteration  {T * W / dt:.3e} walker-updates/s  (nt={a.nt}, {torch.cuda.get_device_name(0)})")
+    if a.cpu_iters <= 0:
+        return
     like = rjo.PulseLike(t, y, 2.0, [0, 1])
     osmp = rjo.OracleSamplerMB(cases_rj.priors_for(t), like, [0, 0], [L, L], rjo.PhiloxStreamsMB(1),
                                betas=orc.make_ladder_default(6 * L, T), nfriends=nfriends, n_iter_update=100)
