@@ -57,15 +57,20 @@ static __device__ long long eb_dbg_marks[64];   // one copy per translation unit
     }                                                                                                 \
     cudaMemcpyFromSymbol(mn, eb_dbg_gmin, sizeof(unsigned long long) * 64);                           \
     return cudaMemcpyFromSymbol(mx, eb_dbg_gmax, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : 3; \
+  }                                                                                                   \
+  extern "C" __attribute__((visibility("default"))) int NAME##_cta(unsigned long long* out8x1024) {  \
+    return cudaMemcpyFromSymbol(out8x1024, eb_dbg_cta, sizeof(unsigned long long) * 8 * 1024) == cudaSuccess ? 0 : 3; \
   }
-static __device__ unsigned long long eb_dbg_gmin[64], eb_dbg_gmax[64];   // globaltimer (ns) spread over all CTAs
+static __device__ unsigned long long eb_dbg_gmin[64], eb_dbg_gmax[64];   // globaltimer (ns): first CTA / last CTA
+static __device__ unsigned long long eb_dbg_cta[8][1024];                // marks >= 16: globaltimer of every CTA, slot i & 7
 #define EB_MARK(i)                                                                     \
   do {                                                                                 \
-    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0) {  \
+    if (threadIdx.x == 0 && blockIdx.y == 0) {                                         \
       unsigned long long gt_;                                                          \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                          \
       if (blockIdx.x == 0) { eb_dbg_gmin[i] = gt_; eb_dbg_marks[i] = clock64(); }      \
       if (blockIdx.x == gridDim.x - 1) eb_dbg_gmax[i] = gt_;                           \
+      if ((i) >= 16 && blockIdx.x < 1024) eb_dbg_cta[(i) & 7][blockIdx.x] = gt_;       \
     }                                                                                  \
   } while (0)
 #else

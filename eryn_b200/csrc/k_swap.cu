@@ -60,7 +60,7 @@ __host__ __device__ inline int publish_ctas(size_t ndoubles, int nreal) {
 }
 
 struct SwapLayout {  // byte offsets into dynamic shared memory
-  size_t betas, dts, ll, lu, keys, pos, cnt, total;
+  size_t betas, dts, ll, lu, keys, pos, cnt, band, rej, total;
 };
 __host__ __device__ inline SwapLayout swap_layout(int T, int cpb) {
   SwapLayout s;
@@ -72,6 +72,8 @@ __host__ __device__ inline SwapLayout swap_layout(int T, int cpb) {
   s.keys = o; o += sizeof(uint32_t) * FEISTEL_ROUNDS * T;
   s.pos = o; o += sizeof(int) * T * cpb;
   s.cnt = o; o += sizeof(int) * T;
+  s.band = o; o += (size_t)T * cpb;
+  s.rej = o; o += (size_t)T * cpb;
   s.total = (o + 15) & ~(size_t)15;
   return s;
 }
@@ -152,6 +154,10 @@ __device__ __forceinline__ void publish_ll(const SwapArgs& p, unsigned long long
   }
 }
 
+// slots the CTAs spread their partial swap counts and arrivals over (same-address atomics serialise in L2, but the
+// adapt CTA reads slots x (T-1) words): fewer slots for long ladders
+__device__ __forceinline__ int swap_slots(int T) { return T > 16 ? 8 : EB_SWAP_SLOTS; }
+
 // The adapt CTA of the swap pass: wait for the counts of all `nreal` chain CTAs, fold them into swaps_accepted and
 // apply adapt_temps (tempering.py:563-596); ticks the iteration counter.
 __device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, int nreal, unsigned long long it,
@@ -163,8 +169,9 @@ __device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, i
   if (tid == 0) { s_time = time_now_t0; s_ok2 = 1; }
   for (int r = tid; r < T; r += blockDim.x) s_cnt[r] = 0;
   __syncthreads();
-  if (tid < EB_SWAP_SLOTS) {
-    const unsigned expected = (unsigned)(nreal / EB_SWAP_SLOTS + (tid < nreal % EB_SWAP_SLOTS ? 1 : 0));
+  const int NS = swap_slots(T);
+  if (tid < NS) {
+    const unsigned expected = (unsigned)(nreal / NS + (tid < nreal % NS ? 1 : 0));
     const volatile unsigned* a = &ctrl->arrive[tid];
     const long long t_start = clock64();
     while (*a < expected)
@@ -173,17 +180,19 @@ __device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, i
     ctrl->arrive[tid] = 0u;
   }
   __syncthreads();
+  EB_MARK(28);
   if (!s_ok2) {
     if (tid == 0) atomicExch(&ctrl->error, EB_DEVERR_SWAP_TIMEOUT);
     return;
   }
   // fold the slot counts (independent loads first, the dependent bookkeeping stores last: the ladder is what the next
   // kernel waits for)
-  for (int e = tid; e < EB_SWAP_SLOTS * (T - 1); e += blockDim.x) {
+  for (int e = tid; e < NS * (T - 1); e += blockDim.x) {
     const int v = *reinterpret_cast<volatile int*>(&ctrl->swaps_work[e / (T - 1)][e % (T - 1)]);
     if (v) atomicAdd(&s_cnt[e % (T - 1)], v);
   }
   __syncthreads();
+  EB_MARK(29);
   const long long time_now = s_time;
   if (p.adapt_on && p.adaptive && T > 1) {                                     // tempering.py:632-633
     if (p.stop_adaptation < 0 || time_now < (long long)p.stop_adaptation) {   // :590
@@ -212,7 +221,8 @@ __device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, i
     }
     if (tid == 0) ctrl->time = time_now + 1;                                   // :596
   }
-  for (int e = tid; e < EB_SWAP_SLOTS * (T - 1); e += blockDim.x) ctrl->swaps_work[e / (T - 1)][e % (T - 1)] = 0;
+  EB_MARK(30);
+  for (int e = tid; e < NS * (T - 1); e += blockDim.x) ctrl->swaps_work[e / (T - 1)][e % (T - 1)] = 0;
   for (int r = tid; r < T - 1; r += blockDim.x) {
     const int v = s_cnt[r];
     ctrl->swaps_accepted[r] = v;
@@ -222,6 +232,7 @@ __device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, i
 }
 
 constexpr int SWAP_THREADS = 256;
+constexpr int SWAP_AGES = 8;      // tests per walker evaluated ahead of the cascade walk (bits of one band byte)
 
 // CL lanes resolve one chain; lane l owns rungs l, l+CL, l+2CL, ...  (CL = 8, 16 or 32).
 // RR > 0: rows of up to RR doubles move through registers (needs T <= RPL*CL and no leaf flags); RR == 0: through the
@@ -382,60 +393,146 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   }
   __syncthreads();
   EB_MARK(18);
-  // ---- the cascade, hot -> cold (tempering.py:515-559 restricted to this chain); every lane of the chain runs it
-  //      (same operands, broadcast reads), so every lane knows all accept bits.
-  // The carried log-likelihood is always an ORIGINAL value: after a rejected swap at rung i+1 the walker of rung i is
-  // carried on, and its test at rung i, dts[i] * (ll[i] - ll[i-1]) > lu[i], depends on nothing the cascade decides.
-  // Those "fresh" tests are evaluated for all rungs at once, one or a few rungs per lane (same expression, same
-  // rounding), and exchanged by ballot; the sequential walk then needs the dependent DADD -> DMUL -> DSETP chain only
-  // while a walker is carried further than one rung (a run of accepted swaps), and a bit test otherwise.
+  // ---- the cascade, hot -> cold (tempering.py:515-559 restricted to this chain).  Long ladders (RR == 0):
+  // The carried log-likelihood is always an ORIGINAL value ll[j]: the walker that starts on rung j is tested at rungs
+  // j, j-1, ... (test_i(x) = dts[i] * (x - ll[i-1]) > lu[i], :538/:541, s_dts[i] = betas[i-1]-betas[i]) until a swap is
+  // rejected at rung s = j - run; it settles there and the walker of rung s-1 is carried on.  None of these tests depends
+  // on what the cascade decides, only on WHICH of them are looked at.  So the lanes first evaluate, in parallel and with
+  // the reference's expression and rounding, the first SWAP_AGES tests of every walker ("band" of walker j, bit a-1 =
+  // test at rung j-a+1); the sequential part is then a walk j -> j - run - 1 that costs one shared-memory load and a
+  // bit scan per CARRIED walker instead of a dependent DADD -> DMUL -> DSETP chain per rung.  Runs longer than the band
+  // (probability ~ accept_rate^8) continue with the plain sequential tests.  Every lane of the chain runs the walk
+  // (broadcast reads), so every lane knows all accept bits.
   unsigned long long sel_lo = 0ull, sel_hi = 0ull;
-  {
-    unsigned long long fr_lo = 0ull, fr_hi = 0ull;
-    constexpr int NB = CL == 32 ? 4 : 1;              // T <= 128 with 32 lanes, T <= CL otherwise
-    const int sh = (tid & 31) - lane;                 // first lane of this chain's group within the warp
-#pragma unroll
-    for (int m = 0; m < NB; ++m) {
-      const int r = lane + m * CL;
-      bool f = false;
-      if (valid && r >= 1 && r < T) f = s_dts[r] * (ll[r] - ll[r - 1]) > lu[r];     // :538, :541  (s_dts[i] = betas[i-1]-betas[i])
-      const unsigned v = __ballot_sync(0xffffffffu, f);
-      if (CL == 32) {                                 // one chain per warp: ballot m holds rungs 32m .. 32m+31
-        if (m == 0) fr_lo |= (unsigned long long)v;
-        if (m == 1) fr_lo |= (unsigned long long)v << 32;
-        if (m == 2) fr_hi |= (unsigned long long)v;
-        if (m == 3) fr_hi |= (unsigned long long)v << 32;
-      } else {                                        // several chains per warp: this chain's CL bits
-        fr_lo = (unsigned long long)((v >> sh) & ((1u << (CL & 31)) - 1u));
-      }
-    }
+  if (RR > 0) {
+    // short ladders (T <= CL * RPL <= 64): the plain sequential cascade with a compile-time trip count, so that the operand
+    // loads of all rungs are hoisted above the dependent chain; every lane runs it on broadcast operands.  Measured
+    // faster than the band walk below up to 32 rungs (1.8 us against 2.2 us for the pass at T = 32).
     if (valid && !EB_DBG_SKIP(8)) {
-      bool fresh = true;
-      double carry = 0.0;
-      for (int i = T - 1; i >= 1; --i) {
-        if (fresh) {
-          if (sel_bit(fr_lo, fr_hi, i)) {
-            if (i < 64) sel_lo |= 1ull << i;
-            else sel_hi |= 1ull << (i - 64);
-            carry = ll[i];             // carried past rung i-1: from here on the test depends on the cascade
-            fresh = false;
-          }                            // else: the carried walker settles on rung i, rung i-1's walker is carried on
-        } else {
-          const bool sel = s_dts[i] * (carry - ll[i - 1]) > lu[i];
+      double carry = ll[T - 1];
+#pragma unroll
+      for (int i = CL * RPL - 1; i >= 1; --i) {
+        if (i < T) {
+          const double lower = ll[i - 1];
+          const bool sel = s_dts[i] * (carry - lower) > lu[i];                 // :538, :541  (s_dts[i] = betas[i-1]-betas[i])
           if (sel) {
             if (i < 64) sel_lo |= 1ull << i;
             else sel_hi |= 1ull << (i - 64);
           } else {
-            fresh = true;
+            carry = lower;               // the carried walker settles on rung i, rung i-1's walker is carried on
+          }
+        }
+      }
+    }
+  } else {
+    constexpr int NB = CL == 32 ? 4 : 1;              // T <= 128 with 32 lanes, T <= CL otherwise
+    unsigned char* sband = smraw + lay.band + (size_t)gg * T;
+    unsigned char* s_rej = smraw + lay.rej + (size_t)gg * T;
+    if (valid) {
+#pragma unroll
+      for (int m = 0; m < NB; ++m) {
+        const int j = lane + m * CL;
+        if (j < T) s_rej[j] = 0;
+        if (j >= 1 && j < T) {
+          const double x = ll[j];
+          unsigned b = 0u;
+#pragma unroll
+          for (int a = 0; a < SWAP_AGES; ++a) {
+            const int i = j - a;
+            if (i >= 1) b |= (unsigned)(s_dts[i] * (x - ll[i - 1]) > lu[i]) << a;
+          }
+          sband[j] = (unsigned char)b;
+        }
+      }
+    }
+    __syncwarp();
+    // the walk: every rung sees exactly one test, and the rejected ones are the rungs where a carried walker settles,
+    // so the walk only MARKS those (one byte store per carried walker, nothing depends on it); the accept bits are
+    // the complement, collected by ballot afterwards
+    if (valid && !EB_DBG_SKIP(8)) {
+      int j = T - 1;
+      while (j >= 1) {
+        const unsigned b = sband[j];
+        int run = __ffs((int)~b) - 1;                 // accepted swaps in a row, as far as the band knows
+        if (run == SWAP_AGES) {                       // beyond the band: the plain sequential tests
+          const double carry = ll[j];
+          int i = j - SWAP_AGES;
+          while (i >= 1 && s_dts[i] * (carry - ll[i - 1]) > lu[i]) { ++run; --i; }
+        }
+        j -= run;                                     // it settles on this rung: the swap here was rejected (unless rung 0)
+        s_rej[j] = 1;
+        --j;                                          // the walker below is carried on
+      }
+    }
+    __syncwarp();
+    {
+      const int sh = (tid & 31) - lane;               // first lane of this chain's group within the warp
+#pragma unroll
+      for (int m = 0; m < NB; ++m) {
+        if (m * CL < T) {                             // uniform
+          const int r = lane + m * CL;
+          const bool acc = valid && r >= 1 && r < T && s_rej[r] == 0;
+          const unsigned v = __ballot_sync(0xffffffffu, acc);
+          if (CL == 32) {                             // one chain per warp: ballot m holds rungs 32m .. 32m+31
+            if (m == 0) sel_lo |= (unsigned long long)v;
+            if (m == 1) sel_lo |= (unsigned long long)v << 32;
+            if (m == 2) sel_hi |= (unsigned long long)v;
+            if (m == 3) sel_hi |= (unsigned long long)v << 32;
+          } else {                                    // several chains per warp: this chain's CL bits
+            sel_lo = (unsigned long long)((v >> sh) & ((1u << (CL & 31)) - 1u));
           }
         }
       }
     }
   }
 
-  // ---- sharded: rows that change rank leave NOW, before the counts are published, as mail pushed by the rank that
+  EB_MARK(19);
+  // ---- swap counts: swaps_accepted[r-1] counts accepted swaps at rung r (:542): ballot over the chains of the warp,
+  //      shared-memory atomics over the block, global atomics over the grid
+  {
+    constexpr int CPW = 32 / CL;                     // chains per warp
+    const int wl = tid & 31;
+    for (int r0 = 0; r0 < T; r0 += CL) {             // uniform trip count: the loop body votes
+      const int r = r0 + lane;
+      const bool b = valid && r >= 1 && r < T && sel_bit(sel_lo, sel_hi, r);
+      const unsigned v = __ballot_sync(0xffffffffu, b);
+      if (wl < CL) {
+        unsigned m = 0u;
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) m |= 1u << (wl + q * CL);
+        const int n = __popc(v & m);
+        if (n) atomicAdd(&s_cnt[r - 1], n);
+      }
+    }
+  }
+
+  // the counts are published here, before the rows move (fire-and-forget reductions + one arrival per CTA, all spread
+  // over EB_SWAP_SLOTS addresses: same-address atomics serialise in L2)
+  __syncthreads();
+  if (EB_DBG_SKIP(2)) {
+    if (adapt_cta) return;
+  } else if (!adapt_cta) {
+    for (int r = tid; r < T - 1; r += blockDim.x)
+      if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[blockIdx.x % swap_slots(T)][r], s_cnt[r]);
+    __syncthreads();
+    if (tid == 0) {        // block barrier + one device-scope release by the signalling thread (cumulative)
+      fence_acq_rel_gpu();
+      atomicAdd(&ctrl->arrive[blockIdx.x % swap_slots(T)], 1u);
+    }
+  } else {
+    if (EB_DBG_SKIP(4)) { if (tid < EB_SWAP_SLOTS) ctrl->arrive[tid] = 0u; return; }
+    pt_swap_adapt(p, T, W, nreal, it, time_now, s_betas, s_dts, s_cnt);
+    EB_MARK(23);
+    return;
+  }
+
+  EB_MARK(20);
+  // ---- move the rows that changed rung (do_swaps_indexing, tempering.py:351-482): every lane gathers the source rows
+  //      of its rungs, the lanes of the chain synchronise (all reads before any write), then write
+  if (EB_DBG_SKIP(1)) return;
+  // ---- sharded: rows that change rank leave first (right after the counts, which the adapt CTA waits for), as mail pushed by the rank that
   //      owns the source rung (every rank has resolved the whole chain, so sender and receiver agree without talking):
-  //      a one-way NVLink trip that runs under the count publication and the local row copies, instead of the round
+  //      a one-way NVLink trip that runs under the local row copies, instead of the round
   //      trip of a pull.  A mail is LD+1 self-validating units (row, then logp) in the receiver's mailbox, slot
   //      [direction][chain]; per chain and rank at most one walker arrives from below (into rung t_lo, when the swap at
   //      t_lo is accepted) and at most one from above (the carried walker, where it settles).  The lanes of the chain
@@ -474,50 +571,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     }
   }
 
-  EB_MARK(19);
-  // ---- swap counts: swaps_accepted[r-1] counts accepted swaps at rung r (:542): ballot over the chains of the warp,
-  //      shared-memory atomics over the block, global atomics over the grid
-  {
-    constexpr int CPW = 32 / CL;                     // chains per warp
-    const int wl = tid & 31;
-    for (int r0 = 0; r0 < T; r0 += CL) {             // uniform trip count: the loop body votes
-      const int r = r0 + lane;
-      const bool b = valid && r >= 1 && r < T && sel_bit(sel_lo, sel_hi, r);
-      const unsigned v = __ballot_sync(0xffffffffu, b);
-      if (wl < CL) {
-        unsigned m = 0u;
-#pragma unroll
-        for (int q = 0; q < CPW; ++q) m |= 1u << (wl + q * CL);
-        const int n = __popc(v & m);
-        if (n) atomicAdd(&s_cnt[r - 1], n);
-      }
-    }
-  }
-
-  // the counts are published here, before the rows move (fire-and-forget reductions + one arrival per CTA, all spread
-  // over EB_SWAP_SLOTS addresses: same-address atomics serialise in L2)
-  __syncthreads();
-  if (EB_DBG_SKIP(2)) {
-    if (adapt_cta) return;
-  } else if (!adapt_cta) {
-    for (int r = tid; r < T - 1; r += blockDim.x)
-      if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[blockIdx.x % EB_SWAP_SLOTS][r], s_cnt[r]);
-    __syncthreads();
-    if (tid == 0) {        // block barrier + one device-scope release by the signalling thread (cumulative)
-      fence_acq_rel_gpu();
-      atomicAdd(&ctrl->arrive[blockIdx.x % EB_SWAP_SLOTS], 1u);
-    }
-  } else {
-    if (EB_DBG_SKIP(4)) { if (tid < EB_SWAP_SLOTS) ctrl->arrive[tid] = 0u; return; }
-    pt_swap_adapt(p, T, W, nreal, it, time_now, s_betas, s_dts, s_cnt);
-    EB_MARK(23);
-    return;
-  }
-
-  EB_MARK(20);
-  // ---- move the rows that changed rung (do_swaps_indexing, tempering.py:351-482): every lane gathers the source rows
-  //      of its rungs, the lanes of the chain synchronise (all reads before any write), then write
-  if (EB_DBG_SKIP(1)) return;
+  EB_MARK(31);
   if (!SHARDED) {
     if (RR > 0) {
       constexpr int RRX = RR > 0 ? RR : 1;

@@ -81,8 +81,19 @@ def main():
                 f = lambda v: int(v) - int(base)
                 print(f"[{comm}] rank {rank} timeline ns: K1b start 0 end {f(sn[7])} lastCTA-end {f(sx[7])} | swap start {f(mn[16])} "
                       f"keys {f(mn[17])} publish-issued {f(mn[27])} flags-seen {f(mn[26])} gathered {f(mn[18])} cascade {f(mn[19])} "
-                      f"counts {f(mn[20])} rows {f(mn[21])} | adaptCTA start {f(mx[16])} flags-seen {f(mx[26])} done {f(mx[23])}",
+                      f"counts {f(mn[20])} mail-pushed {f(mn[31])} rows {f(mn[21])} | adaptCTA start {f(mx[16])} gathered {f(mx[18])} all-arrived {f(mx[28])} "
+                      f"folded {f(mx[29])} betas {f(mx[30])} done {f(mx[23])}",
                       flush=True)
+            cta = (ctypes.c_uint64 * (8 * 1024))()
+            if hasattr(run.lib, "eb_debug_marks_swap_cta") and run.lib.eb_debug_marks_swap_cta(cta) == 0:
+                a = np.frombuffer(cta, dtype=np.uint64).reshape(8, 1024).astype(np.int64)
+                nreal = (W + 7) // 8 if T > 16 else (W + 15) // 16
+                names = {0: "start", 1: "keys", 2: "gathered", 3: "cascade", 4: "counts", 7: "mail-pushed", 5: "rows"}
+                txt = []
+                for slot in (0, 1, 2, 3, 4, 7, 5):
+                    v = a[slot, :nreal] - int(base)
+                    txt.append(f"{names[slot]} min {v.min()} med {int(np.median(v))} max {v.max()} (argmax CTA {int(v.argmax())})")
+                print(f"[{comm}] rank {rank} over the {nreal} chain CTAs, ns: " + " | ".join(txt), flush=True)
         dist.barrier()
         run.close()
     dist.destroy_process_group()
