@@ -60,7 +60,7 @@ __host__ __device__ inline int publish_ctas(size_t ndoubles, int nreal) {
 }
 
 struct SwapLayout {  // byte offsets into dynamic shared memory
-  size_t betas, dts, ll, lu, keys, pos, cnt, band, rej, total;
+  size_t betas, dts, ll, lu, keys, pos, cnt, band, rej, on, total;
 };
 __host__ __device__ inline SwapLayout swap_layout(int T, int cpb) {
   SwapLayout s;
@@ -74,6 +74,7 @@ __host__ __device__ inline SwapLayout swap_layout(int T, int cpb) {
   s.cnt = o; o += sizeof(int) * T;
   s.band = o; o += (size_t)T * cpb;
   s.rej = o; o += (size_t)T * cpb;
+  s.on = o; o += (size_t)T * cpb;
   s.total = (o + 15) & ~(size_t)15;
   return s;
 }
@@ -207,9 +208,16 @@ __device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, i
         s_dts[j] = dT * exp(dS);                                               // :579
       }
       __syncthreads();
-      if (tid == 0) {                                                          // np.cumsum: sequential adds
+      if (tid == 0) {                                                          // np.cumsum: sequential adds, in order
         double cum = 0.0;
-        for (int j = 0; j + 2 < T; ++j) { cum = cum + s_dts[j]; s_dts[j] = cum; }
+        for (int j0 = 0; j0 + 2 < T; j0 += 8) {                                // operands loaded ahead of the dependent adds
+          double v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = j0 + k + 2 < T ? s_dts[j0 + k] : 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (j0 + k + 2 < T) { cum = cum + v[k]; s_dts[j0 + k] = cum; }
+        }
       }
       __syncthreads();
       const double inv_b0 = 1.0 / s_betas[0];
@@ -393,21 +401,18 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   }
   __syncthreads();
   EB_MARK(18);
-  // ---- the cascade, hot -> cold (tempering.py:515-559 restricted to this chain).  Long ladders (RR == 0):
+  // ---- the cascade, hot -> cold (tempering.py:515-559 restricted to this chain).
   // The carried log-likelihood is always an ORIGINAL value ll[j]: the walker that starts on rung j is tested at rungs
   // j, j-1, ... (test_i(x) = dts[i] * (x - ll[i-1]) > lu[i], :538/:541, s_dts[i] = betas[i-1]-betas[i]) until a swap is
   // rejected at rung s = j - run; it settles there and the walker of rung s-1 is carried on.  None of these tests depends
-  // on what the cascade decides, only on WHICH of them are looked at.  So the lanes first evaluate, in parallel and with
-  // the reference's expression and rounding, the first SWAP_AGES tests of every walker ("band" of walker j, bit a-1 =
-  // test at rung j-a+1); the sequential part is then a walk j -> j - run - 1 that costs one shared-memory load and a
-  // bit scan per CARRIED walker instead of a dependent DADD -> DMUL -> DSETP chain per rung.  Runs longer than the band
-  // (probability ~ accept_rate^8) continue with the plain sequential tests.  Every lane of the chain runs the walk
-  // (broadcast reads), so every lane knows all accept bits.
+  // on what the cascade decides, only on WHICH walkers get carried.  Sharded passes and long ladders therefore resolve
+  // the chain by walking over the CARRIED walkers only (below), with their first tests evaluated ahead for all walkers at
+  // once and long runs extended 32 rungs per step (same expression and rounding as the reference throughout).
   unsigned long long sel_lo = 0ull, sel_hi = 0ull;
-  if (RR > 0) {
-    // short ladders (T <= CL * RPL <= 64): the plain sequential cascade with a compile-time trip count, so that the operand
-    // loads of all rungs are hoisted above the dependent chain; every lane runs it on broadcast operands.  Measured
-    // faster than the band walk below up to 32 rungs (1.8 us against 2.2 us for the pass at T = 32).
+  if (RR > 0 && !SHARDED) {
+    // single-GPU passes with rows in registers (T <= CL * RPL <= 64): the plain sequential cascade with a compile-time
+    // trip count, so that the operand loads of all rungs are hoisted above the dependent chain; every lane runs it on
+    // broadcast operands (0.8 us at 16 rungs, 3.9 us at 64).
     if (valid && !EB_DBG_SKIP(8)) {
       double carry = ll[T - 1];
 #pragma unroll
@@ -428,6 +433,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     constexpr int NB = CL == 32 ? 4 : 1;              // T <= 128 with 32 lanes, T <= CL otherwise
     unsigned char* sband = smraw + lay.band + (size_t)gg * T;
     unsigned char* s_rej = smraw + lay.rej + (size_t)gg * T;
+    // (a) band of walker j: bit a = test at rung j-a with x = ll[j], a < SWAP_AGES — all walkers at once
     if (valid) {
 #pragma unroll
       for (int m = 0; m < NB; ++m) {
@@ -446,22 +452,45 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
       }
     }
     __syncwarp();
-    // the walk: every rung sees exactly one test, and the rejected ones are the rungs where a carried walker settles,
-    // so the walk only MARKS those (one byte store per carried walker, nothing depends on it); the accept bits are
-    // the complement, collected by ballot afterwards
-    if (valid && !EB_DBG_SKIP(8)) {
+    // (b) the walk over the CARRIED walkers only: j -> j - run - 1.  Every rung sees exactly one test and the rejected
+    //     ones are the rungs where a carried walker settles, so the walk only marks those; the accept bits are the
+    //     complement, collected by ballot below.  A run that outlasts the band (hot end of a long ladder: beta ~ 0, every
+    //     swap accepted) is extended 32 rungs per step — the tests of one carried value are independent of each other,
+    //     so the lanes of the warp evaluate one rung each and vote (CL == 32: one chain per warp, uniform control flow);
+    //     groups of 8 / 16 lanes (T <= 16) extend it with the plain sequential tests.
+    if (CL == 32) {
+      int j = T - 1;
+      while (j >= 1) {                                // uniform over the warp
+        int run = 0;
+        if (valid && !EB_DBG_SKIP(8)) {
+          run = __ffs((int)~(unsigned)sband[j]) - 1;
+          if (run == SWAP_AGES) {
+            const double x = ll[j];
+            int base = j - SWAP_AGES;                 // next untested rung
+            while (base >= 1) {
+              const int i = base - lane;
+              const bool f = i >= 1 && s_dts[i] * (x - ll[i - 1]) > lu[i];
+              const int n = __ffs((int)~__ballot_sync(0xffffffffu, f)) - 1;   // wins in a row from rung `base` downwards
+              if (n < 0) { run += 32; base -= 32; continue; }                 // all 32 won
+              run += n;
+              break;
+            }
+          }
+          s_rej[j - run] = 1;                         // settles here: this swap was rejected (or rung 0)
+        }
+        j -= run + 1;                                 // the walker below is carried on
+      }
+    } else if (valid && !EB_DBG_SKIP(8)) {
       int j = T - 1;
       while (j >= 1) {
-        const unsigned b = sband[j];
-        int run = __ffs((int)~b) - 1;                 // accepted swaps in a row, as far as the band knows
-        if (run == SWAP_AGES) {                       // beyond the band: the plain sequential tests
-          const double carry = ll[j];
+        int run = __ffs((int)~(unsigned)sband[j]) - 1;
+        if (run == SWAP_AGES) {
+          const double x = ll[j];
           int i = j - SWAP_AGES;
-          while (i >= 1 && s_dts[i] * (carry - ll[i - 1]) > lu[i]) { ++run; --i; }
+          while (i >= 1 && s_dts[i] * (x - ll[i - 1]) > lu[i]) { ++run; --i; }
         }
-        j -= run;                                     // it settles on this rung: the swap here was rejected (unless rung 0)
-        s_rej[j] = 1;
-        --j;                                          // the walker below is carried on
+        s_rej[j - run] = 1;
+        j -= run + 1;
       }
     }
     __syncwarp();

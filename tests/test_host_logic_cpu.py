@@ -99,3 +99,59 @@ def test_oracle_philox_sampler_is_a_valid_sampler():
     assert np.all(np.abs(xs.mean(0)) < 0.15)
     assert np.all(np.abs(xs.var(0) - 1.0) < 0.2)
     assert smp.swaps_accepted.sum() > 0
+
+
+def _cascade_sequential(T, ll, lu, dts):
+    """tempering.py:515-559 restricted to one chain (the order the reference resolves the ladder in)"""
+    sel = np.zeros(T, bool)
+    carry = ll[T - 1]
+    for i in range(T - 1, 0, -1):
+        lower = ll[i - 1]
+        if dts[i] * (carry - lower) > lu[i]:
+            sel[i] = True
+        else:
+            carry = lower
+    return sel
+
+
+def _cascade_band_walk(T, ll, lu, dts, ages=8, lanes=32):
+    """the resolution of k_swap.cu for long ladders / sharded passes: a band of `ages` tests per walker evaluated ahead,
+    a walk over the carried walkers only (j -> j - run - 1) that marks the rung where each settles, runs that outlast
+    the band extended `lanes` rungs per step by a vote; accepted rungs = the complement of the marked ones"""
+    band = np.zeros(T, int)
+    for j in range(1, T):
+        for a in range(ages):
+            i = j - a
+            if i >= 1 and dts[i] * (ll[j] - ll[i - 1]) > lu[i]:
+                band[j] |= 1 << a
+    rej = np.zeros(T, bool)
+    j = T - 1
+    while j >= 1:
+        run = 0
+        while run < ages and (band[j] >> run) & 1:
+            run += 1
+        if run == ages:
+            base = j - ages
+            while base >= 1:
+                votes = [(base - l >= 1) and bool(dts[base - l] * (ll[j] - ll[base - l - 1]) > lu[base - l]) for l in range(lanes)]
+                n = votes.index(False) if False in votes else -1
+                if n < 0:
+                    run, base = run + lanes, base - lanes
+                    continue
+                run += n
+                break
+        rej[j - run] = True
+        j -= run + 1
+    sel = ~rej
+    sel[0] = False
+    return sel
+
+
+def test_band_walk_cascade_equals_sequential_ladder():
+    rng = np.random.RandomState(3)
+    for _ in range(600):
+        T = int(rng.choice([2, 3, 5, 8, 16, 24, 32, 70, 128]))
+        ll = rng.randn(T) * rng.choice([0.1, 1, 10])
+        lu = np.log(rng.rand(T)) * rng.choice([0.01, 1])
+        dts = np.abs(rng.randn(T)) * rng.choice([0.0, 0.01, 1, 100])   # 0.0: the hot end, every swap accepted
+        assert np.array_equal(_cascade_sequential(T, ll, lu, dts), _cascade_band_walk(T, ll, lu, dts))

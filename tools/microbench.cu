@@ -138,6 +138,11 @@ int main(int argc, char** argv) {
   sr.mode = EB_RNG_PHILOX; sr.randomize_split = 1; sr.seed = 7; sr.iter_dev = &ctrl->iter_next; sr.pdl_chain = 1;
   eb_swap_rng wr; std::memset(&wr, 0, sizeof(wr));
   wr.mode = EB_RNG_PHILOX; wr.permute = 1; wr.seed = 7; wr.iter_dev = &ctrl->iter;
+  {   // staging buffers of the shapes whose rows do not move through registers (long ladders / long rows)
+    double *rs, *ls;
+    CK(cudaMalloc(&rs, (size_t)T * W * D * 8)); CK(cudaMalloc(&ls, (size_t)T * W * 8));
+    wr.row_scratch = rs; wr.logp_scratch = ls;
+  }
   eb_adapt ad{1, -1, 10000.0, 100.0};
   eb_gauss_rng gr; std::memset(&gr, 0, sizeof(gr));
   gr.mode = EB_RNG_PHILOX; gr.cov_kind = 0; gr.scale = 0.1; gr.seed = 7; gr.iter_dev = &ctrl->iter;
