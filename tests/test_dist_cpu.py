@@ -35,11 +35,15 @@ def test_arena_layout_is_deterministic_and_disjoint():
     for rank in range(2):
         a, b = ArenaLayout(tb, rank, 100, 1, 8), ArenaLayout(tb, rank, 100, 1, 8)
         assert a.__dict__ == b.__dict__
-        offs = a.coords + a.logl + a.logp + a.logl_all + [a.betas_all, a.flags, a.total]
+        offs = a.coords + a.logl + a.logp + a.logl_all + [a.betas_all, a.flags] + a.logl_ll + a.mail + [a.total]
         assert offs == sorted(offs) and len(set(offs)) == len(offs)
         assert all(o % ALIGN == 0 for o in offs)
         assert a.coords[1] - a.coords[0] >= a.Tg * 100 * 8 * 8
         assert a.logl_all[1] - a.logl_all[0] >= 5 * 100 * 8
+        # fused publish: one 16-byte self-validating unit per (temperature, walker) of the FULL ladder, per parity;
+        # row mail: [direction][walker chain][L*D + 1] units per parity
+        assert a.logl_ll[1] - a.logl_ll[0] >= 5 * 100 * 16
+        assert a.mail[1] - a.mail[0] >= 2 * 100 * (8 + 1) * 16 and a.total - a.mail[1] >= 2 * 100 * (8 + 1) * 16
     assert ArenaLayout(tb, 0, 100, 1, 8).Tg == 3 and ArenaLayout(tb, 1, 100, 1, 8).Tg == 2
 
 
@@ -128,3 +132,65 @@ def test_sharded_oracle_equals_unsharded_gloo(tmp_path, T, world):
     assert np.array_equal(got["logp"], st.logp)
     assert np.array_equal(got["betas"], smp.betas)
     assert np.array_equal(got["swaps"], smp.swaps_accepted)
+
+
+def _swap_source(sel, r, T):
+    """k_swap.cu:swap_source — rung whose walker ends on rung r (sel[i] = swap accepted at rung i)"""
+    if r >= 1 and sel[r]:
+        return r - 1
+    o = r
+    while o + 1 < T and sel[o + 1]:
+        o += 1
+    return o
+
+
+def test_row_mail_routing_senders_and_receivers_agree():
+    """The sharded swap pass pushes rows that change rank (eb_shard.mail_*): the rank owning the SOURCE rung sends, the
+    rank owning the destination rung polls its mailbox slot [direction] — both derive everything from the accept bits.
+    Restated here for random bit patterns and partitions (walkers carried across several ranks included): every owned
+    rung with a remote source is served by exactly one mail, addressed to the right rank and direction."""
+    from eryn_b200.dist import owner_of, temperature_partition
+    rng = np.random.RandomState(11)
+    for _ in range(2000):
+        world = int(rng.choice([2, 3, 4, 8]))
+        T = int(rng.randint(world, 40))
+        tb = temperature_partition(T, world)
+        sel = np.zeros(T + 1, bool)
+        sel[1:T] = rng.rand(T - 1) < rng.choice([0.2, 0.5, 0.9, 1.0])
+        sent = {}  # (dest rank, direction) -> source rung
+        for g in range(world):
+            t_lo, t_hi = tb[g], tb[g + 1]
+            if t_hi < T and sel[t_hi]:  # up: my top walker moves to rung t_hi
+                key = (owner_of(tb, t_hi), 0)
+                assert key not in sent
+                sent[key] = t_hi - 1
+            if t_lo >= 1 and sel[t_lo]:  # down: the walker carried across my lower boundary, if it started here
+                o = t_lo
+                while o + 1 < T and sel[o + 1]:
+                    o += 1
+                if o < t_hi:
+                    d = t_lo - 1
+                    while d >= 1 and sel[d]:
+                        d -= 1
+                    key = (owner_of(tb, d), 1)
+                    assert key not in sent
+                    sent[key] = o
+        expected = {}
+        for g in range(world):
+            t_lo, t_hi = tb[g], tb[g + 1]
+            dest = [-1, -1]
+            if t_lo >= 1 and sel[t_lo]:
+                dest[0] = t_lo
+            if t_hi < T and sel[t_hi]:
+                d = t_hi - 1
+                while d >= 1 and sel[d]:
+                    d -= 1
+                if d >= t_lo:
+                    dest[1] = d
+            remote = {r: _swap_source(sel, r, T) for r in range(t_lo, t_hi) if owner_of(tb, _swap_source(sel, r, T)) != g}
+            assert sorted(remote) == sorted(x for x in dest if x >= 0)
+            for direction, r in enumerate(dest):
+                if r >= 0:
+                    assert (remote[r] == r - 1) == (direction == 0)
+                    expected[(g, direction)] = remote[r]
+        assert sent == expected
