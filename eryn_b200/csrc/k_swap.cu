@@ -273,8 +273,10 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   unsigned long long it = p.iter;   // (not a ?: of the two: with a __grid_constant__ parameter block nvcc merges the
   // arms into ONE global load whose address may then point into parameter space)
   if (p.iter_dev) it = ld_volatile_u64(p.iter_dev);
-  if (blockIdx.x == 0 && tid == 0) {
-    // the next move kernel may start its draws while this pass still runs: it keys them by iter_next
+  if (adapt_cta && tid == 0) {
+    // the next move kernel may start its draws while this pass still runs: it keys them by iter_next.  The adapt CTA
+    // does it (it has nothing else to do yet): on a chain CTA the fence would delay that CTA's chains — and, in a
+    // sharded pass, its share of the publish — by a microsecond, and every rank waits for the slowest chain.
     *reinterpret_cast<volatile unsigned long long*>(&ctrl->iter_next) = it + 1ull;
     fence_acq_rel_gpu();
   }
@@ -400,6 +402,21 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     for (int r = lane; r < T; r += CL) ll[r] = p.logl_in[(size_t)r * W + pos[r]];
   }
   __syncthreads();
+  // sharded: the rows most likely to leave this rank as mail (my top rung's walker if the swap above it is accepted, my
+  // bottom rung's walker if it gets carried down) are requested now, one element per lane, so that their L2 latency runs
+  // under the cascade; needs the LD+1 units of a mail to fit the lanes of the chain
+  const bool mail_pre = SHARDED && p.mail_in && valid && LD + 1 <= CL;
+  double mail_up = 0.0, mail_dn = 0.0;
+  if (mail_pre && lane <= LD) {
+    if (p.t_hi < T) {
+      const size_t sslot = (size_t)(p.t_hi - 1 - p.t_lo) * W + pos[p.t_hi - 1];
+      mail_up = lane < LD ? p.coords_src[p.rank][sslot * LD + lane] : p.logp_src[p.rank][sslot];
+    }
+    if (p.t_lo >= 1) {
+      const size_t sslot = (size_t)pos[p.t_lo];
+      mail_dn = lane < LD ? p.coords_src[p.rank][sslot * LD + lane] : p.logp_src[p.rank][sslot];
+    }
+  }
   EB_MARK(18);
   // ---- the cascade, hot -> cold (tempering.py:515-559 restricted to this chain).
   // The carried log-likelihood is always an ORIGINAL value ll[j]: the walker that starts on rung j is tested at rungs
@@ -516,6 +533,51 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   }
 
   EB_MARK(19);
+  // ---- sharded: rows that change rank leave first, as mail pushed by the rank that owns the source rung (every rank has
+  //      resolved the whole chain, so sender and receiver agree without talking): a one-way NVLink trip that runs under
+  //      the count publication and the local row copies, instead of the round trip of a pull.  A mail is LD+1
+  //      self-validating units (row, then logp) in the receiver's mailbox, slot [direction][chain]; per chain and rank at
+  //      most one walker arrives from below (into rung t_lo, when the swap at t_lo is accepted) and at most one from above
+  //      (the carried walker, where it settles).  The lanes of the chain share the units of a mail (coalesced loads and
+  //      peer stores); the two usual source rows were requested before the cascade (mail_up / mail_dn), so sending them
+  //      costs stores only.  This is the head of the longest dependence between ranks (my publish -> the peer's cascade
+  //      -> its mail -> my rows), which is why it comes before the counts.
+  if (SHARDED && p.mail_in && valid) {
+    const int MU = LD + 1;
+    const uint32_t tag = (uint32_t)(it + 1ull);
+    // up: the walker of my top rung moves up to rung t_hi
+    if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {
+      const int sr = p.t_hi - 1;
+      int gd = p.rank;
+      while (gd + 1 < p.world && p.t_hi >= p.temp_begin[gd + 1]) ++gd;
+      const size_t sslot = (size_t)(sr - p.t_lo) * W + pos[sr];
+      uint4* box = p.mail_dst[gd] + ((size_t)0 * W + chain) * MU;
+      for (int e = lane; e < MU; e += CL) {
+        const double v = mail_pre ? mail_up : e < LD ? p.coords_src[p.rank][sslot * LD + e] : p.logp_src[p.rank][sslot];
+        st_volatile_u4(box + e, make_uint4((uint32_t)__double2loint(v), tag, (uint32_t)__double2hiint(v), tag));
+      }
+    }
+    // down: the walker carried across my lower boundary, if it started on one of my rungs
+    if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) {
+      int o = p.t_lo;
+      while (o + 1 < T && sel_bit(sel_lo, sel_hi, o + 1)) ++o;      // rung the carried walker started on
+      if (o < p.t_hi) {
+        int d = p.t_lo - 1;
+        while (d >= 1 && sel_bit(sel_lo, sel_hi, d)) --d;           // rung it settles on
+        int gd = 0;
+        while (gd + 1 < p.world && d >= p.temp_begin[gd + 1]) ++gd;
+        const size_t sslot = (size_t)(o - p.t_lo) * W + pos[o];
+        uint4* box = p.mail_dst[gd] + ((size_t)1 * W + chain) * MU;
+        for (int e = lane; e < MU; e += CL) {
+          const double v = (mail_pre && o == p.t_lo) ? mail_dn
+                           : e < LD ? p.coords_src[p.rank][sslot * LD + e] : p.logp_src[p.rank][sslot];
+          st_volatile_u4(box + e, make_uint4((uint32_t)__double2loint(v), tag, (uint32_t)__double2hiint(v), tag));
+        }
+      }
+    }
+  }
+  EB_MARK(31);
+
   // ---- swap counts: swaps_accepted[r-1] counts accepted swaps at rung r (:542): ballot over the chains of the warp,
   //      shared-memory atomics over the block, global atomics over the grid
   {
@@ -559,48 +621,6 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   // ---- move the rows that changed rung (do_swaps_indexing, tempering.py:351-482): every lane gathers the source rows
   //      of its rungs, the lanes of the chain synchronise (all reads before any write), then write
   if (EB_DBG_SKIP(1)) return;
-  // ---- sharded: rows that change rank leave first (right after the counts, which the adapt CTA waits for), as mail pushed by the rank that
-  //      owns the source rung (every rank has resolved the whole chain, so sender and receiver agree without talking):
-  //      a one-way NVLink trip that runs under the local row copies, instead of the round
-  //      trip of a pull.  A mail is LD+1 self-validating units (row, then logp) in the receiver's mailbox, slot
-  //      [direction][chain]; per chain and rank at most one walker arrives from below (into rung t_lo, when the swap at
-  //      t_lo is accepted) and at most one from above (the carried walker, where it settles).  The lanes of the chain
-  //      share the units of a mail (coalesced loads and peer stores).
-  if (SHARDED && p.mail_in && valid) {
-    const int MU = LD + 1;
-    const uint32_t tag = (uint32_t)(it + 1ull);
-    // up: the walker of my top rung moves up to rung t_hi
-    if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {
-      const int sr = p.t_hi - 1;
-      int gd = p.rank;
-      while (gd + 1 < p.world && p.t_hi >= p.temp_begin[gd + 1]) ++gd;
-      const size_t sslot = (size_t)(sr - p.t_lo) * W + pos[sr];
-      uint4* box = p.mail_dst[gd] + ((size_t)0 * W + chain) * MU;
-      for (int e = lane; e < MU; e += CL) {
-        const double v = e < LD ? p.coords_src[p.rank][sslot * LD + e] : p.logp_src[p.rank][sslot];
-        st_volatile_u4(box + e, make_uint4((uint32_t)__double2loint(v), tag, (uint32_t)__double2hiint(v), tag));
-      }
-    }
-    // down: the walker carried across my lower boundary, if it started on one of my rungs
-    if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) {
-      int o = p.t_lo;
-      while (o + 1 < T && sel_bit(sel_lo, sel_hi, o + 1)) ++o;      // rung the carried walker started on
-      if (o < p.t_hi) {
-        int d = p.t_lo - 1;
-        while (d >= 1 && sel_bit(sel_lo, sel_hi, d)) --d;           // rung it settles on
-        int gd = 0;
-        while (gd + 1 < p.world && d >= p.temp_begin[gd + 1]) ++gd;
-        const size_t sslot = (size_t)(o - p.t_lo) * W + pos[o];
-        uint4* box = p.mail_dst[gd] + ((size_t)1 * W + chain) * MU;
-        for (int e = lane; e < MU; e += CL) {
-          const double v = e < LD ? p.coords_src[p.rank][sslot * LD + e] : p.logp_src[p.rank][sslot];
-          st_volatile_u4(box + e, make_uint4((uint32_t)__double2loint(v), tag, (uint32_t)__double2hiint(v), tag));
-        }
-      }
-    }
-  }
-
-  EB_MARK(31);
   if (!SHARDED) {
     if (RR > 0) {
       constexpr int RRX = RR > 0 ? RR : 1;

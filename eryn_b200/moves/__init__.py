@@ -1,3 +1,4 @@
+from .combine import CombineMove
 from .distgen import DistributionGenerate
 from .gaussian import GaussianMove
 from .group import GroupStretchMove
@@ -6,5 +7,5 @@ from .move import Move
 from .stretch import StretchMove
 from .tempering import TemperatureControl, make_ladder
 
-__all__ = ["Move", "StretchMove", "GaussianMove", "GroupStretchMove", "ReversibleJumpMove", "DistributionGenerateRJ", "DistributionGenerate",
+__all__ = ["Move", "CombineMove", "StretchMove", "GaussianMove", "GroupStretchMove", "ReversibleJumpMove", "DistributionGenerateRJ", "DistributionGenerate",
            "TemperatureControl", "make_ladder"]

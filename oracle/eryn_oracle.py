@@ -516,12 +516,26 @@ class OracleSampler:
         return state
 
     def iterate(self, state):
+        """one sampler iteration (ensemble.py:965-985): choose a move, propose; a {"kind": "combine", "moves": [...]}
+        move runs its sub-moves in order, each with its own tempering tail (combine.py:99-135), and returns the accept
+        COUNT of every walker"""
+        mi = self.streams.move_choice(self.iteration, self.weights)
+        move = self.moves[mi]
+        self.last_move = mi
+        if move["kind"] == "combine":
+            accepted = None
+            for sub in move["moves"]:
+                acc = self._propose(state, sub)
+                accepted = acc.astype(np.int64) if accepted is None else accepted + acc
+            return accepted
+        return self._propose(state, move)
+
+    def _propose(self, state, move):
+        """move.propose(model, state): proposal + Metropolis step + temper_comps; ticks the iteration counter that keys
+        the counter-based streams (the device ticks it in the swap pass)"""
         T, W, L, D = state.coords.shape
         it = self.iteration
         st = self.streams
-        mi = st.move_choice(it, self.weights)
-        move = self.moves[mi]
-        self.last_move = mi
         accepted = np.zeros((T, W), dtype=bool)
         if move["kind"] == "stretch":
             lists = st.split_lists(it, T, W)

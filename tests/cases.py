@@ -36,6 +36,9 @@ CASES = {
                          weights=[0.5, 0.5], periods=np.array([2 * np.pi, 2 * np.pi, 0.0])),
     "distgen_mix": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                         moves=[dict(kind="stretch", a=2.0), dict(kind="distgen")], weights=[0.5, 0.5]),
+    "combine_sg": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                       moves=[dict(kind="combine", moves=[dict(kind="stretch", a=2.0),
+                                                          dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.25)))])]),
     "noadapt_noperm": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                            moves=[dict(kind="stretch", a=2.0)], adaptive=False, permute=False),
 }
@@ -45,6 +48,8 @@ def load(name):
     g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     T, W = int(g["ntemps"]), int(g["nwalkers"])
     g["accepted"] = np.unpackbits(g["accepted"], axis=-1)[..., :W].astype(bool)
+    if "acc_count" in g:  # combined moves: accept COUNT of every walker per iteration
+        g["accepted"] = g["acc_count"].astype(np.int64)
     return g
 
 

@@ -48,7 +48,7 @@ import warnings  # noqa: E402
 
 warnings.filterwarnings("ignore")
 from eryn.ensemble import EnsembleSampler  # noqa: E402
-from eryn.moves import DistributionGenerate, GaussianMove, StretchMove  # noqa: E402
+from eryn.moves import CombineMove, DistributionGenerate, GaussianMove, StretchMove  # noqa: E402
 from eryn.prior import ProbDistContainer, uniform_dist  # noqa: E402
 from eryn.state import State  # noqa: E402
 
@@ -92,6 +92,13 @@ def run_case(name, seed, ndim, nwalkers, ntemps, nits, like, like_args, vectoriz
     rec = dict(coords=[], logl=[], logp=[], accepted=[], swaps=[], betas=[], move=[])
     prev_acc = [np.zeros((T, nwalkers)) for _ in sampler.moves]
     prev_np = [0 for _ in sampler.moves]
+
+    def nprop(mv):  # a CombineMove counts proposals in its sub-moves only (combine.py:126)
+        return sum(m.num_proposals for m in mv.moves) if isinstance(mv, CombineMove) else mv.num_proposals
+
+    def acc_of(mv):  # the sub-moves hold the counters (the reference's own CombineMove.accepted getter reads an attribute
+        # its setter never creates, combine.py:35,44-48)
+        return np.sum([m.accepted for m in mv.moves], axis=0) if isinstance(mv, CombineMove) else mv.accepted
     state0 = State(x0[:, :, None, :].copy())
     first = True
     for state in sampler.sample(state0, iterations=nits, store=False, skip_initial_state_check=True):
@@ -100,12 +107,13 @@ def run_case(name, seed, ndim, nwalkers, ntemps, nits, like, like_args, vectoriz
         which = None
         acc = None
         for k, mv in enumerate(sampler.moves):
-            if mv.num_proposals != prev_np[k]:
+            if nprop(mv) != prev_np[k]:
                 which = k
-                acc = mv.accepted - prev_acc[k]
-                prev_acc[k] = mv.accepted.copy()
-                prev_np[k] = mv.num_proposals
+                acc = acc_of(mv) - prev_acc[k]
+                prev_acc[k] = acc_of(mv).copy()
+                prev_np[k] = nprop(mv)
         rec["move"].append(which)
+        rec.setdefault("acc_count", []).append(acc.astype(np.uint8))
         rec["accepted"].append(acc.astype(bool))
         rec["coords"].append(state.branches_coords["model_0"].copy())
         rec["logl"].append(state.log_like.copy())
@@ -126,6 +134,8 @@ def run_case(name, seed, ndim, nwalkers, ntemps, nits, like, like_args, vectoriz
         swaps=np.stack(rec["swaps"]), betas=np.stack(rec["betas"]),
         move=np.asarray(rec["move"], dtype=np.int64),
     )
+    if np.stack(rec["acc_count"]).max() > 1:  # combined moves: several proposals per walker and iteration
+        out["acc_count"] = np.stack(rec["acc_count"])
     # initial logl/logp the sampler computed
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(f"{name}: T={T} W={nwalkers} d={ndim} its={nits}  coords.sum={out['coords'][-1].sum():.15e} "
@@ -146,6 +156,11 @@ if __name__ == "__main__":
         run_case("distgen_mix", 33, 3, 24, 3, 40, ll_gauss_vec, [np.zeros(3), np.eye(3)], True, -2.0, 2.0,
                  moves_factory=lambda: [(StretchMove(), 0.5),
                                         (DistributionGenerate({"model_0": run_case.priors}), 0.5)])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "combine":
+        # CombineMove (combine.py): a stretch move then a Gaussian move per iteration, each with its own tempering tail
+        run_case("combine_sg", 57, 3, 24, 3, 30, ll_gauss_vec, [np.zeros(3), np.eye(3)], True, -5.0, 5.0,
+                 moves_factory=lambda: [(CombineMove([StretchMove(), GaussianMove({"model_0": 0.25})]), 1.0)])
         sys.exit(0)
     run_case("c1_kat1", 42, 5, 32, None, 100, ll_single, [np.zeros(5), np.eye(5)], False, -5.0, 5.0)
     run_case("pt_kat2", 42, 3, 16, 4, 50, ll_single, [np.zeros(3), np.eye(3)], False, -5.0, 5.0)

@@ -28,11 +28,21 @@ def dev_like(olike):
     return lk.GaussianMixtureLikelihood(olike.mus, olike.sigmas, olike.weights)
 
 
+def _nprop(mv):  # a CombineMove counts proposals in its sub-moves (combine.py:126)
+    return sum(m.num_proposals for m in mv.moves) if hasattr(mv, "moves") else mv.num_proposals
+
+
+def _acc(mv):  # CombineMove.accepted is the list of its sub-moves' counters (combine.py:32-41)
+    return np.sum(mv.accepted, axis=0) if hasattr(mv, "moves") else mv.accepted
+
+
 def dev_moves(moves, priors=None):
-    from eryn_b200.moves import DistributionGenerate, GaussianMove, StretchMove
+    from eryn_b200.moves import CombineMove, DistributionGenerate, GaussianMove, StretchMove
     out = []
     for m in moves:
-        if m["kind"] == "stretch":
+        if m["kind"] == "combine":
+            out.append(CombineMove(dev_moves(m["moves"], priors)))
+        elif m["kind"] == "stretch":
             out.append(StretchMove(a=m.get("a", 2.0)))
         elif m["kind"] == "distgen":
             out.append(DistributionGenerate({"model_0": priors}))
@@ -75,10 +85,10 @@ def test_replay_matches_reference_golden(name):
     for it, state in enumerate(sampler.sample(x0, iterations=int(g["nits"]), store=False)):
         which, acc = None, None
         for k, mv in enumerate(sampler.moves):
-            if mv.num_proposals != prev_n[k]:
-                a = mv.accepted
-                which, acc = k, (a - prev[k]).astype(bool)
-                prev[k], prev_n[k] = a.copy(), mv.num_proposals
+            if _nprop(mv) != prev_n[k]:
+                a = _acc(mv)
+                which, acc = k, (a - prev[k]).astype(g["accepted"].dtype)  # masks; accept counts for combined moves
+                prev[k], prev_n[k] = a.copy(), _nprop(mv)
         assert which == g["move"][it], f"move choice differs at iteration {it}"
         assert np.array_equal(acc, g["accepted"][it]), f"accept mask differs at iteration {it}"
         close(state.branches_coords["model_0"][:, :, 0, :], g["coords"][it], f"coords it {it}")
@@ -143,6 +153,9 @@ PHILOX_CASES = {
     "c4_slice": (8, 1024, 20, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 5, -10, 10),
     "distgen": (3, 64, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                 [dict(kind="stretch", a=2.0), dict(kind="distgen")], [0.5, 0.5], 12, -2, 2),
+    "combine": (3, 64, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                [dict(kind="combine", moves=[dict(kind="stretch", a=2.0),
+                                             dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.4))])], [1.0], 10, -5, 5),
     "distgen_d8": (2, 128, 8, c2_like, [dict(kind="distgen")], [1.0], 6, -1, 1),
     "d13": (2, 64, 13, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 8, -5, 5),
     "d18": (2, 64, 18, lambda d: orc.RosenbrockLike(), [dict(kind="stretch", a=2.0)], [1.0], 8, -5, 5),
@@ -193,7 +206,7 @@ def run_philox_case(T, W, d, like_f, moves, weights, nits, lo, hi, seed=2024, un
         if not untempered and T > 1:
             assert np.array_equal(smp.temperature_control.swaps_accepted, osmp.swaps_accepted), f"swaps it {it}"
             close(state.betas, osmp.betas, f"betas it {it}")
-    total = sum(m.accepted.sum() for m in smp.moves)
+    total = sum(_acc(m).sum() for m in smp.moves)
     assert total > 0
     return smp, osmp
 

@@ -155,3 +155,25 @@ def test_band_walk_cascade_equals_sequential_ladder():
         lu = np.log(rng.rand(T)) * rng.choice([0.01, 1])
         dts = np.abs(rng.randn(T)) * rng.choice([0.0, 0.01, 1, 100])   # 0.0: the hot end, every swap accepted
         assert np.array_equal(_cascade_sequential(T, ll, lu, dts), _cascade_band_walk(T, ll, lu, dts))
+
+
+def test_combine_move_surface():
+    """CombineMove attribute plumbing (combine.py:32-97): counters, tempering object and periodic info go to the sub-moves"""
+    from eryn_b200.moves import CombineMove, GaussianMove, StretchMove, TemperatureControl
+    subs = [StretchMove(a=2.0), (GaussianMove({"model_0": 0.25}), 0.3)]   # weights in tuples are ignored (combine.py:16-18)
+    mv = CombineMove(subs)
+    assert [type(m).__name__ for m in mv.moves] == ["StretchMove", "GaussianMove"]
+    mv.accepted = np.zeros((2, 6))
+    assert len(mv.accepted) == 2 and all(a.shape == (2, 6) for a in mv.accepted)
+    tc = TemperatureControl(3, 6, ntemps=2)
+    mv.temperature_control = tc
+    assert all(m.temperature_control is tc for m in mv.moves) and mv.ntemps == 2
+    mv.periodic = {"model_0": {0: 1.0}}
+    assert all(m.periodic == {"model_0": {0: 1.0}} for m in mv.moves)
+    for m, n in zip(mv.moves, (4, 2)):
+        m.num_proposals = n
+        m.accepted = np.full((2, 6), 2.0)
+    np.testing.assert_allclose(mv.acceptance_fraction, np.full((2, 6), 0.75))   # mean of 2/4 and 2/2
+    assert len(mv.acceptance_fraction_separate) == 2
+    with pytest.raises(ValueError):
+        CombineMove([])
