@@ -58,3 +58,24 @@ def test_known_answers_appendix_c():
     assert np.array_equal(g["swaps"].sum(0), [228, 436, 677])
     np.testing.assert_allclose(g["betas"][-1], [1, 0.24676878824520287, 0.05735976075520548, 0.01115873741850507],
                                rtol=1e-14)
+
+
+def test_ladders_match_reference():
+    """tests/golden/ladders.npz (make_golden_ladders.py ran the unmodified reference): make_ladder on a grid of
+    (ndim, ntemps, Tmax) for the host mirror and the oracle, and adapt_temps driven by recorded swap counts."""
+    import os
+    from eryn_b200.moves import make_ladder
+    g = np.load(os.path.join(cases.GOLDEN, "ladders.npz"))
+    for k, (ndim, ntemps, tmax) in enumerate(g["grid"]):
+        ref = g[f"ladder_{k}"]
+        got = make_ladder(int(ndim), ntemps=int(ntemps), Tmax=None if tmax < 0 else float(tmax))
+        np.testing.assert_allclose(got, ref, rtol=1e-14, atol=0, err_msg=f"make_ladder({ndim}, {ntemps}, {tmax})")
+        if tmax < 0:
+            np.testing.assert_allclose(orc.make_ladder_default(int(ndim), int(ntemps)), ref, rtol=1e-14, atol=0)
+    for k in range(3):
+        T, W, lag, t0 = g[f"adapt_{k}_cfg"]
+        betas = g[f"adapt_{k}_betas0"].copy()
+        for step, counts in enumerate(g[f"adapt_{k}_counts"]):
+            betas = orc.adapt_temps(betas, counts.astype(float), int(W), step, adaptation_lag=lag, adaptation_time=t0)
+            np.testing.assert_allclose(betas, g[f"adapt_{k}_hist"][step], rtol=1e-13, atol=0,
+                                       err_msg=f"adapt_temps cfg {k} step {step}")
