@@ -218,11 +218,13 @@ def run_gpu(args):
                                                f"weak scaling: 16 temperatures x 4096 walkers per GPU",
                                    comm={"fused": "logl all-gather as NVLink peer stores + iteration flags inside the swap kernel "
                                                   "(no separate publish launch, no NCCL on the data path)",
+                                         "split": "EXPERIMENTAL chain-split pass: every rank resolves 1/N of the chains, two one-way "
+                                                  "NVLink hops of self-validating units (k_swap_split.cu)",
                                          "p2p": "publish kernel: NVLink peer stores + flag words, no NCCL on the data path",
                                          "nccl": "NCCL all_gather of logl + NVLink peer row pulls"}[res["comm"]],
                                    l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
                                    step=("one iteration = 2 stretch launches + 1 sharded publish/swap/adapt kernel, chained by "
-                                         "programmatic dependent launch" if res["comm"] == "fused" else
+                                         "programmatic dependent launch" if res["comm"] in ("fused", "split") else
                                          "one iteration = move kernel + publish kernel + sharded swap/adapt kernel")
                                         + (" (CUDA graph replay)" if res["graph"] else "")),
                        clocks=res["clocks"], e2e=dict(unit=UNIT, **res["e2e"]), gpu_launches=res["launches"],
@@ -441,7 +443,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--comm", default="fused", choices=["fused", "p2p", "nccl"], help="multi-GPU logl exchange (N > 1)")
+    ap.add_argument("--comm", default="fused", choices=["fused", "split", "p2p", "nccl"], help="multi-GPU logl exchange (N > 1)")
     ap.add_argument("--profile", action="store_true", help="shorten the CPU-baseline leg (for runs under ncu)")
     a = ap.parse_args()
     if a.warmup < 3:

@@ -86,6 +86,14 @@ class eb_shard(C.Structure):
                 ("mail_peer", vp * EB_MAX_RANKS), ("mail_in", vp)]
 
 
+class eb_split(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ntemps_total", C.c_int32), ("_pad", C.c_int32),
+                ("temp_begin", C.c_int32 * (EB_MAX_RANKS + 1)),
+                ("coords_cur", vp), ("logl_cur", vp), ("logp_cur", vp), ("betas_all", vp),
+                ("llc_peer", vp * EB_MAX_RANKS), ("llc_in", vp), ("bits_peer", vp * EB_MAX_RANKS), ("bits_in", vp),
+                ("cnt_peer", vp * EB_MAX_RANKS), ("cnt_in", vp), ("mail_peer", vp * EB_MAX_RANKS), ("mail_in", vp)]
+
+
 class eb_publish(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ntemps_total", C.c_int32), ("nwalkers", C.c_int32),
                 ("temp_begin", C.c_int32 * (EB_MAX_RANKS + 1)),
@@ -139,6 +147,7 @@ SYMBOLS = {
     "eb_pt_swap": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_pt_swap_sharded": (C.c_int, [P(eb_shard), P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_publish_logl": (C.c_int, [P(eb_publish), vp, vp]),
+    "eb_pt_swap_split": (C.c_int, [P(eb_split), P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_dev_malloc": (C.c_int, [C.c_size_t, P(vp)]),
     "eb_dev_free": (C.c_int, [vp]),
     "eb_ipc_export": (C.c_int, [vp, vp]),
@@ -160,7 +169,8 @@ SYMBOLS = {
 }
 
 STRUCTS = [eb_state, eb_prior, eb_like, eb_stretch_rng, eb_gauss_rng, eb_swap_rng, eb_ctrl, eb_adapt, eb_host_job,
-           eb_shard, eb_publish, eb_mb_layout, eb_mb_state, eb_pulse_data, eb_mb_friends, eb_mb_group_rng, eb_mb_rj_rng]
+           eb_shard, eb_publish, eb_mb_layout, eb_mb_state, eb_pulse_data, eb_mb_friends, eb_mb_group_rng, eb_mb_rj_rng,
+           eb_split]
 
 _lib = None
 
@@ -183,7 +193,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.eb_abi_version() != 4:
+    if lib.eb_abi_version() != 5:
         raise ErynB200Error("liberyn_b200.so ABI version mismatch; rebuild")
     for i, st in enumerate(STRUCTS):
         if lib.eb_struct_size(i) != C.sizeof(st):

@@ -19,7 +19,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "liberyn_b200.so")
 # (source, extra defines, object name): the two move kernels are compiled once per likelihood kind so the template
 # instantiations build in parallel
-SOURCES = [("abi_core.cu", [], "abi_core.o"), ("k_swap.cu", [], "k_swap.o"), ("k_shard.cu", [], "k_shard.o"), ("k_rj.cu", [], "k_rj.o"),
+SOURCES = [("abi_core.cu", [], "abi_core.o"), ("k_swap.cu", [], "k_swap.o"), ("k_shard.cu", [], "k_shard.o"), ("k_swap_split.cu", [], "k_swap_split.o"), ("k_rj.cu", [], "k_rj.o"),
            ("host_job.cu", [], "host_job.o")]
 for _k in range(3):
     SOURCES.append(("k_stretch.cu", [f"-DEB_ONLY_LIKE={_k}"], f"k_stretch_{_k}.o"))

@@ -145,6 +145,7 @@ size_t eb_struct_size(int which) {
     case 14: return sizeof(eb_mb_friends);
     case 15: return sizeof(eb_mb_group_rng);
     case 16: return sizeof(eb_mb_rj_rng);
+    case 17: return sizeof(eb_split);
     default: return 0;
   }
 }

@@ -85,6 +85,14 @@ class ArenaLayout(object):
         self.logl_ll = [take(T * self.W * 16) for _ in range(2)]
         # row mail: [direction][walker chain][L*D + 1] units per parity (eb_shard.mail_peer / mail_in)
         self.mail = [take(2 * self.W * (self.L * self.D + 1) * 16) for _ in range(2)]
+        # chain-split pass (comm="split", eb_split; EXPERIMENTAL): units per parity — logl of the chains this rank resolves
+        # [T][ceil(W / world)], accept bits of every chain [W][2], partial swap counts [world][T], row mail with logl
+        world = len(temp_begin) - 1
+        self.Wr = (self.W + world - 1) // world
+        self.llc = [take(T * self.Wr * 16) for _ in range(2)]
+        self.bits = [take(self.W * 2 * 16) for _ in range(2)]
+        self.cnt = [take(world * T * 16) for _ in range(2)]
+        self.mail2 = [take(2 * self.W * (self.L * self.D + 2) * 16) for _ in range(2)]
         self.total = o
 
 
@@ -135,8 +143,8 @@ class ShardedRun(object):
         import torch.distributed as dist
         from . import _lib
         from .device import DeviceState
-        if comm not in ("fused", "p2p", "nccl"):
-            raise ValueError("comm must be 'fused', 'p2p' or 'nccl'")
+        if comm not in ("fused", "split", "p2p", "nccl"):
+            raise ValueError("comm must be 'fused', 'split', 'p2p' or 'nccl'")
         if ctx.rng != "philox":
             raise ValueError("temperature-sharded runs use the philox streams (replay mode is single-GPU)")
         self.ctx, self.group, self.comm = ctx, group, comm
@@ -214,6 +222,24 @@ class ShardedRun(object):
             pb.logl_local = self.base + lay.logl[p]
             self._shard.append(sh)
             self._pub.append(pb)
+        self._split = []
+        if comm == "split":  # EXPERIMENTAL: every rank resolves 1/world of the chains (csrc/k_swap_split.cu)
+            for p in range(2):
+                sp = _lib.eb_split()
+                sp.rank, sp.world, sp.ntemps_total = self.rank, self.world, self.T
+                for g in range(self.world + 1):
+                    sp.temp_begin[g] = self.temp_begin[g]
+                sp.coords_cur = self.base + lay.coords[p]
+                sp.logl_cur = self.base + lay.logl[p]
+                sp.logp_cur = self.base + lay.logp[p]
+                sp.betas_all = self.base + lay.betas_all
+                sp.llc_in, sp.bits_in = self.base + lay.llc[p], self.base + lay.bits[p]
+                sp.cnt_in, sp.mail_in = self.base + lay.cnt[p], self.base + lay.mail2[p]
+                for g in range(self.world):
+                    lg = self.layouts[g]
+                    sp.llc_peer[g], sp.bits_peer[g] = self.bases[g] + lg.llc[p], self.bases[g] + lg.bits[p]
+                    sp.cnt_peer[g], sp.mail_peer[g] = self.bases[g] + lg.cnt[p], self.bases[g] + lg.mail2[p]
+                self._split.append(sp)
         ctx.write_ctrl(iter=0)  # the flag words count publish CTAs since iteration 0
         torch.cuda.synchronize(dev)
         dist.barrier(group)  # every arena is mapped and zeroed (flags = 0) before anyone publishes
@@ -272,9 +298,14 @@ class ShardedRun(object):
             ad = _lib.eb_adapt(int(adapt["adaptive"]), int(adapt["stop_adaptation"]), float(adapt["adaptation_lag"]),
                                float(adapt["adaptation_time"]))
         dst = self.states[1 - p].c_struct()
-        _lib.check(self.lib.eb_pt_swap_sharded(C.byref(self._shard[p]), C.byref(dst), C.byref(r),
-                                               C.byref(ad) if ad is not None else None,
-                                               C.c_void_p(ctx.ctrl.data_ptr()), ctx.stream()), "eb_pt_swap_sharded")
+        if self.comm == "split":
+            _lib.check(self.lib.eb_pt_swap_split(C.byref(self._split[p]), C.byref(dst), C.byref(r),
+                                                 C.byref(ad) if ad is not None else None,
+                                                 C.c_void_p(ctx.ctrl.data_ptr()), ctx.stream()), "eb_pt_swap_split")
+        else:
+            _lib.check(self.lib.eb_pt_swap_sharded(C.byref(self._shard[p]), C.byref(dst), C.byref(r),
+                                                   C.byref(ad) if ad is not None else None,
+                                                   C.c_void_p(ctx.ctrl.data_ptr()), ctx.stream()), "eb_pt_swap_sharded")
         ctx.launches += 1
         self.parity = 1 - p
         return self.states[self.parity]

@@ -32,7 +32,7 @@ extern "C" {
 #define EB_API
 #endif
 
-#define EB_ABI_VERSION 4
+#define EB_ABI_VERSION 5
 #define EB_MAX_TEMPS 128
 #define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
 #define EB_MAX_RANKS 16 /* GPUs of one temperature-sharded run */
@@ -183,7 +183,7 @@ EB_API size_t eb_ctrl_size(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 eb_state, 1 eb_prior, 2 eb_like,
  * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job, 9 eb_shard,
  * 10 eb_publish, 11 eb_mb_layout, 12 eb_mb_state, 13 eb_pulse_data, 14 eb_mb_friends, 15 eb_mb_group_rng,
- * 16 eb_mb_rj_rng */
+ * 16 eb_mb_rj_rng, 17 eb_split */
 EB_API size_t eb_struct_size(int which);
 
 /* ---- probability evaluation:  EnsembleSampler.compute_log_prior (ensemble.py:1127) and
@@ -260,6 +260,31 @@ typedef struct {
 } eb_shard;
 EB_API int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rng* rng,
                        const eb_adapt* adapt, eb_ctrl* ctrl, void* stream);
+
+/* ---- EXPERIMENTAL (not yet run on a GPU): the sharded pass with the CHAINS split over the ranks.  Rank h
+ *      resolves the chains c with c % world == h: (A) every rank sends logl[r][sigma_r(c)] of its own rungs r to the
+ *      resolver of c (`llc`, [T][ceil(W/world)] 16-byte self-validating units as in eb_shard.pub_ll), (B) the resolver
+ *      runs the cascade and sends the accept bits of the chain to every rank (`bits`, [W][2] units), (C) every rank moves
+ *      its rows — rows that change rank as mail pushed by the source rank (`mail`, [2][W][nleaves*ndim + 2] units: row,
+ *      logp, logl) — and (D) the partial swap counts are exchanged (`cnt`, [world][T] units) and the ladder adapted
+ *      identically everywhere.  Two one-way NVLink hops, per-rank work and traffic independent of the number of ranks.
+ *      All exchange buffers alternate with the iteration parity and must be zero when ctrl->iter is 0.  The grid
+ *      (nwalkers/8 + 1 CTAs) must be resident at once (EB_ERR_UNSUPPORTED otherwise).  Philox mode only. */
+typedef struct {
+  int32_t rank, world;
+  int32_t ntemps_total, _pad;
+  int32_t temp_begin[EB_MAX_RANKS + 1];
+  const double* coords_cur;                /* this rank's CURRENT buffers [T_rank][W][L][D], [T_rank][W], [T_rank][W] */
+  const double* logl_cur;
+  const double* logp_cur;
+  double* betas_all;                       /* [T] local copy of the full ladder; adapted in place */
+  void* llc_peer[EB_MAX_RANKS];  const void* llc_in;
+  void* bits_peer[EB_MAX_RANKS]; const void* bits_in;
+  void* cnt_peer[EB_MAX_RANKS];  const void* cnt_in;
+  void* mail_peer[EB_MAX_RANKS]; const void* mail_in;
+} eb_split;
+EB_API int eb_pt_swap_split(const eb_split* sp, const eb_state* dst, const eb_swap_rng* rng,
+                     const eb_adapt* adapt, eb_ctrl* ctrl, void* stream);
 
 typedef struct {
   int32_t rank, world;

@@ -52,12 +52,26 @@ def _oracle(T, W, d, nit, seed, mix):
 
 @pytest.mark.parametrize("comm,T,W,mix", [("fused", 4, 256, 0), ("p2p", 4, 256, 0), ("nccl", 4, 256, 0), ("fused", 5, 99, 1),
                                                 ("fused", 16, 4096, 0), ("p2p", 16, 4096, 0), ("fused", 72, 64, 0),
-                                                ("fused", 128, 48, 0), ("fused", 32, 16384, 0)])
+                                                ("fused", 128, 48, 0), ("fused", 32, 16384, 0),
+                                                ("split", 4, 256, 0), ("split", 5, 99, 1), ("split", 16, 4096, 0),
+                                                ("split", 128, 48, 0)])
 def test_sharded_run_matches_unsharded_oracle(tmp_path, comm, T, W, mix):
-    if _ngpu() < 2:
-        pytest.skip("needs 2 GPUs")
+    _run_and_compare(tmp_path, comm, T, W, mix, nproc=2)
+
+
+@pytest.mark.parametrize("T,W", [(4, 256), (16, 4096), (128, 48)])
+def test_split_pass_single_rank_matches_oracle(tmp_path, T, W):
+    """the chain-split pass with world = 1 (one GPU is enough): positions, units, cascade, counts exchange with itself"""
+    _run_and_compare(tmp_path, "split", T, W, 0, nproc=1)
+
+
+def _run_and_compare(tmp_path, comm, T, W, mix, nproc):
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    if comm == "split" and os.environ.get("EB_TEST_SPLIT") != "1":
+        pytest.skip("the chain-split pass (k_swap_split.cu) has not run on a GPU yet: EB_TEST_SPLIT=1 enables its cases")
     d, nit, seed = 8, 6, 4242
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--out",
            str(tmp_path), "--comm", comm, "--ntemps", str(T), "--nwalkers", str(W), "--ndim", str(d), "--nit", str(nit), "--seed",
            str(seed), "--mix", str(mix)]
