@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
       st_volatile_u4(p.llc_dst[h] + (size_t)(p.t_lo + k) * p.Wr + cslot, unit_of(v, tag));
     }
   }
+  __syncwarp();               // pos[] of the chain is read by all lanes below
   pdl_launch_dependents();    // the next move kernel may begin its draws
 
   // ---- B: the resolver of the chain: log u, the T units, the cascade, the accept bits to every rank
