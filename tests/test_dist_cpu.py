@@ -194,3 +194,100 @@ def test_row_mail_routing_senders_and_receivers_agree():
                     assert (remote[r] == r - 1) == (direction == 0)
                     expected[(g, direction)] = remote[r]
         assert sent == expected
+
+
+def test_chain_split_pass_protocol_model():
+    """NumPy model of the chain-split sharded pass (csrc/k_swap_split.cu, phases A-D) with the kernel's buffer indexing:
+    every rank sends logl of its own rungs to the chain's resolver (slot [r][c // world] on rank c % world), the resolver
+    cascades and broadcasts accept bits, rows move locally or as mail (coords, logp, logl), partial counts are summed
+    over the ranks.  The gathered result must equal the sequential reference ladder (oracle temperature_swaps) on the
+    unsharded state — counts included — for uneven partitions and walkers carried across several ranks."""
+    from eryn_b200.dist import owner_of, temperature_partition
+    from oracle import philox_np as px
+    rng = np.random.RandomState(5)
+    for world, T, W, hot in ((2, 5, 12, 0.0), (3, 9, 10, 1.0), (4, 16, 9, 30.0), (8, 24, 16, 100.0), (1, 6, 8, 1.0)):
+        D, it, seed = 3, 7, 99
+        tb = temperature_partition(T, world)
+        coords = rng.randn(T, W, 1, D)
+        logl = rng.randn(T, W) * 3.0
+        logp = rng.randn(T, W)
+        betas = np.sort(rng.rand(T))[::-1].copy()
+        betas[0] = 1.0
+        betas[T // 2:] *= 1.0 / (1.0 + hot)  # a hot end where nearly every swap is accepted (long runs)
+        sig = [px.swap_perm(it, seed, r, W) for r in range(T)]
+        us = [None] + [px.swap_uniforms(it, seed, i, W) for i in range(1, T)]
+        ref = orc.OState(coords.copy(), logl=logl.copy(), logp=logp.copy())
+        ref_counts = orc.temperature_swaps(ref, betas, [None] + sig[1:], [None] + sig[:-1], us)
+
+        Wr = (W + world - 1) // world
+        llc = [np.full((T, Wr), np.nan) for _ in range(world)]
+        bits = [np.zeros((W, T), bool) for _ in range(world)]
+        got_bits = [np.zeros(W, bool) for _ in range(world)]
+        partial = np.zeros((world, T - 1), int)
+        mail = [[dict(), dict()] for _ in range(world)]  # [rank][direction][chain] -> (row, logp, logl)
+        # A: own rungs of every chain -> the chain's resolver
+        for g in range(world):
+            for r in range(tb[g], tb[g + 1]):
+                for c in range(W):
+                    llc[c % world][r, c // world] = logl[r, sig[r][c]]
+        # B: resolvers
+        for h in range(world):
+            for c in range(h, W, world):
+                ll = llc[h][:, c // world]
+                assert not np.isnan(ll).any()
+                sel = np.zeros(T, bool)
+                carry = ll[T - 1]
+                for i in range(T - 1, 0, -1):
+                    if (betas[i - 1] - betas[i]) * (carry - ll[i - 1]) > np.log(us[i][c]):
+                        sel[i] = True
+                    else:
+                        carry = ll[i - 1]
+                partial[h] += sel[1:]
+                for g in range(world):
+                    bits[g][c] = sel
+                    got_bits[g][c] = True
+        assert all(b.all() for b in got_bits)
+        # C: mail pushes, then rows
+        new = [dict(coords=np.full((tb[g + 1] - tb[g], W, 1, D), np.nan), logl=np.full((tb[g + 1] - tb[g], W), np.nan),
+                    logp=np.full((tb[g + 1] - tb[g], W), np.nan)) for g in range(world)]
+        for g in range(world):
+            t_lo, t_hi = tb[g], tb[g + 1]
+            for c in range(W):
+                sel = bits[g][c]
+                if t_hi < T and sel[t_hi]:
+                    s = t_hi - 1
+                    mail[owner_of(tb, t_hi)][0][c] = (coords[s, sig[s][c]], logp[s, sig[s][c]], logl[s, sig[s][c]])
+                if t_lo >= 1 and sel[t_lo]:
+                    o = t_lo
+                    while o + 1 < T and sel[o + 1]:
+                        o += 1
+                    if o < t_hi:
+                        d = t_lo - 1
+                        while d >= 1 and sel[d]:
+                            d -= 1
+                        mail[owner_of(tb, d)][1][c] = (coords[o, sig[o][c]], logp[o, sig[o][c]], logl[o, sig[o][c]])
+        for g in range(world):
+            t_lo, t_hi = tb[g], tb[g + 1]
+            for c in range(W):
+                sel = np.append(bits[g][c], False)
+                dest = [-1, -1]
+                if t_lo >= 1 and sel[t_lo]:
+                    dest[0] = t_lo
+                if t_hi < T and sel[t_hi]:
+                    d = t_hi - 1
+                    while d >= 1 and sel[d]:
+                        d -= 1
+                    if d >= t_lo:
+                        dest[1] = d
+                for r in range(t_lo, t_hi):
+                    s = _swap_source(sel, r, T)
+                    if t_lo <= s < t_hi:
+                        row = (coords[s, sig[s][c]], logp[s, sig[s][c]], logl[s, sig[s][c]])
+                    else:
+                        row = mail[g][dest.index(r)][c]
+                    new[g]["coords"][r - t_lo, sig[r][c]], new[g]["logp"][r - t_lo, sig[r][c]] = row[0], row[1]
+                    new[g]["logl"][r - t_lo, sig[r][c]] = row[2]
+        out = {k: np.concatenate([n[k] for n in new], axis=0) for k in ("coords", "logl", "logp")}
+        assert np.array_equal(out["coords"], ref.coords) and np.array_equal(out["logl"], ref.logl)
+        assert np.array_equal(out["logp"], ref.logp)
+        assert np.array_equal(partial.sum(0), ref_counts.astype(int))  # D: the counts exchange
