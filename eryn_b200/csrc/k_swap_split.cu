@@ -2,9 +2,11 @@
 //
 // K3s: the swap pass of a temperature-sharded run with the CHAINS split over the ranks.
 //
-// EXPERIMENTAL — written at the end of round 1 after the GPU budget of the round was spent: it compiles and its host
-// plumbing is covered by the CPU tests, but it has NOT run on a GPU yet.  `comm="fused"` (k_swap.cu, validated) stays the
-// default; this pass is selected with `comm="split"` and its 2-GPU parity cases are skipped unless EB_TEST_SPLIT=1.
+// EXPERIMENTAL — written at the end of round 1 when the GPU budget of the round was nearly spent.  Its one GPU run so far
+// (single rank, 16 temps x 4096 walkers, 6 iterations, tests/test_mgpu.py::test_split_pass_single_rank_matches_oracle)
+// reproduced the oracle's coords / logl / logp; the ladder differed by 2e-6 because the adaptation clock reached
+// thread 0 only — fixed since (s_time), not re-run.  No multi-rank run yet.  `comm="fused"` (k_swap.cu, validated) stays
+// the default; this pass is selected with `comm="split"` and its GPU cases are skipped unless EB_TEST_SPLIT=1.
 //
 // Why: the fused sharded pass (k_swap.cu) resolves the WHOLE ladder on every rank — every rank draws positions and
 // log u for all T rungs of all W chains and receives the logl of every other rank, so its cost grows with the number
@@ -136,7 +138,8 @@ __device__ __forceinline__ void adapt_cta_work(const Args& p, int nreal, unsigne
   const int tid = threadIdx.x, T = p.T, W = p.c.W;
   const uint32_t tag = (uint32_t)(it + 1ull);
   __shared__ int s_ok;
-  if (tid == 0) s_ok = 1;
+  __shared__ long long s_time;    // TemperatureControl.time, read by thread 0 at kernel start
+  if (tid == 0) { s_ok = 1; s_time = time_t0; }
   for (int r = tid; r < T; r += blockDim.x) s_cnt[r] = 0;
   __syncthreads();
   constexpr int NS = 8;           // arrival / count slots (k_swap.cu:swap_slots for long ladders)
@@ -172,7 +175,7 @@ __device__ __forceinline__ void adapt_cta_work(const Args& p, int nreal, unsigne
     s_cnt[r] = tot;
   }
   __syncthreads();
-  const long long time_now = time_t0;
+  const long long time_now = s_time;
   if (p.adapt_on && p.adaptive && T > 1) {                                     // tempering.py:632-633
     if (p.stop_adaptation < 0 || time_now < (long long)p.stop_adaptation) {   // :590
       const double decay = p.lag / ((double)time_now + p.lag);                 // :571

@@ -261,7 +261,7 @@ typedef struct {
 EB_API int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rng* rng,
                        const eb_adapt* adapt, eb_ctrl* ctrl, void* stream);
 
-/* ---- EXPERIMENTAL (not yet run on a GPU): the sharded pass with the CHAINS split over the ranks.  Rank h
+/* ---- EXPERIMENTAL (one single-rank GPU run so far): the sharded pass with the CHAINS split over the ranks.  Rank h
  *      resolves the chains c with c % world == h: (A) every rank sends logl[r][sigma_r(c)] of its own rungs r to the
  *      resolver of c (`llc`, [T][ceil(W/world)] 16-byte self-validating units as in eb_shard.pub_ll), (B) the resolver
  *      runs the cascade and sends the accept bits of the chain to every rank (`bits`, [W][2] units), (C) every rank moves

@@ -69,7 +69,7 @@ def _run_and_compare(tmp_path, comm, T, W, mix, nproc):
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
     if comm == "split" and os.environ.get("EB_TEST_SPLIT") != "1":
-        pytest.skip("the chain-split pass (k_swap_split.cu) has not run on a GPU yet: EB_TEST_SPLIT=1 enables its cases")
+        pytest.skip("the chain-split pass (k_swap_split.cu) is experimental (no multi-rank GPU run yet): EB_TEST_SPLIT=1 enables its cases")
     d, nit, seed = 8, 6, 4242
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--out",
