@@ -8,12 +8,18 @@ Metropolis test) + one parallel-tempering swap pass + ladder adaptation.  N=1 ru
 (16 temps x 4096 walkers x 8-d correlated Gaussian, StretchMove + PT).  Prints ONE JSON line on rank 0.
 
   value     device-resident throughput (state already in HBM), production (philox) mode, each step a
-            replay of the captured 2-kernel iteration graph, timed by its own CUDA-event pair with an
+            replay of the captured iteration graph, timed by its own CUDA-event pair with an
             L2 flush between steps (outside the pairs);
   e2e       the same step through the C-ABI entry with HOST buffers (eb_run_host): pinned host state ->
             H2D -> kernels -> D2H -> host state, every step;
-  roofline  the fused stretch half-step kernel: algorithmic bytes / CUDA-event duration vs measured HBM peak;
-  cpu_baseline  the NumPy oracle port of the reference path on this box's host cores, same workload.
+  roofline  the fused stretch step kernel: algorithmic bytes / CUDA-event duration vs measured HBM peak;
+            extra.roofline_swap: the swap pass; extra.roofline_c4: the stretch kernel on the HBM-sized config 4;
+  cpu_baseline  the NumPy oracle port of the reference path on this box's host cores, same workload;
+  extra.api the same workload through the public sampler API (EnsembleSampler.run_mcmc, thin_by=25, stored);
+  extra.c3 / extra.c4 / extra.c5   the other BASELINE configurations (one GPU);
+  N > 1     the ladder sharded by temperature, weak scaling of config 2 (16 temperatures x 4096 walkers per GPU);
+            extra.c4_strong = config 4 (32 temperatures fixed) sharded over the N GPUs; `parity` = a sharded chain
+            against the same chain on one GPU (the run exits non-zero on a mismatch).
 """
 import argparse
 import ctypes
@@ -65,6 +71,11 @@ def workload(name, ngpus=1):
     raise SystemExit(f"unknown workload {name}")
 
 
+def config_of(wl):
+    """the `config` object of the JSON line: the same for the GPU arm and the reference arm"""
+    return dict(workload=wl["label"], ntemps=wl["T"], nwalkers=wl["W"], ndim=wl["d"])
+
+
 def oracle_objects(wl):
     from oracle import eryn_oracle as orc
     k = wl["like"]
@@ -109,6 +120,41 @@ def run_cpu(wl, steps, warmup, budget_s=None):
     return wl["T"] * wl["W"] * done / dt, dt / done, done
 
 
+_POOL_LIKE = None
+
+
+def _pool_init(kind, params):
+    global _POOL_LIKE
+    from oracle import eryn_oracle as orc
+    _POOL_LIKE = orc.GaussianLike(*params) if kind == "gauss" else orc.RosenbrockLike() if kind == "rosen" \
+        else orc.GaussianMixtureLike(*params)
+
+
+def _pool_call(x):
+    return float(_POOL_LIKE(x[None, :])[0])
+
+
+def run_cpu_pool(wl, budget_s=20.0):
+    """The reference's only multi-core facility (ensemble.py:1474-1481): vectorize=False, the likelihood called once per
+    walker through multiprocessing.Pool(ncores).map.  Timed: the likelihood leg of ONE iteration (every walker evaluated
+    once) on a bounded number of walkers, on top of the vectorised rest of the iteration."""
+    import multiprocessing as mp
+    k = wl["like"]
+    ncores = os.cpu_count() or 1
+    x = initial_coords(wl).reshape(-1, wl["d"])
+    n = x.shape[0]
+    with mp.get_context("fork").Pool(ncores, initializer=_pool_init, initargs=(k[0], tuple(k[1:]))) as pool:
+        pool.map(_pool_call, list(x[:1024]))
+        t0 = time.perf_counter()
+        m = 0
+        chunk = 16384
+        while m < n and time.perf_counter() - t0 < budget_s:
+            pool.map(_pool_call, list(x[m:m + chunk]))
+            m += min(chunk, n - m)
+        dt = time.perf_counter() - t0
+    return m / dt, ncores, m
+
+
 def cpu_threads():
     """threads the NumPy port actually computes with: its work is elementwise / einsum-without-BLAS / fancy indexing,
     all single-threaded in NumPy (the BLAS pool, if any, stays idle on this path)"""
@@ -124,7 +170,7 @@ def blas_pool():
 
 
 # ------------------------------------------------------------------------------------------------------
-# clocks sampler (nvidia-smi fields via NVML) — runs during the timed region
+# clocks sampler (nvidia-smi fields via NVML) — runs during the timed region and a sustained replay of the same step
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
@@ -155,12 +201,13 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def summary(self):
         self.stop_flag = True
         med = float(np.median(self.samples)) if self.samples else None
-        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples),
+                    window="the timed steps plus >= 0.3 s of the same step replayed back to back")
 
 
 def measured_peak_gbs():
@@ -171,6 +218,207 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# one workload on one GPU: context, moves, one captured graph per move kind
+# ------------------------------------------------------------------------------------------------------
+class SingleGpu(object):
+    def __init__(self, wl, dev, seed=20261017):
+        import torch
+        from eryn_b200.device import DeviceContext
+        from eryn_b200.moves import GaussianMove, StretchMove, TemperatureControl
+        from eryn_b200.prior import ProbDistContainer, uniform_dist
+        from eryn_b200.state import State
+        self.torch, self.wl, self.dev = torch, wl, dev
+        T, W, d = wl["T"], wl["W"], wl["d"]
+        self.pri = ProbDistContainer({i: uniform_dist(wl["lo"], wl["hi"]) for i in range(d)})
+        self.ctx = DeviceContext(self.pri, device_like(wl), device=dev, rng="philox", seed=seed)
+        self.tc = TemperatureControl(d, W, ntemps=T)
+        self.tc.bind(self.ctx)
+        self.moves = []
+        for m in wl["moves"]:
+            mv = StretchMove(a=m["a"]) if m["kind"] == "stretch" else GaussianMove({"model_0": m["proposal"]["scale"] ** 2})
+            mv.temperature_control = self.tc
+            mv.bind(self.ctx)
+            mv.accepted = np.zeros((T, W))
+            self.moves.append(mv)
+        self.ds = self.ctx.upload(State(initial_coords(wl)), betas=self.tc.betas_dev)
+        self.ctx.eval_state(self.ds)
+        torch.cuda.synchronize()
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graphs = []
+        with torch.cuda.stream(self.stream):
+            for mv in self.moves:  # warm-up launches outside capture (module load, attribute setup)
+                mv.propose(None, self.ds)
+            torch.cuda.synchronize()
+            for mv in self.moves:
+                g = torch.cuda.CUDAGraph()
+                l0 = self.ctx.launches
+                with torch.cuda.graph(g, stream=self.stream):
+                    mv.propose(None, self.ds)
+                self.graphs.append((g, self.ctx.launches - l0))
+        torch.cuda.synchronize()
+        self.stretch = [m for m in self.moves if isinstance(m, StretchMove)]
+
+    def schedule(self, n):
+        w = np.asarray(self.wl["weights"], dtype=float)
+        return np.random.RandomState(7).choice(len(self.moves), p=w / w.sum(), size=n)
+
+    def timed_steps(self, steps, warmup, flush=None, clk=None):
+        """per-step CUDA-event pairs, L2 flushed between steps (outside the pairs); returns (total_ms, launches)"""
+        torch = self.torch
+        sched = self.schedule(warmup + steps)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        with torch.cuda.stream(self.stream):
+            for i in range(warmup):
+                self.graphs[sched[i]][0].replay()
+            torch.cuda.synchronize()
+            if clk is not None:
+                clk.start()
+            launches = 0
+            for i in range(steps):
+                if flush is not None:
+                    flush.fill_(i & 0xFF)  # L2 flush between timed iterations, outside the event pair
+                g, nl = self.graphs[sched[warmup + i]]
+                evs[i][0].record(self.stream)
+                g.replay()
+                evs[i][1].record(self.stream)
+                launches += nl
+            torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in evs)), launches
+
+    def resident_ms(self, steps, min_seconds=0.0):
+        """the same steps back to back without flush (state stays L2-resident, as in a real run)"""
+        torch = self.torch
+        sched = self.schedule(steps)
+        with torch.cuda.stream(self.stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            for i in range(steps):
+                self.graphs[sched[i]][0].replay()
+            e1.record(self.stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            if min_seconds > 0:  # sustained load for the clock sampler
+                n = int(min_seconds / max(ms * 1e-3, 1e-7))
+                for i in range(n):
+                    self.graphs[sched[i % steps]][0].replay()
+                torch.cuda.synchronize()
+        return ms
+
+    def graph_us(self, body, nrep):
+        """average duration of `body` (kernel launches) over nrep back-to-back repetitions inside one graph"""
+        torch = self.torch
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(self.stream):
+            body()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gk, stream=self.stream):
+                for _ in range(nrep):
+                    body()
+            gk.replay()
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(self.stream)
+            gk.replay()
+            k1.record(self.stream)
+            torch.cuda.synchronize()
+        return k0.elapsed_time(k1) * 1e3 / nrep
+
+    def stretch_us(self, nrep):
+        cnt = self.stretch[0]._count_buffer(self.ctx, self.wl["T"], self.wl["W"])
+        return self.graph_us(lambda: self.ctx.stretch_step(self.ds, 2.0, accepted_count=cnt), nrep)
+
+    def swap_us(self, nrep):
+        return self.graph_us(lambda: self.tc.temper_comps(self.ds), nrep)
+
+    def moved_fraction(self):
+        """fraction of walkers whose row changes rung in one swap pass (measured on the current state)"""
+        torch = self.torch
+        before = self.ds.logl.clone()
+        with torch.cuda.stream(self.stream):
+            self.tc.temper_comps(self.ds)
+            torch.cuda.synchronize()
+        return float((self.ds.logl != before).double().mean().item())
+
+
+def roofline_entry(kernel, alg_bytes, us, peak, peak_src, traffic=None, **extra):
+    a = alg_bytes / (us * 1e-6) / 1e9
+    out = dict(bound="hbm", kernel=kernel, achieved=round(a, 1), peak=peak, unit="GB/s", frac=round(a / peak, 4),
+               traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=int(alg_bytes), avg_launch_us=round(us, 3))
+    out.update(extra)
+    return out
+
+
+def bench_api(wl, dev, nsteps=40, thin_by=25, store=True):
+    """the public sampler API: EnsembleSampler.run_mcmc(x0, nsteps, thin_by) in production mode, stored steps included"""
+    import torch
+    from eryn_b200 import EnsembleSampler
+    from eryn_b200.moves import GaussianMove, StretchMove
+    from eryn_b200.prior import ProbDistContainer, uniform_dist
+    T, W, d = wl["T"], wl["W"], wl["d"]
+    np.random.seed(11)
+    pri = ProbDistContainer({i: uniform_dist(wl["lo"], wl["hi"]) for i in range(d)})
+    moves = [(StretchMove(a=m["a"]) if m["kind"] == "stretch" else GaussianMove({"model_0": m["proposal"]["scale"] ** 2}), w)
+             for m, w in zip(wl["moves"], wl["weights"])]
+    smp = EnsembleSampler(W, d, device_like(wl), pri, tempering_kwargs=dict(ntemps=T), moves=moves, rng="philox",
+                          seed=20261017, device=dev)
+    x0 = initial_coords(wl)[:, :, 0, :]
+    smp.run_mcmc(x0, 3, thin_by=thin_by, store=store)  # warm-up: first launches, graph capture
+    torch.cuda.synchronize()
+    l0 = smp.ctx.launches
+    t0 = time.perf_counter()
+    smp.run_mcmc(None, nsteps, thin_by=thin_by, store=store)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    nit = nsteps * thin_by
+    return dict(value=T * W * nit / dt, ms_per_step=dt / nit * 1e3, iterations=nit, thin_by=thin_by, store=store,
+                stored_steps=int(smp.backend.iteration), launches_per_iteration=round((smp.ctx.launches - l0) / nit, 3),
+                api="EnsembleSampler.run_mcmc(None, %d, thin_by=%d, store=%s): wall clock around the call + a final "
+                    "synchronize; CUDA-graph replay between yields, stored steps through the staging ring" % (nsteps, thin_by, store))
+
+
+# ---- config 5: reversible jump + group stretch over two branches (tests/test_eryn.py:38-92, :416-427, :813-907) -----
+C5_GINJ = np.array([[3.3, -0.2, 0.1], [2.6, -0.1, 0.1], [3.4, 0.0, 0.1], [2.9, 0.3, 0.1]])
+
+
+def bench_c5(dev, iters=40, nt=500):
+    import torch
+    from eryn_b200 import EnsembleSampler
+    from eryn_b200.moves import GroupStretchMove
+    from eryn_b200.multibranch import PulseLikelihood
+    from eryn_b200.prior import uniform_dist
+    from eryn_b200.state import State
+    T, W, L, nfriends = 8, 2048, 10, 16
+    t = np.linspace(-1, 1, nt)
+    y = C5_GINJ[:, 0:1].T @ np.exp(-((t[None, :] - C5_GINJ[:, 1:2]) ** 2) / (2 * C5_GINJ[:, 2:3] ** 2))
+    y = y[0] + 2.0 * np.random.RandomState(0).randn(nt)
+    bounds = {"gauss": ([2.5, t.min(), 0.01], [3.5, t.max(), 0.21]), "sine": ([0.5, 1.0, 0.0], [1.5, 20.0, 2 * np.pi])}
+    priors = {n: {i: uniform_dist(lo[i], hi[i]) for i in range(3)} for n, (lo, hi) in bounds.items()}
+    r = np.random.RandomState(11)
+    coords, inds = {}, {}
+    for n, (lo, hi) in bounds.items():
+        coords[n] = r.uniform(np.asarray(lo), np.asarray(hi), size=(T, W, L, 3))
+        inds[n] = r.rand(T, W, L) < 0.4
+        inds[n][:, :, 0] = True
+    np.random.seed(3)
+    smp = EnsembleSampler(W, {"gauss": 3, "sine": 3}, PulseLikelihood(t, y, 2.0, {"gauss": "gauss", "sine": "sine"}), priors,
+                          tempering_kwargs=dict(ntemps=T), nbranches=2, branch_names=["gauss", "sine"],
+                          nleaves_max={"gauss": L, "sine": L}, nleaves_min={"gauss": 0, "sine": 0},
+                          moves=GroupStretchMove(nfriends=nfriends, n_iter_update=100), rj_moves=True, rng="philox", seed=1,
+                          device=dev)
+    st0 = State(coords, inds=inds)
+    smp.run_mcmc(st0, 0, burn=5)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    smp.run_mcmc(st0, 1, burn=iters - 1, thin_by=1)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / iters
+    return dict(value=T * W / dt, ms_per_step=dt * 1e3, iterations=iters,
+                workload=f"C5: {T} temps x {W} walkers, branches gauss + sine (3-d leaves, nleaves_max={L}), {nt}-point data, "
+                         f"GroupStretchMove(nfriends={nfriends}) + DistributionGenerateRJ birth/death, 2 swap passes per iteration",
+                api="EnsembleSampler.run_mcmc (burn + 1 stored step), wall clock")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -189,194 +437,99 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from eryn_b200 import _lib
-    from eryn_b200.device import DeviceContext
-    from eryn_b200.moves import StretchMove, GaussianMove, TemperatureControl
-    from eryn_b200.prior import ProbDistContainer, uniform_dist
-    from eryn_b200.state import State
 
     wl = workload(args.workload, world)
     T, W, d = wl["T"], wl["W"], wl["d"]
+    dev = torch.device("cuda", local)
+    peak, peak_src = measured_peak_gbs()
     if world > 1:
-        from eryn_b200.dist import run_sharded_bench
-        wl["device_like"] = device_like(wl)
-        wl["x0"] = initial_coords(wl)
-        res = run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=ClockSampler, comm=args.comm)
-        if rank == 0:
-            peak, peak_src = measured_peak_gbs()
-            roof = None
-            if res.get("k1_us"):
-                b = (24 * d + 41) * res["local_temps"] * W
-                a = b / (res["k1_us"] * 1e-6) / 1e9
-                roof = dict(bound="hbm", kernel="stretch_step_kernel (rank 0's temperatures, both launches of one step)",
-                            achieved=round(a, 1), peak=peak, unit="GB/s", frac=round(a / peak, 4), traffic=None,
-                            peak_source=peak_src, algorithmic_bytes_per_launch=b, avg_launch_us=round(res["k1_us"], 3))
-            out = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                       ms_per_step=res["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
-                       dtype="f64", data="synthetic",
-                       config=dict(workload=wl["label"], ntemps=T, nwalkers=W, ndim=d, rng="philox",
-                                   parallelism=f"temperature-sharded x{world} (temp_begin={res['temp_begin']}), "
-                                               f"weak scaling: 16 temperatures x 4096 walkers per GPU",
-                                   comm={"fused": "logl all-gather as NVLink peer stores + iteration flags inside the swap kernel "
-                                                  "(no separate publish launch, no NCCL on the data path)",
-                                         "split": "EXPERIMENTAL chain-split pass: every rank resolves 1/N of the chains, two one-way "
-                                                  "NVLink hops of self-validating units (k_swap_split.cu)",
-                                         "p2p": "publish kernel: NVLink peer stores + flag words, no NCCL on the data path",
-                                         "nccl": "NCCL all_gather of logl + NVLink peer row pulls"}[res["comm"]],
-                                   l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
-                                   step=("one iteration = 2 stretch launches + 1 sharded publish/swap/adapt kernel, chained by "
-                                         "programmatic dependent launch" if res["comm"] in ("fused", "split") else
-                                         "one iteration = move kernel + publish kernel + sharded swap/adapt kernel")
-                                        + (" (CUDA graph replay)" if res["graph"] else "")),
-                       clocks=res["clocks"], e2e=dict(unit=UNIT, **res["e2e"]), gpu_launches=res["launches"],
-                       roofline=roof, cpu_baseline=None,
-                       extra=dict(ms_per_step_resident_no_flush=res["resident_ms"],
-                                  value_resident_no_flush=T * W / (res["resident_ms"] * 1e-3),
-                                  betas_cold_hot=res["betas"], swaps_accepted_last=res["swaps"],
-                                  timing="per-step CUDA events on each rank, summed, MAX over ranks"))
-            print(json.dumps(out))
-        dist.barrier()
-        dist.destroy_process_group()
+        run_multi(args, wl, rank, world, local, dev, peak, peak_src)
         return
 
-    dev = torch.device("cuda", local)
-    pri = ProbDistContainer({i: uniform_dist(wl["lo"], wl["hi"]) for i in range(d)})
-    ctx = DeviceContext(pri, device_like(wl), device=dev, rng="philox", seed=20261017)
-    tc = TemperatureControl(d, W, ntemps=T)
-    tc.bind(ctx)
-    moves = []
-    for m in wl["moves"]:
-        mv = StretchMove(a=m["a"]) if m["kind"] == "stretch" else GaussianMove({"model_0": m["proposal"]["scale"] ** 2})
-        mv.temperature_control = tc
-        mv.bind(ctx)
-        mv.accepted = np.zeros((T, W))
-        moves.append(mv)
-    x0 = initial_coords(wl)
-    ds = ctx.upload(State(x0), betas=tc.betas_dev)
-    ctx.eval_state(ds)
-    torch.cuda.synchronize()
-
-    # host-side move schedule (the reference's per-iteration random.choice, ensemble.py:971)
-    sched_rng = np.random.RandomState(7)
-    nmoves = len(moves)
-
-    # ---- capture one iteration per move kind into a CUDA graph -------------------------------------------
-    stream = torch.cuda.Stream(device=dev)
-    graphs = []
-    with torch.cuda.stream(stream):
-        for mv in moves:  # warm-up launches outside capture (module load, attribute setup)
-            mv.propose(None, ds)
-        torch.cuda.synchronize()
-        for mv in moves:
-            g = torch.cuda.CUDAGraph()
-            l0 = ctx.launches
-            with torch.cuda.graph(g, stream=stream):
-                mv.propose(None, ds)
-            graphs.append((g, ctx.launches - l0))
-    torch.cuda.synchronize()
-
+    sg = SingleGpu(wl, dev)
+    ctx, tc = sg.ctx, sg.tc
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    schedule = sched_rng.choice(nmoves, p=np.asarray(wl["weights"]) / np.sum(wl["weights"]), size=args.warmup + args.steps)
-
     clk = ClockSampler(local)
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            graphs[schedule[i]][0].replay()
-        torch.cuda.synchronize()
-        clk.start()
-        launches = 0
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)  # L2 flush between timed iterations, outside the event pair
-            g, nl = graphs[schedule[args.warmup + i]]
-            evs[i][0].record(stream)
-            g.replay()
-            evs[i][1].record(stream)
-            launches += nl
-        torch.cuda.synchronize()
-        t_wall = time.perf_counter() - t_wall0
-        # the same K steps back to back without flush (state stays L2-resident, as in a real run)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(args.steps):
-            graphs[schedule[args.warmup + i]][0].replay()
-        e1.record(stream)
-        torch.cuda.synchronize()
-    clocks = clk.summary()
-    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
-    total_ms = float(step_ms.sum())
+    t_wall0 = time.perf_counter()
+    total_ms, launches = sg.timed_steps(args.steps, args.warmup, flush=flush, clk=clk)
+    t_wall = time.perf_counter() - t_wall0
     value = T * W * args.steps / (total_ms * 1e-3)
-    resident_ms = e0.elapsed_time(e1) / args.steps
+    resident_ms = sg.resident_ms(args.steps, min_seconds=0.0 if args.profile else 0.35)
+    clocks = clk.summary()
 
     # ---- roofline of the dominant kernel: the fused stretch step (two launches: red half, blue half) ------------------
-    def stretch_us(ctx_, ds_, cnt_, nrep):
-        gk = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(stream):
-            ctx_.stretch_step(ds_, 2.0, accepted_count=cnt_)
-            torch.cuda.synchronize()
-            with torch.cuda.graph(gk, stream=stream):
-                for r in range(nrep):
-                    ctx_.stretch_step(ds_, 2.0, accepted_count=cnt_)
-            gk.replay()
-            torch.cuda.synchronize()
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record(stream)
-            gk.replay()
-            k1.record(stream)
-            torch.cuda.synchronize()
-        return k0.elapsed_time(k1) * 1e3 / nrep
-
-    st_move = [m for m in moves if isinstance(m, StretchMove)][0]
-    cnt = st_move._count_buffer(ctx, T, W)
-    k_us = stretch_us(ctx, ds, cnt, 100)
-    D = d
-    alg_bytes = (24 * D + 41) * T * W  # 24*D+41 B per walker-update; one step updates all T*W walkers
-    peak, peak_src = measured_peak_gbs()
-    achieved = alg_bytes / (k_us * 1e-6) / 1e9
+    k_us = sg.stretch_us(100)
+    alg_bytes = (24 * d + 41) * T * W  # 24*D+41 B per walker-update; one step updates all T*W walkers
     traffic = None  # DRAM bytes per stretch step from the committed ncu --set full capture of this workload
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.workload]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[args.workload]
         traffic = tr["launches_per_step"] * (tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"])
     except Exception:
         pass
-    roofline = dict(bound="hbm", kernel="stretch_step_kernel (both red/blue launches of one step)", achieved=round(achieved, 1),
-                    peak=peak, unit="GB/s", frac=round(achieved / peak, 4), traffic=traffic, peak_source=peak_src,
-                    algorithmic_bytes_per_launch=alg_bytes, avg_launch_us=round(k_us, 3),
-                    note="per stretch step = 2 launches; state (4.7 MB at C2) is L2-resident across launches, so this is an "
-                         "algorithmic-bytes rate against the HBM peak, limited by launch/dependency latency at this size; "
-                         "extra.roofline_c4 is the same kernel on the HBM-sized config-4 working set")
-    # the same kernel where the working set exceeds what one launch can hide behind latency: BASELINE config 4 on one GPU
+    roofline = roofline_entry("stretch_step_kernel (both red/blue launches of one step)", alg_bytes, k_us, peak, peak_src, traffic,
+                              note="per stretch step = 2 launches; the state (4.7 MB at C2) is L2-resident across launches, so this "
+                                   "is an algorithmic-bytes rate against the HBM peak, limited by launch/dependency latency at this "
+                                   "size; extra.roofline_c4 is the same step on the HBM-sized config-4 working set")
+    # ---- the swap pass: 12 B per walker (logl read + slot bookkeeping) + (16 D + 34) B per walker whose row moves -------
+    roofline_swap = None
+    extra = {}
+    if not args.profile:
+        mf = sg.moved_fraction()
+        s_us = sg.swap_us(100)
+        sb = (12 + (16 * d + 34) * mf) * T * W
+        roofline_swap = roofline_entry("pt_swap_kernel (ladder + row moves + adaptation, one launch)", sb, s_us, peak, peak_src,
+                                       moved_fraction=round(mf, 4),
+                                       note="algorithmic bytes = 12 + (16 D + 34) x moved_fraction per walker; latency-bound at "
+                                            "this size (the ladder is a dependent chain over the rungs)")
+        # whole iteration against its algorithmic bytes (~ 40 D + 90 B per walker-update)
+        extra["roofline_iteration"] = roofline_entry("one iteration = stretch step + swap pass (graph replay, L2 flushed)",
+                                                     (40 * d + 90) * T * W, total_ms / args.steps * 1e3, peak, peak_src)
+
+    # ---- the other BASELINE configurations on this GPU ------------------------------------------------------------------
     roofline_c4 = None
     if not args.profile:
+        del sg.graphs
         wl4 = workload("c4")
-        pri4 = ProbDistContainer({i: uniform_dist(wl4["lo"], wl4["hi"]) for i in range(wl4["d"])})
-        ctx4 = DeviceContext(pri4, device_like(wl4), device=dev, rng="philox", seed=7)
-        tc4 = TemperatureControl(wl4["d"], wl4["W"], ntemps=wl4["T"])
-        tc4.bind(ctx4)
-        ds4 = ctx4.upload(State(initial_coords(wl4)), betas=tc4.betas_dev)
-        ctx4.eval_state(ds4)
-        cnt4 = torch.zeros((wl4["T"], wl4["W"]), dtype=torch.int32, device=dev)
-        k4_us = stretch_us(ctx4, ds4, cnt4, 20)
+        sg4 = SingleGpu(wl4, dev, seed=7)
+        k4_us = sg4.stretch_us(20)
         b4 = (24 * wl4["d"] + 41) * wl4["T"] * wl4["W"]
-        a4 = b4 / (k4_us * 1e-6) / 1e9
-        roofline_c4 = dict(workload=wl4["label"], kernel="stretch_step_kernel", achieved=round(a4, 1), peak=peak, unit="GB/s",
-                           frac=round(a4 / peak, 4), algorithmic_bytes_per_launch=b4, avg_launch_us=round(k4_us, 2),
-                           walker_updates_per_s=wl4["T"] * wl4["W"] / (k4_us * 1e-6))
-        del ds4, ctx4, cnt4
+        roofline_c4 = roofline_entry("stretch step (lane-split kernel, both launches)", b4, k4_us, peak, peak_src,
+                                     workload=wl4["label"], walker_updates_per_s=wl4["T"] * wl4["W"] / (k4_us * 1e-6))
+        tot4, _ = sg4.timed_steps(30, 5, flush=flush)
+        res4 = sg4.resident_ms(30)
+        n4 = wl4["T"] * wl4["W"]
+        extra["c4"] = dict(value=n4 * 30 / (tot4 * 1e-3), ms_per_step=tot4 / 30, ms_per_step_resident_no_flush=res4,
+                           swap_us=round(sg4.swap_us(20), 2), workload=wl4["label"],
+                           roofline_iteration=roofline_entry("one iteration = stretch step + swap pass", (40 * wl4["d"] + 90) * n4,
+                                                             tot4 / 30 * 1e3, peak, peak_src))
+        del sg4
+        wl3 = workload("c3")
+        sg3 = SingleGpu(wl3, dev, seed=9)
+        tot3, _ = sg3.timed_steps(100, 10, flush=flush)
+        extra["c3"] = dict(value=wl3["T"] * wl3["W"] * 100 / (tot3 * 1e-3), ms_per_step=tot3 / 100,
+                           ms_per_step_resident_no_flush=sg3.resident_ms(100), workload=wl3["label"])
+        del sg3
+        try:
+            extra["c5"] = bench_c5(dev)
+        except Exception as e:  # reported, never silently dropped
+            extra["c5"] = dict(error=f"{type(e).__name__}: {e}")
+        extra["api"] = bench_api(wl, dev, store=True)
+        extra["api_not_stored"] = bench_api(wl, dev, store=False)
 
     # ---- e2e: C-ABI call with HOST buffers, one iteration per call ------------------------------------------
     lib = _lib.load()
-    host = ctx.download(ds)
+    host = ctx.download(sg.ds)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_coords, h_logl, h_logp, h_betas = pin(host.branches_coords["model_0"]), pin(host.log_like), pin(host.log_prior), pin(host.betas)
-    lo, hi, _ = pri.arrays()
-    par = np.ascontiguousarray(device_like(wl).params())
+    lo, hi, _ = sg.pri.arrays()
+    lk = device_like(wl)
+    par = np.ascontiguousarray(lk.params())
+    schedule = sg.schedule(args.warmup + args.steps)
     h_sched = np.ascontiguousarray(schedule.astype(np.uint8))
     job = _lib.eb_host_job()
     job.ntemps, job.nwalkers, job.nleaves, job.ndim = T, W, 1, d
     job.coords_host, job.logl_host, job.logp_host, job.betas_host = [ctypes.c_void_p(t.data_ptr()) for t in (h_coords, h_logl, h_logp, h_betas)]
     job.prior_lo_host, job.prior_hi_host = ctypes.c_void_p(lo.ctypes.data), ctypes.c_void_p(hi.ctypes.data)
-    lk = device_like(wl)
     job.like_kind, job.like_ncomp, job.like_nparams = int(lk.kind), int(lk.ncomp), int(par.size)
     job.like_params_host = ctypes.c_void_p(par.ctypes.data) if par.size else None
     job.stretch_a, job.gauss_scale, job.seed, job.iter0 = 2.0, 0.1, 20261017, 0
@@ -394,7 +547,7 @@ def run_gpu(args):
     state_bytes = h_coords.numel() * 8 + h_logl.numel() * 8 + h_logp.numel() * 8 + h_betas.numel() * 8
     e2e = dict(value=T * W / e2e_s, unit=UNIT, h2d_bytes_per_step=int(state_bytes + par.size * 8 + 3 * d * 8 + 4120),
                d2h_bytes_per_step=int(state_bytes + 4120), ms_per_step=e2e_s * 1e3,
-               api="eb_run_host(job, niter=1): pinned host State -> H2D -> 2 kernels -> D2H, every step")
+               api="eb_run_host(job, niter=1): pinned host State -> H2D -> 3 kernels -> D2H, every step")
 
     # ---- CPU baseline (oracle port), bounded sample -------------------------------------------------------------
     cpu_v, cpu_s, cpu_n = run_cpu(wl, steps=10 ** 6, warmup=1, budget_s=0.5 if args.profile else 12.0)
@@ -402,18 +555,86 @@ def run_gpu(args):
                sample=f"{cpu_n} iterations of the same workload ({cpu_s * 1e3:.1f} ms/iteration), NumPy oracle port, "
                       f"os.cpu_count()={os.cpu_count()}, BLAS pool {blas_pool()} (idle: the path is single-threaded NumPy, like the reference)")
 
+    extra.update(ms_per_step_resident_no_flush=resident_ms, value_resident_no_flush=T * W / (resident_ms * 1e-3),
+                 roofline_c4=roofline_c4, roofline_swap=roofline_swap, wall_s_timed_region=t_wall,
+                 betas_cold_hot=[float(tc.betas[0]), float(tc.betas[-1])], swaps_accepted_last=tc.swaps_accepted.tolist()[:4],
+                 notes=dict(rng="philox (counter-based, in-kernel)",
+                            l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
+                            step="one iteration = stretch step (red launch + blue launch chained by programmatic dependent "
+                                 "launch) + 1 swap/adapt kernel (CUDA graph replay)"))
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-               dtype="f64", data="synthetic",
-               config=dict(workload=wl["label"], ntemps=T, nwalkers=W, ndim=d, rng="philox",
-                           l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
-                           step="one iteration = stretch step (red launch + blue launch chained by programmatic dependent launch) + 1 swap/adapt kernel (CUDA graph replay)"),
-               clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
-               extra=dict(ms_per_step_resident_no_flush=resident_ms,
-                          value_resident_no_flush=T * W / (resident_ms * 1e-3), roofline_c4=roofline_c4,
-                          wall_s_timed_region=t_wall, betas_cold_hot=[float(tc.betas[0]), float(tc.betas[-1])],
-                          swaps_accepted_last=tc.swaps_accepted.tolist()[:4]))
+               dtype="f64", data="synthetic", config=config_of(wl),
+               clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, extra=extra)
     print(json.dumps(out))
+
+
+def run_multi(args, wl, rank, world, local, dev, peak, peak_src):
+    """N > 1: the ladder sharded by temperature (eryn_b200/dist.py)"""
+    import torch
+    import torch.distributed as dist
+    from eryn_b200.dist import run_sharded_bench, sharded_parity_check
+    T, W, d = wl["T"], wl["W"], wl["d"]
+    wl["device_like"] = device_like(wl)
+    wl["x0"] = initial_coords(wl)
+    res = run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=ClockSampler, comm=args.comm, sustain_s=0.35)
+    # ---- BASELINE config 4 (32 temperatures, fixed) sharded over the same ranks: strong scaling -------------------------
+    wl4 = workload("c4")
+    c4 = None
+    if wl4["T"] >= world and not args.profile:
+        wl4["device_like"] = device_like(wl4)
+        wl4["x0"] = initial_coords(wl4)
+        a4 = argparse.Namespace(steps=min(args.steps, 50), warmup=max(3, min(args.warmup, 5)))
+        r4 = run_sharded_bench(a4, wl4, rank, world, local, comm=args.comm, with_e2e=False, with_k1=False)
+        one = None
+        if rank == 0:  # the same configuration on ONE GPU (rank 0's), same timing method
+            sg4 = SingleGpu(wl4, dev, seed=7)
+            flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+            tot4, _ = sg4.timed_steps(a4.steps, a4.warmup, flush=flush)
+            one = tot4 / a4.steps
+            del sg4, flush
+        dist.barrier()
+        if rank == 0:
+            c4 = dict(workload=wl4["label"], value=r4["value"], ms_per_step=r4["ms_per_step"],
+                      ms_per_step_resident_no_flush=r4["resident_ms"], ms_per_step_1gpu=one,
+                      speedup_vs_1gpu=one / r4["ms_per_step"], temps_per_gpu=wl4["T"] // world,
+                      scaling="strong: the configuration is fixed, its 32 temperatures are spread over the GPUs")
+    # ---- parity of the sharded path, in the same run ---------------------------------------------------------------------
+    parity = sharded_parity_check(rank, world, local, comm=args.comm)
+    if rank == 0:
+        roof = None
+        if res.get("k1_us"):
+            b = (24 * d + 41) * res["local_temps"] * W
+            roof = roofline_entry("stretch_step_kernel (rank 0's temperatures, both launches of one step)", b, res["k1_us"], peak,
+                                  peak_src)
+        comm_txt = {"fused": "every rank resolves the whole ladder: logl all-gather as NVLink peer stores of self-validating units "
+                             "inside the swap kernel, rows pushed as mail (no NCCL on the data path)",
+                    "split": "chain-split pass: every rank resolves 1/N of the chains; logl units to the resolver, accept bits to "
+                             "every rank, rows pushed as mail — three one-way NVLink hops of self-validating units inside ONE "
+                             "kernel (k_swap_split.cu), no NCCL on the data path",
+                    "p2p": "publish kernel: NVLink peer stores + flag words, no NCCL on the data path",
+                    "nccl": "NCCL all_gather of logl + NVLink peer row pulls"}[res["comm"]]
+        out = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=res["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                   dtype="f64", data="synthetic", config=config_of(wl),
+                   clocks=res["clocks"], e2e=dict(unit=UNIT, **res["e2e"]), gpu_launches=res["launches"],
+                   roofline=roof, cpu_baseline=None, parity=parity,
+                   extra=dict(ms_per_step_resident_no_flush=res["resident_ms"],
+                              value_resident_no_flush=T * W / (res["resident_ms"] * 1e-3), c4_strong=c4,
+                              betas_cold_hot=res["betas"], swaps_accepted_last=res["swaps"],
+                              timing="per-step CUDA events on each rank, summed, MAX over ranks",
+                              notes=dict(rng="philox (counter-based, in-kernel)",
+                                         parallelism=f"temperature-sharded x{world} (temp_begin={res['temp_begin']}), weak "
+                                                     f"scaling: 16 temperatures x 4096 walkers per GPU",
+                                         comm=comm_txt,
+                                         l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
+                                         step="one iteration = 2 stretch launches + 1 sharded swap/adapt kernel, chained by "
+                                              "programmatic dependent launch" + (" (CUDA graph replay)" if res["graph"] else ""))))
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        raise SystemExit("sharded parity check FAILED: " + json.dumps(parity))
 
 
 def run_reference(args):
@@ -427,13 +648,22 @@ def run_reference(args):
                sample=f"{n} iterations, {s * 1e3:.1f} ms/iteration, os.cpu_count()={os.cpu_count()}, BLAS pool {blas_pool()} "
                       f"(idle: the reference path is single-process, single-threaded NumPy; its only multi-core "
                       f"facility is pool.map over per-walker likelihood calls, slower than vectorising)")
+    extra = dict(rng="numpy MT19937 (reference order)")
+    if args.gpus <= 1:
+        try:  # the secondary baseline BASELINE.md §3 names: vectorize=False + multiprocessing.Pool (ensemble.py:1474-1481)
+            rate, ncores, m = run_cpu_pool(wl)
+            per_iter = wl["T"] * wl["W"] / rate
+            extra["pool_baseline"] = dict(
+                likelihood_calls_per_s=rate, cores=ncores, sample=f"{m} per-walker likelihood calls through Pool({ncores}).map",
+                value=wl["T"] * wl["W"] / (per_iter + s), unit=UNIT,
+                note="walker-updates/s of an iteration whose likelihood leg goes through the pool (one call per walker) and "
+                     "whose remaining legs take the vectorised port's time: slower than vectorize=True, as SURVEY.md §8d expects")
+        except Exception as e:
+            extra["pool_baseline"] = dict(error=f"{type(e).__name__}: {e}")
     print(json.dumps(dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=n,
                           warmup=args.warmup, ms_per_step=s * 1e3, higher_is_better=True, scaling="weak",
-                          vs_baseline=None, dtype="f64", data="synthetic",
-                          config=dict(workload=wl["label"], ntemps=wl["T"], nwalkers=wl["W"], ndim=wl["d"],
-                                      rng="numpy MT19937 (reference order)"),
-                          cpu_baseline=cpu,
-                          e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+                          vs_baseline=None, dtype="f64", data="synthetic", config=config_of(wl), cpu_baseline=cpu,
+                          e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), extra=extra)))
 
 
 if __name__ == "__main__":
@@ -443,8 +673,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--comm", default="fused", choices=["fused", "split", "p2p", "nccl"], help="multi-GPU logl exchange (N > 1)")
-    ap.add_argument("--profile", action="store_true", help="shorten the CPU-baseline leg (for runs under ncu)")
+    ap.add_argument("--comm", default="split", choices=["fused", "split", "p2p", "nccl"], help="multi-GPU swap pass (N > 1)")
+    ap.add_argument("--profile", action="store_true", help="shorten the CPU-baseline leg and skip the extras (for runs under ncu)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3

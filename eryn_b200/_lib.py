@@ -94,6 +94,15 @@ class eb_split(C.Structure):
                 ("cnt_peer", vp * EB_MAX_RANKS), ("cnt_in", vp), ("mail_peer", vp * EB_MAX_RANKS), ("mail_in", vp)]
 
 
+EB_STAGE_MAX_SEGMENTS = 16
+
+
+class eb_stage(C.Structure):
+    _fields_ = [("nseg", C.c_int32), ("mask_nleaves", C.c_int32), ("mask_ndim", C.c_int32), ("_pad", C.c_int32),
+                ("src", vp * EB_STAGE_MAX_SEGMENTS), ("nbytes", C.c_uint64 * EB_STAGE_MAX_SEGMENTS),
+                ("mask_inds", vp), ("fill", C.c_double), ("dst", vp), ("dst_bytes", C.c_uint64)]
+
+
 class eb_publish(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ntemps_total", C.c_int32), ("nwalkers", C.c_int32),
                 ("temp_begin", C.c_int32 * (EB_MAX_RANKS + 1)),
@@ -166,11 +175,12 @@ SYMBOLS = {
                                    vp, vp, vp]),
     "eb_box_log_prior": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, P(eb_prior), vp, vp]),
     "eb_run_host": (C.c_int, [P(eb_host_job), C.c_int32]),
+    "eb_stage_pack": (C.c_int, [P(eb_stage), vp]),
 }
 
 STRUCTS = [eb_state, eb_prior, eb_like, eb_stretch_rng, eb_gauss_rng, eb_swap_rng, eb_ctrl, eb_adapt, eb_host_job,
            eb_shard, eb_publish, eb_mb_layout, eb_mb_state, eb_pulse_data, eb_mb_friends, eb_mb_group_rng, eb_mb_rj_rng,
-           eb_split]
+           eb_split, eb_stage]
 
 _lib = None
 
@@ -193,7 +203,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.eb_abi_version() != 5:
+    if lib.eb_abi_version() != 6:
         raise ErynB200Error("liberyn_b200.so ABI version mismatch; rebuild")
     for i, st in enumerate(STRUCTS):
         if lib.eb_struct_size(i) != C.sizeof(st):

@@ -11,6 +11,11 @@ class Backend(object):
     def __init__(self, store_missing_leaves=np.nan):
         self.initialized = False
         self.store_missing_leaves = store_missing_leaves
+        self._flush_cb = None  # the sampler's deferred stores (staging.py): every getter drains them first
+
+    def _flush(self):
+        if self._flush_cb is not None:
+            self._flush_cb()
 
     def reset(self, nwalkers, ndims, nleaves_max=1, ntemps=1, branch_names=None, nbranches=1, rj=False,
               moves=None, key_order=None, **info):
@@ -76,7 +81,33 @@ class Backend(object):
         self.random_state = state.random_state
         self.iteration += 1
 
+    def save_arrays(self, coords, inds, log_like, log_prior, betas, accepted, rj_accepted=None, swaps_accepted=None,
+                    moves_accepted_fraction=None, random_state=None):
+        """save_step (backend.py:1014-1091) for a sample that arrives as plain arrays out of the staging ring: `coords`
+        already carry `store_missing_leaves` for inactive leaves (masked on the device, csrc/k_stage.cu)"""
+        it = self.iteration
+        if it >= len(self.log_like):
+            raise ValueError("backend is full: call grow() first")
+        for n in self.branch_names:
+            self.chain[n][it] = coords[n]
+            self.inds[n][it] = True if inds is None else inds[n]
+        self.log_like[it] = log_like
+        self.log_prior[it] = log_prior
+        if betas is not None:
+            self.betas[it] = betas
+        self.accepted += np.asarray(accepted).astype(int)
+        if swaps_accepted is not None:
+            self.swaps_accepted += np.asarray(swaps_accepted).astype(int)
+        if rj_accepted is not None and self.rj_accepted is not None:
+            self.rj_accepted += np.asarray(rj_accepted).astype(int)
+        if moves_accepted_fraction is not None:
+            for k, v in moves_accepted_fraction.items():
+                self.move_info[k]["acceptance_fraction"][:] = v
+        self.random_state = random_state
+        self.iteration += 1
+
     def _get(self, arr, thin=1, discard=0):
+        self._flush()
         return arr[discard + thin - 1:self.iteration:thin]
 
     def get_chain(self, thin=1, discard=0):
@@ -99,6 +130,7 @@ class Backend(object):
         return self._get(self.betas, thin, discard)
 
     def get_last_sample(self):
+        self._flush()
         if (not self.initialized) or self.iteration <= 0:
             raise AttributeError("you must run the sampler with 'store == True' before accessing the results")
         it = self.iteration - 1
@@ -109,4 +141,5 @@ class Backend(object):
 
     @property
     def acceptance_fraction(self):
+        self._flush()
         return self.accepted / float(max(self.iteration, 1))

@@ -61,9 +61,14 @@ __global__ void __launch_bounds__(BLOCK) box_prior_kernel(const double* __restri
   out[r] = tot;
 }
 
+// A stretch kernel launched as a programmatic dependent reads iter_next BEFORE its grid-dependency wait
+// (eb_stretch_rng.pdl_chain), so the writer publishes it like the swap pass does: store, device-scope fence, trigger.
 __global__ void advance_iter_kernel(eb_ctrl* ctrl) {
-  ctrl->iter += 1ull;
-  ctrl->iter_next = ctrl->iter;
+  const unsigned long long next = ctrl->iter + 1ull;
+  ctrl->iter = next;
+  *reinterpret_cast<volatile unsigned long long*>(&ctrl->iter_next) = next;
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 int fill_common(Common& c, const eb_state* st, const eb_prior* prior, const eb_like* like, bool need_fused) {
@@ -146,6 +151,7 @@ size_t eb_struct_size(int which) {
     case 15: return sizeof(eb_mb_group_rng);
     case 16: return sizeof(eb_mb_rj_rng);
     case 17: return sizeof(eb_split);
+    case 18: return sizeof(eb_stage);
     default: return 0;
   }
 }

@@ -181,7 +181,7 @@ __device__ __forceinline__ double np_mod(double a, double b) {
 
 int fill_common(Common& c, const eb_state* st, const eb_prior* prior, const eb_like* like, bool need_fused);
 
-static inline size_t smem_bytes(const Common& c, int extra = 0) {
+__host__ __device__ inline size_t smem_bytes(const Common& c, int extra = 0) {
   return sizeof(double) * (size_t)(PRIOR_ROWS * c.D + c.like_nparams + extra);
 }
 

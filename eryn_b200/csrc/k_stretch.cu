@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(STRETCH_HALF_THREADS, 2) stretch_step_kernel(c
   EB_MARK(7);
 }
 
+}  // namespace eb
+#include "stretch_lanes.cuh"
+namespace eb {
+
 #if !defined(EB_ONLY_LIKE) || EB_ONLY_LIKE == 0
 // split path: proposal only, thread per (t, k) of split s.  Generic in L and D (rows streamed).
 template <bool PHILOX>
@@ -327,9 +331,36 @@ static int launch_stretch_kernel(K kernel, const StretchArgs& a, size_t sb, cuda
   return EB_OK;
 }
 
+// Which kernel runs a per-half launch: 0 = one thread per walker with the row in registers (stretch_step_kernel: the
+// latency-optimised kernel of the shapes that do not fill the GPU), 2 / 4 = lanes per walker (stretch_lanes.cuh).  Below
+// about one wave of CTAs the step is bound by the latency of one walker's dependent chain, which the rounds of the
+// lane-split kernel lengthen; at HBM-sized shapes occupancy decides (numbers in profiles/README.md).  EB_K1_LPW = 1 / 2 / 4
+// forces a variant (tests, profiling); it is read at every launch.
+static int stretch_variant_for(const StretchArgs& a) {
+  const char* env = getenv("EB_K1_LPW");
+  const int forced = env ? atoi(env) : 0;
+  if (a.both || a.c.L != 1 || (a.c.LD != 8 && a.c.LD != 20)) return 0;
+  if (forced == 1) return 0;
+  if (forced == 2 && a.c.LD == 8) return 2;
+  if (forced == 2 || forced == 4) return 4;
+  static const long long min_walkers = getenv("EB_K1_LANES_MIN") ? atoll(getenv("EB_K1_LANES_MIN")) : 148ll * 2 * 256;
+  return (long long)a.c.T * a.Ns[a.split] >= min_walkers ? 4 : 0;
+}
+
 template <int DMAX, int LIKE, bool EXACT>
 static int launch_stretch(const StretchArgs& a, cudaStream_t s) {
   const size_t sb = smem_bytes(a.c);
+  if constexpr (EXACT) {
+    const int v = stretch_variant_for(a);
+    if (v == 4) {
+      if (a.philox) return launch_stretch_kernel(stretch_lanes_kernel<DMAX, 4, LIKE, true>, a, sb, s);
+      return launch_stretch_kernel(stretch_lanes_kernel<DMAX, 4, LIKE, false>, a, sb, s);
+    }
+    if constexpr (DMAX == 8) if (v == 2) {
+      if (a.philox) return launch_stretch_kernel(stretch_lanes_kernel<8, 2, LIKE, true>, a, sb, s);
+      return launch_stretch_kernel(stretch_lanes_kernel<8, 2, LIKE, false>, a, sb, s);
+    }
+  }
   if (a.philox) return launch_stretch_kernel(stretch_step_kernel<DMAX, LIKE, true, EXACT>, a, sb, s);
   return launch_stretch_kernel(stretch_step_kernel<DMAX, LIKE, false, EXACT>, a, sb, s);
 }

@@ -183,7 +183,15 @@ __device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, i
   __syncthreads();
   EB_MARK(28);
   if (!s_ok2) {
+    // A CTA never arrived (bounded wait ran out: a debugger / profiler replay, a wedged SM).  The error word is sticky —
+    // the host raises at its next look at the control block (DeviceContext.download, the sampler's yield points, the
+    // staged stores) — and the control block is left CONSISTENT: counts and arrivals zeroed, iter == iter_next, no
+    // adaptation from partial counts, so later kernels key their draws alike.
     if (tid == 0) atomicExch(&ctrl->error, EB_DEVERR_SWAP_TIMEOUT);
+    for (int e = tid; e < EB_SWAP_SLOTS * (EB_MAX_TEMPS); e += blockDim.x) ctrl->swaps_work[e / EB_MAX_TEMPS][e % EB_MAX_TEMPS] = 0;
+    if (tid < EB_SWAP_SLOTS) ctrl->arrive[tid] = 0u;
+    for (int r = tid; r < T - 1; r += blockDim.x) ctrl->swaps_accepted[r] = 0;
+    if (tid == 0) ctrl->iter = it + 1ull;
     return;
   }
   // fold the slot counts (independent loads first, the dependent bookkeeping stores last: the ladder is what the next

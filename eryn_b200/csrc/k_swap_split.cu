@@ -40,6 +40,7 @@ constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000ll;
 struct Args {
   Common c;                       // destination (alternate) buffers of this rank: rungs [t_lo, t_hi)
   int T, world, rank, t_lo, t_hi, permute, Wr;   // Wr = chains a rank resolves at most = ceil(W / world)
+  int gpc;                        // chain groups per CTA (shared-memory layout)
   int temp_begin[EB_MAX_RANKS + 1];
   const double* coords_cur; const double* logl_cur; const double* logp_cur;   // this rank's CURRENT buffers
   double* betas;                  // [T] local copy of the full ladder, adapted identically on every rank
@@ -53,17 +54,19 @@ struct Args {
 };
 
 struct Layout {  // byte offsets into dynamic shared memory
-  size_t betas, dts, ll, lu, keys, pos, cnt, band, rej, total;
+  size_t betas, dts, ll, lu, keys, pos, sel, cnt, band, rej, total;
 };
-__host__ __device__ inline Layout layout(int T, int nown) {
+// gpc = chain groups per CTA (the grid is capped at what is resident; a CTA loops over its groups phase by phase)
+__host__ __device__ inline Layout layout(int T, int nown, int gpc) {
   Layout s;
   size_t o = 0;
   s.betas = o; o += sizeof(double) * T;
   s.dts = o; o += sizeof(double) * T;
   s.ll = o; o += sizeof(double) * T * CPB;
   s.lu = o; o += sizeof(double) * T * CPB;
+  s.sel = o; o += sizeof(unsigned long long) * 2 * CPB * gpc;
   s.keys = o; o += sizeof(uint32_t) * FEISTEL_ROUNDS * nown;
-  s.pos = o; o += sizeof(int) * nown * CPB;
+  s.pos = o; o += sizeof(int) * nown * CPB * gpc;
   s.cnt = o; o += sizeof(int) * T;
   s.band = o; o += (size_t)T * CPB;
   s.rej = o; o += (size_t)T * CPB;
@@ -153,8 +156,12 @@ __device__ __forceinline__ void adapt_cta_work(const Args& p, int nreal, unsigne
     ctrl->arrive[tid] = 0u;
   }
   __syncthreads();
-  if (!s_ok) {
+  if (!s_ok) {   // sticky error, control block left consistent (k_swap.cu:pt_swap_adapt)
     if (tid == 0) atomicExch(&ctrl->error, EB_DEVERR_SWAP_TIMEOUT);
+    for (int e = tid; e < EB_SWAP_SLOTS * (EB_MAX_TEMPS); e += blockDim.x) ctrl->swaps_work[e / EB_MAX_TEMPS][e % EB_MAX_TEMPS] = 0;
+    if (tid < EB_SWAP_SLOTS) ctrl->arrive[tid] = 0u;
+    for (int r = tid; r < T - 1; r += blockDim.x) ctrl->swaps_accepted[r] = 0;
+    if (tid == 0) ctrl->iter = it + 1ull;
     return;
   }
   for (int e = tid; e < NS * (T - 1); e += blockDim.x) {
@@ -211,22 +218,152 @@ __device__ __forceinline__ void adapt_cta_work(const Args& p, int nreal, unsigne
   if (tid == 0) ctrl->iter = it + 1ull;
 }
 
+// One chain's share of phase A: positions on this rank's rungs, and the log-likelihood found there goes to the chain's
+// resolver.  `pos` (shared memory, nown ints) is kept for phases C1 / C2.
+__device__ __forceinline__ void phase_a(const Args& p, const uint32_t* s_keys, int chain, int lane, int nown, uint32_t tag,
+                                        int* pos) {
+  const int W = p.c.W;
+  const int h = chain % p.world;
+  const size_t cslot = (size_t)(chain / p.world);
+  for (int k = lane; k < nown; k += 32) {
+    int pz = chain;
+    if (p.permute) {
+      Feistel sig;
+      sig.init_from(s_keys + FEISTEL_ROUNDS * k, (uint32_t)W);
+      pz = (int)sig((uint32_t)chain);
+    }
+    pos[k] = pz;
+    const double v = p.logl_cur[(size_t)k * W + pz];
+    st_volatile_u4(p.llc_dst[h] + (size_t)(p.t_lo + k) * p.Wr + cslot, unit_of(v, tag));
+  }
+}
+
+// Phase B for one chain this rank resolves: log u, the T units, the cascade (walk over the carried walkers, k_swap.cu),
+// the accept bits to every rank, the accepted swaps into the CTA's partial counts.
+__device__ __forceinline__ void phase_b(const Args& p, const RngKey& key, int chain, int lane, uint32_t tag, bool& ok,
+                                        long long t_start, const double* s_dts, double* ll, double* lu,
+                                        unsigned char* sband, unsigned char* s_rej, int* s_cnt) {
+  const int T = p.T;
+  eb_ctrl* ctrl = p.ctrl;
+  for (int r = lane; r < T; r += 32) {
+    // one Philox block serves rungs r and r + 8 of a chain (k_swap.cu): counter (chain, (r & 7) | ((r >> 4) << 3)),
+    // word pair (r >> 3) & 1
+    const bool second = ((r >> 3) & 1) != 0;
+    const uint4 q = stream(key, TAG_SWAP_U, (uint32_t)chain, (uint32_t)((r & 7) | ((r >> 4) << 3)));
+    const double u = second ? u01_52(q.z, q.w) : u01_52(q.x, q.y);
+    lu[r] = log(u);                                                          // tempering.py:535
+    s_rej[r] = 0;
+  }
+  const uint4* src = p.llc_in + (size_t)(chain / p.world);
+  {   // the (up to four) units of a lane are requested together, then re-polled until their tags match
+    uint4 v[4];
+    bool pend[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) pend[m] = lane + 32 * m < T;
+    for (;;) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (pend[m]) v[m] = ld_volatile_u4(src + (size_t)(lane + 32 * m) * p.Wr);
+      bool any = false;
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (pend[m]) {
+          if ((v[m].y == tag && v[m].w == tag) || !ok) {
+            ll[lane + 32 * m] = unit_double(v[m]);
+            pend[m] = false;
+          } else {
+            any = true;
+          }
+        }
+      if (!any) break;
+      if (clock64() - t_start > SPIN_TIMEOUT_CYCLES) {
+        atomicExch(&ctrl->error, EB_DEVERR_PEER_TIMEOUT);
+        ok = false;
+      }
+    }
+  }
+  __syncwarp();
+  EB_MARK(18);
+  // band of walker j: bit a = test at rung j-a with x = ll[j] (tempering.py:538, :541), all walkers at once
+  for (int j = lane; j < T; j += 32) {
+    if (j >= 1) {
+      const double x = ll[j];
+      unsigned b = 0u;
+#pragma unroll
+      for (int a = 0; a < AGES; ++a) {
+        const int i = j - a;
+        if (i >= 1) b |= (unsigned)(s_dts[i] * (x - ll[i - 1]) > lu[i]) << a;
+      }
+      sband[j] = (unsigned char)b;
+    }
+  }
+  __syncwarp();
+  // walk over the carried walkers (k_swap.cu): mark the rung where each settles; long runs extended by a vote
+  int j = T - 1;
+  while (j >= 1) {
+    int run = __ffs((int)~(unsigned)sband[j]) - 1;
+    if (run == AGES) {
+      const double x = ll[j];
+      int base = j - AGES;
+      while (base >= 1) {
+        const int i = base - lane;
+        const bool f = i >= 1 && s_dts[i] * (x - ll[i - 1]) > lu[i];
+        const int n = __ffs((int)~__ballot_sync(0xffffffffu, f)) - 1;
+        if (n < 0) { run += 32; base -= 32; continue; }
+        run += n;
+        break;
+      }
+    }
+    s_rej[j - run] = 1;
+    j -= run + 1;
+  }
+  __syncwarp();
+  unsigned long long sel_lo = 0ull, sel_hi = 0ull;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    if (m * 32 < T) {
+      const int r = lane + m * 32;
+      const bool acc = r >= 1 && r < T && s_rej[r] == 0;
+      const unsigned v = __ballot_sync(0xffffffffu, acc);
+      if (acc) atomicAdd(&s_cnt[r - 1], 1);          // swaps_accepted[r-1] counts accepted swaps at rung r (:542)
+      if (m == 0) sel_lo |= (unsigned long long)v;
+      if (m == 1) sel_lo |= (unsigned long long)v << 32;
+      if (m == 2) sel_hi |= (unsigned long long)v;
+      if (m == 3) sel_hi |= (unsigned long long)v << 32;
+    }
+  }
+  if (lane < p.world) {
+    st_volatile_u4(p.bits_dst[lane] + 2 * (size_t)chain, unit_of((uint32_t)sel_lo, (uint32_t)(sel_lo >> 32), tag));
+    st_volatile_u4(p.bits_dst[lane] + 2 * (size_t)chain + 1, unit_of((uint32_t)sel_hi, (uint32_t)(sel_hi >> 32), tag));
+  }
+  __syncwarp();   // ll / lu / band of this warp are reused by its next chain
+}
+
+// The grid is sized to be RESIDENT (every CTA both feeds remote resolvers and waits for remote ones); a CTA owns the
+// chain groups blockIdx.x, blockIdx.x + nctas, ... and runs every phase over all of its groups before the next phase
+// starts, so no CTA ever waits for a CTA that has not been scheduled, on this rank or on a peer:
+//   A  (never waits)            all groups: own-rung positions, logl units to the resolvers
+//   B  (waits for A of peers)   the chains this rank resolves: cascade, accept bits to every rank, partial counts
+//      counts published for the adapt CTA (it exchanges them and adapts the ladder under C1 / C2)
+//   C1 (waits for B of peers)   all groups: accept bits, mail pushed, local rows copied into the alternate buffers
+//   C2 (waits for C1 of peers)  all groups: mail polled and stored
+// Groups are visited in the same order on every rank (same grid), so the waits of a phase are always served by an
+// earlier or equal step of the peer.
 __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_constant__ Args p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const Common& c = p.c;
   const int T = p.T, W = c.W, LD = c.LD;
   const int nown = p.t_hi - p.t_lo;
-  const Layout lay = layout(T, nown);
+  const Layout lay = layout(T, nown, p.gpc);
   double* s_betas = reinterpret_cast<double*>(smraw + lay.betas);
   double* s_dts = reinterpret_cast<double*>(smraw + lay.dts);
   uint32_t* s_keys = reinterpret_cast<uint32_t*>(smraw + lay.keys);
   int* s_cnt = reinterpret_cast<int*>(smraw + lay.cnt);
 
   const bool adapt_cta = blockIdx.x == gridDim.x - 1;   // one extra CTA without chains (D)
-  const int nreal = (int)gridDim.x - 1;
+  const int nctas = (int)gridDim.x - 1;
+  const int ngroups = (W + CPB - 1) / CPB;
   const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
-  const int chain = blockIdx.x * CPB + g;
-  const bool valid = !adapt_cta && chain < W;            // uniform over the warp
   eb_ctrl* ctrl = p.ctrl;
   long long time_now = 0;
   if (adapt_cta && tid == 0) time_now = *reinterpret_cast<const volatile long long*>(&ctrl->time);
@@ -238,6 +375,7 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
   }
   const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
   const uint32_t tag = (uint32_t)(it + 1ull);
+  EB_MARK(16);
 
   for (int r = tid; r < T; r += blockDim.x) s_cnt[r] = 0;
   for (int r = tid; r < nown; r += blockDim.x)
@@ -251,134 +389,34 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
 
   double* ll = reinterpret_cast<double*>(smraw + lay.ll) + (size_t)g * T;
   double* lu = reinterpret_cast<double*>(smraw + lay.lu) + (size_t)g * T;
-  int* pos = reinterpret_cast<int*>(smraw + lay.pos) + (size_t)g * nown;   // positions on this rank's rungs only
   unsigned char* sband = smraw + lay.band + (size_t)g * T;
   unsigned char* s_rej = smraw + lay.rej + (size_t)g * T;
+  int* pos_all = reinterpret_cast<int*>(smraw + lay.pos);                            // [gpc][CPB][nown]
+  unsigned long long* sel_all = reinterpret_cast<unsigned long long*>(smraw + lay.sel);   // [gpc][CPB][2]
   bool ok = *reinterpret_cast<volatile unsigned int*>(&ctrl->error) == 0u;
   const long long t_start = clock64();
 
-  // ---- A: own rungs of every chain: position, and the log-likelihood there goes to the chain's resolver
-  if (valid) {
-    const int h = chain % p.world;
-    const size_t cslot = (size_t)(chain / p.world);
-    for (int k = lane; k < nown; k += 32) {
-      int pz = chain;
-      if (p.permute) {
-        Feistel sig;
-        sig.init_from(s_keys + FEISTEL_ROUNDS * k, (uint32_t)W);
-        pz = (int)sig((uint32_t)chain);
-      }
-      pos[k] = pz;
-      const double v = p.logl_cur[(size_t)k * W + pz];
-      st_volatile_u4(p.llc_dst[h] + (size_t)(p.t_lo + k) * p.Wr + cslot, unit_of(v, tag));
+  // ---- A ----
+  if (!adapt_cta) {
+    int gi = 0;
+    for (int grp = blockIdx.x; grp < ngroups; grp += nctas, ++gi) {
+      const int chain = grp * CPB + g;
+      if (chain < W) phase_a(p, s_keys, chain, lane, nown, tag, pos_all + ((size_t)gi * CPB + g) * nown);
     }
   }
   __syncwarp();               // pos[] of the chain is read by all lanes below
   pdl_launch_dependents();    // the next move kernel may begin its draws
+  EB_MARK(17);
 
-  // ---- B: the resolver of the chain: log u, the T units, the cascade, the accept bits to every rank
-  unsigned long long sel_lo = 0ull, sel_hi = 0ull;
-  const bool resolver = valid && (chain % p.world) == p.rank;   // uniform over the warp
-  if (resolver) {
-    for (int r = lane; r < T; r += 32) {
-      // one Philox block serves rungs r and r + 8 of a chain (k_swap.cu): counter (chain, (r & 7) | ((r >> 4) << 3)),
-      // word pair (r >> 3) & 1
-      const bool second = ((r >> 3) & 1) != 0;
-      const uint4 q = stream(key, TAG_SWAP_U, (uint32_t)chain, (uint32_t)((r & 7) | ((r >> 4) << 3)));
-      const double u = second ? u01_52(q.z, q.w) : u01_52(q.x, q.y);
-      lu[r] = log(u);                                                          // tempering.py:535
-      s_rej[r] = 0;
-    }
-    const uint4* src = p.llc_in + (size_t)(chain / p.world);
-    for (int r = lane; r < T; r += 32) ll[r] = unit_double(poll_unit(src + (size_t)r * p.Wr, tag, ok, t_start, ctrl));
-    __syncwarp();
-    // band of walker j: bit a = test at rung j-a with x = ll[j] (tempering.py:538, :541), all walkers at once
-    for (int j = lane; j < T; j += 32) {
-      if (j >= 1) {
-        const double x = ll[j];
-        unsigned b = 0u;
-#pragma unroll
-        for (int a = 0; a < AGES; ++a) {
-          const int i = j - a;
-          if (i >= 1) b |= (unsigned)(s_dts[i] * (x - ll[i - 1]) > lu[i]) << a;
-        }
-        sband[j] = (unsigned char)b;
-      }
-    }
-    __syncwarp();
-    // walk over the carried walkers (k_swap.cu): mark the rung where each settles; long runs extended by a vote
-    int j = T - 1;
-    while (j >= 1) {
-      int run = __ffs((int)~(unsigned)sband[j]) - 1;
-      if (run == AGES) {
-        const double x = ll[j];
-        int base = j - AGES;
-        while (base >= 1) {
-          const int i = base - lane;
-          const bool f = i >= 1 && s_dts[i] * (x - ll[i - 1]) > lu[i];
-          const int n = __ffs((int)~__ballot_sync(0xffffffffu, f)) - 1;
-          if (n < 0) { run += 32; base -= 32; continue; }
-          run += n;
-          break;
-        }
-      }
-      s_rej[j - run] = 1;
-      j -= run + 1;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (m * 32 < T) {
-        const int r = lane + m * 32;
-        const bool acc = r >= 1 && r < T && s_rej[r] == 0;
-        const unsigned v = __ballot_sync(0xffffffffu, acc);
-        if (acc) atomicAdd(&s_cnt[r - 1], 1);          // swaps_accepted[r-1] counts accepted swaps at rung r (:542)
-        if (m == 0) sel_lo |= (unsigned long long)v;
-        if (m == 1) sel_lo |= (unsigned long long)v << 32;
-        if (m == 2) sel_hi |= (unsigned long long)v;
-        if (m == 3) sel_hi |= (unsigned long long)v << 32;
-      }
-    }
-    if (lane < p.world) {
-      st_volatile_u4(p.bits_dst[lane] + 2 * (size_t)chain, unit_of((uint32_t)sel_lo, (uint32_t)(sel_lo >> 32), tag));
-      st_volatile_u4(p.bits_dst[lane] + 2 * (size_t)chain + 1, unit_of((uint32_t)sel_hi, (uint32_t)(sel_hi >> 32), tag));
-    }
-  } else if (valid) {
-    // ---- C (first part): the accept bits of the chain from its resolver
-    const uint4 a = poll_unit(p.bits_in + 2 * (size_t)chain, tag, ok, t_start, ctrl);
-    const uint4 b = poll_unit(p.bits_in + 2 * (size_t)chain + 1, tag, ok, t_start, ctrl);
-    sel_lo = ((unsigned long long)a.z << 32) | a.x;
-    sel_hi = ((unsigned long long)b.z << 32) | b.x;
-  }
-
-  // ---- C: rows that change rank leave as mail pushed by the rank that owns the source rung: coords, logp, logl
-  const int MU = LD + 2;
-  if (valid) {
-    if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {          // up: my top rung's walker moves to rung t_hi
-      const int gd = owner_of(p, p.t_hi);
-      const size_t sslot = (size_t)(nown - 1) * W + pos[nown - 1];
-      uint4* box = p.mail_dst[gd] + ((size_t)0 * W + chain) * MU;
-      for (int e = lane; e < MU; e += 32) {
-        const double v = e < LD ? p.coords_cur[sslot * LD + e] : e == LD ? p.logp_cur[sslot] : p.logl_cur[sslot];
-        st_volatile_u4(box + e, unit_of(v, tag));
-      }
-    }
-    if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) {         // down: the walker carried across my lower boundary
-      int o = p.t_lo;
-      while (o + 1 < T && sel_bit(sel_lo, sel_hi, o + 1)) ++o;    // rung it started on
-      if (o < p.t_hi) {                                           // ... one of mine
-        int d = p.t_lo - 1;
-        while (d >= 1 && sel_bit(sel_lo, sel_hi, d)) --d;         // rung it settles on
-        const int gd = owner_of(p, d);
-        const size_t sslot = (size_t)(o - p.t_lo) * W + pos[o - p.t_lo];
-        uint4* box = p.mail_dst[gd] + ((size_t)1 * W + chain) * MU;
-        for (int e = lane; e < MU; e += 32) {
-          const double v = e < LD ? p.coords_cur[sslot * LD + e] : e == LD ? p.logp_cur[sslot] : p.logl_cur[sslot];
-          st_volatile_u4(box + e, unit_of(v, tag));
-        }
-      }
+  // ---- B ----
+  if (!adapt_cta) {
+    for (int grp = blockIdx.x; grp < ngroups; grp += nctas) {
+      const int chain = grp * CPB + g;
+      if (chain < W && (chain % p.world) == p.rank)    // uniform over the warp
+        phase_b(p, key, chain, lane, tag, ok, t_start, s_dts, ll, lu, sband, s_rej, s_cnt);
     }
   }
+  EB_MARK(19);
 
   // ---- the rank's partial swap counts (resolved chains only) for the adapt CTA
   __syncthreads();
@@ -391,41 +429,100 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
       atomicAdd(&ctrl->arrive[blockIdx.x % 8], 1u);
     }
   } else {
-    adapt_cta_work(p, nreal, it, time_now, s_betas, s_dts, s_cnt);
+    adapt_cta_work(p, nctas, it, time_now, s_betas, s_dts, s_cnt);
+    EB_MARK(23);
     return;
   }
-  if (!valid) return;
+  EB_MARK(20);
 
-  // ---- C: every owned slot is rewritten into the alternate buffers; sources on this rank are copied, the others
-  //      arrive by mail: [0] from below into rung t_lo, [1] from above into the rung where the carried walker settles
-  for (int r = p.t_lo + lane; r < p.t_hi; r += 32) {
-    const int s = swap_source(sel_lo, sel_hi, r, T);
-    if (s < p.t_lo || s >= p.t_hi) continue;
-    const size_t sslot = (size_t)(s - p.t_lo) * W + pos[s - p.t_lo];
-    const size_t dslot = (size_t)(r - p.t_lo) * W + pos[r - p.t_lo];
-    copy_row(c.coords + dslot * LD, p.coords_cur + sslot * LD, LD);
-    c.logp[dslot] = p.logp_cur[sslot];
-    c.logl[dslot] = p.logl_cur[sslot];
-  }
-  int dest[2] = {-1, -1};
-  if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) dest[0] = p.t_lo;
-  if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {
-    int d = p.t_hi - 1;
-    while (d >= 1 && sel_bit(sel_lo, sel_hi, d)) --d;
-    if (d >= p.t_lo) dest[1] = d;
-  }
-#pragma unroll
-  for (int dir = 0; dir < 2; ++dir) {
-    if (dest[dir] < 0) continue;
-    const size_t dslot = (size_t)(dest[dir] - p.t_lo) * W + pos[dest[dir] - p.t_lo];
-    const uint4* box = p.mail_in + ((size_t)dir * W + chain) * MU;
-    for (int e = lane; e < MU; e += 32) {
-      const double x = unit_double(poll_unit(box + e, tag, ok, t_start, ctrl));
-      if (e < LD) c.coords[dslot * LD + e] = x;
-      else if (e == LD) c.logp[dslot] = x;
-      else c.logl[dslot] = x;
+  // ---- C1: accept bits of every chain; rows that change rank leave as mail pushed by the rank that owns the source rung
+  //      (coords, logp, logl); rows that stay on this rank are copied into the alternate buffers
+  const int MU = LD + 2;
+  {
+    int gi = 0;
+    for (int grp = blockIdx.x; grp < ngroups; grp += nctas, ++gi) {
+      const int chain = grp * CPB + g;
+      if (chain >= W) continue;
+      const int* pos = pos_all + ((size_t)gi * CPB + g) * nown;
+      const uint4 a = poll_unit(p.bits_in + 2 * (size_t)chain, tag, ok, t_start, ctrl);
+      const uint4 b = poll_unit(p.bits_in + 2 * (size_t)chain + 1, tag, ok, t_start, ctrl);
+      const unsigned long long sel_lo = ((unsigned long long)a.z << 32) | a.x;
+      const unsigned long long sel_hi = ((unsigned long long)b.z << 32) | b.x;
+      if (lane == 0) {
+        sel_all[((size_t)gi * CPB + g) * 2] = sel_lo;
+        sel_all[((size_t)gi * CPB + g) * 2 + 1] = sel_hi;
+      }
+      if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {          // up: my top rung's walker moves to rung t_hi
+        const int gd = owner_of(p, p.t_hi);
+        const size_t sslot = (size_t)(nown - 1) * W + pos[nown - 1];
+        uint4* box = p.mail_dst[gd] + ((size_t)0 * W + chain) * MU;
+        for (int e = lane; e < MU; e += 32) {
+          const double v = e < LD ? p.coords_cur[sslot * LD + e] : e == LD ? p.logp_cur[sslot] : p.logl_cur[sslot];
+          st_volatile_u4(box + e, unit_of(v, tag));
+        }
+      }
+      if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) {         // down: the walker carried across my lower boundary
+        int o = p.t_lo;
+        while (o + 1 < T && sel_bit(sel_lo, sel_hi, o + 1)) ++o;    // rung it started on
+        if (o < p.t_hi) {                                           // ... one of mine
+          int d = p.t_lo - 1;
+          while (d >= 1 && sel_bit(sel_lo, sel_hi, d)) --d;         // rung it settles on
+          const int gd = owner_of(p, d);
+          const size_t sslot = (size_t)(o - p.t_lo) * W + pos[o - p.t_lo];
+          uint4* box = p.mail_dst[gd] + ((size_t)1 * W + chain) * MU;
+          for (int e = lane; e < MU; e += 32) {
+            const double v = e < LD ? p.coords_cur[sslot * LD + e] : e == LD ? p.logp_cur[sslot] : p.logl_cur[sslot];
+            st_volatile_u4(box + e, unit_of(v, tag));
+          }
+        }
+      }
+      // every owned slot is rewritten into the alternate buffers; sources on this rank are copied here
+      for (int r = p.t_lo + lane; r < p.t_hi; r += 32) {
+        const int s = swap_source(sel_lo, sel_hi, r, T);
+        if (s < p.t_lo || s >= p.t_hi) continue;
+        const size_t sslot = (size_t)(s - p.t_lo) * W + pos[s - p.t_lo];
+        const size_t dslot = (size_t)(r - p.t_lo) * W + pos[r - p.t_lo];
+        copy_row(c.coords + dslot * LD, p.coords_cur + sslot * LD, LD);
+        c.logp[dslot] = p.logp_cur[sslot];
+        c.logl[dslot] = p.logl_cur[sslot];
+      }
     }
   }
+  __syncwarp();
+  EB_MARK(31);
+
+  // ---- C2: the others arrive by mail: [0] from below into rung t_lo, [1] from above into the rung where the carried
+  //      walker settles
+  {
+    int gi = 0;
+    for (int grp = blockIdx.x; grp < ngroups; grp += nctas, ++gi) {
+      const int chain = grp * CPB + g;
+      if (chain >= W) continue;
+      const int* pos = pos_all + ((size_t)gi * CPB + g) * nown;
+      const unsigned long long sel_lo = sel_all[((size_t)gi * CPB + g) * 2];
+      const unsigned long long sel_hi = sel_all[((size_t)gi * CPB + g) * 2 + 1];
+      int dest[2] = {-1, -1};
+      if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) dest[0] = p.t_lo;
+      if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {
+        int d = p.t_hi - 1;
+        while (d >= 1 && sel_bit(sel_lo, sel_hi, d)) --d;
+        if (d >= p.t_lo) dest[1] = d;
+      }
+#pragma unroll
+      for (int dir = 0; dir < 2; ++dir) {
+        if (dest[dir] < 0) continue;
+        const size_t dslot = (size_t)(dest[dir] - p.t_lo) * W + pos[dest[dir] - p.t_lo];
+        const uint4* box = p.mail_in + ((size_t)dir * W + chain) * MU;
+        for (int e = lane; e < MU; e += 32) {
+          const double x = unit_double(poll_unit(box + e, tag, ok, t_start, ctrl));
+          if (e < LD) c.coords[dslot * LD + e] = x;
+          else if (e == LD) c.logp[dslot] = x;
+          else c.logl[dslot] = x;
+        }
+      }
+    }
+  }
+  EB_MARK(21);
 }
 
 }  // namespace split
@@ -478,21 +575,34 @@ int eb_pt_swap_split(const eb_split* sp, const eb_state* dst, const eb_swap_rng*
   a.stop_adaptation = adapt ? adapt->stop_adaptation : -1;
   a.lag = adapt ? adapt->adaptation_lag : 10000.0;
   a.t0 = adapt ? adapt->adaptation_time : 100.0;
-  const size_t sb = split::layout(T, a.t_hi - a.t_lo).total;
-  rc = set_smem(split::pt_swap_split_kernel, sb);
-  if (rc) return rc;
-  const unsigned grid = (unsigned)((a.c.W + split::CPB - 1) / split::CPB) + 1u;   // + the adapt CTA
-  // Every CTA both feeds remote resolvers (A) and waits for remote ones (C): all CTAs of the grid must be resident at
-  // once, or ranks would wait for each other's unscheduled CTAs.
-  int dev = 0, sms = 0, per_sm = 0;
+  // Every CTA both feeds remote resolvers (A) and waits for remote ones (B, C): the grid must be resident at once, or
+  // ranks would wait for each other's unscheduled CTAs.  A CTA takes gpc chain groups; gpc is the smallest count whose
+  // grid fits (the shared-memory footprint grows with gpc, hence the loop).  Every rank computes the same grid.
+  const int ngroups = (a.c.W + split::CPB - 1) / split::CPB;
+  int dev = 0, sms = 0;
   EB_CUDA(cudaGetDevice(&dev));
   EB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, split::pt_swap_split_kernel, split::THREADS, sb));
-  if ((long long)grid > (long long)per_sm * sms)
-    return fail(EB_ERR_UNSUPPORTED, "chain-split pass: %u CTAs exceed the %d that can be resident (nwalkers %d too large); "
-                "use the fused sharded pass", grid, per_sm * sms, a.c.W);
+  size_t sb = 0;
+  unsigned grid = 0;
+  for (int gpc = 1;; ++gpc) {
+    sb = split::layout(T, a.t_hi - a.t_lo, gpc).total;
+    if (sb > 200 * 1024) return fail(EB_ERR_UNSUPPORTED, "chain-split pass: nwalkers %d does not fit a resident grid", a.c.W);
+    rc = set_smem(split::pt_swap_split_kernel, sb);
+    if (rc) return rc;
+    int per_sm = 0;
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, split::pt_swap_split_kernel, split::THREADS, sb));
+    const int nctas = (ngroups + gpc - 1) / gpc;
+    // keep one SM's worth of slack: the move kernel that follows as a programmatic dependent needs room to start
+    if ((long long)nctas + 1 <= (long long)per_sm * sms - per_sm || gpc >= 64) {
+      a.gpc = gpc;
+      grid = (unsigned)nctas + 1u;   // + the adapt CTA
+      break;
+    }
+  }
   split::pt_swap_split_kernel<<<grid, split::THREADS, sb, (cudaStream_t)stream>>>(a);
   return check_launch("pt_swap_split");
 }
 
 }  // extern "C"
+
+EB_DEFINE_MARK_READER(eb_debug_marks_split)

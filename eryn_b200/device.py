@@ -157,8 +157,16 @@ class DeviceContext(object):
             torch.empty((T, W), dtype=torch.float64, device=self.device)
         return DeviceState(coords, logl, logp, inds, betas, name)
 
+    def check_error(self):
+        """raise if a kernel set eb_ctrl.error (a bounded in-kernel wait ran out): the chain is invalid from there on"""
+        err = int(self.read_ctrl().error)
+        if err:
+            raise _lib.ErynB200Error(f"device error {err} (EB_DEVERR_*): a bounded wait inside the swap pass timed out "
+                                     "(peer never published / a CTA never arrived); results after that pass are invalid")
+
     def download(self, d, into=None, random_state=None):
         """DeviceState -> host State (new, or refreshing the arrays of `into` in place)."""
+        self.check_error()
         coords = d.coords.cpu().numpy()
         logl = d.logl.cpu().numpy()
         logp = d.logp.cpu().numpy()
@@ -294,7 +302,9 @@ class DeviceContext(object):
             elif proposal["kind"] == "prior":
                 r.cov_kind = 2
             else:
-                keep = self.to_dev(proposal["chol"], np.float64)
+                keep = proposal.get("_chol_dev")
+                if keep is None or keep.device != self.device:  # uploaded once: launches must be graph-capturable
+                    keep = proposal["_chol_dev"] = self.to_dev(proposal["chol"], np.float64)
                 r.cov_kind, r.chol = 1, _ptr(keep)
         else:
             delta, u_acc = replay

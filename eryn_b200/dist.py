@@ -27,7 +27,7 @@ import ctypes as C
 import numpy as np
 
 __all__ = ["temperature_partition", "owner_of", "ArenaLayout", "exchange", "scatter_rows", "gather_rows",
-           "ShardedRun", "ShardedTemperatureControl", "run_sharded_bench"]
+           "ShardedRun", "ShardedTemperatureControl", "run_sharded_bench", "sharded_parity_check"]
 
 ALIGN = 256
 
@@ -365,11 +365,82 @@ def __getattr__(name):
 
 
 # ------------------------------------------------------------------------------------------------------
+# parity self-check of a sharded run (bench.py --gpus N prints it; tests/test_mgpu.py checks it against the oracle)
+# ------------------------------------------------------------------------------------------------------
+def sharded_parity_check(rank, world, local, comm="split", ntemps=None, nwalkers=256, ndim=8, nit=6, seed=4242,
+                         like=None, lo=-10.0, hi=10.0):
+    """Run a short temperature-sharded chain over all ranks and the SAME chain unsharded on rank 0's GPU (same seed,
+    same counter-based streams keyed by global temperature / chain) and compare every array of the final state.
+    Returns dict(ok, max_rel, swaps_equal, accepted_equal, ...) on rank 0, None elsewhere.  Results must be bit-identical
+    (max_rel == 0): both runs execute the same arithmetic in the same order."""
+    import torch
+    import torch.distributed as dist
+    from .device import DeviceContext
+    from .likelihood import GaussianLikelihood
+    from .moves import StretchMove, TemperatureControl
+    from .prior import ProbDistContainer, uniform_dist
+    from .state import State
+    T = 16 * world if ntemps is None else int(ntemps)
+    W, d = int(nwalkers), int(ndim)
+    dev = torch.device("cuda", local)
+    if like is None:
+        A = np.random.RandomState(99).randn(d, d)
+        like = GaussianLikelihood(np.zeros(d), np.linalg.inv(A @ A.T / d + np.eye(d)))
+    pri = ProbDistContainer({i: uniform_dist(lo, hi) for i in range(d)})
+    x0 = np.random.RandomState(1).uniform(-3.0, 3.0, size=(T, W, 1, d))
+    ctx = DeviceContext(pri, like, device=dev, rng="philox", seed=seed)
+    run = ShardedRun(ctx, T, W, comm=comm)
+    tc = _make_sharded_tc()(run, d, W)
+    mv = StretchMove(a=2.0)
+    mv.temperature_control = tc
+    mv.bind(ctx)
+    mv.accepted = np.zeros((run.t_hi - run.t_lo, W))
+    run.load(x0, tc._betas_host)
+    for _ in range(nit):
+        mv.propose(None, run.current)
+    full = run.gather()
+    swaps = tc.swaps_accepted
+    acc = gather_rows(mv.accepted, run.temp_begin)
+    run.close()
+    out = None
+    if rank == 0:
+        ctx1 = DeviceContext(pri, like, device=dev, rng="philox", seed=seed)
+        tc1 = TemperatureControl(d, W, ntemps=T)
+        tc1.bind(ctx1)
+        mv1 = StretchMove(a=2.0)
+        mv1.temperature_control = tc1
+        mv1.bind(ctx1)
+        mv1.accepted = np.zeros((T, W))
+        ds = ctx1.upload(State(x0), betas=tc1.betas_dev)
+        ctx1.eval_state(ds)
+        for _ in range(nit):
+            mv1.propose(None, ds)
+        ref = ctx1.download(ds)
+
+        def rel(a, b):
+            a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+            den = np.maximum(np.abs(b), 1e-300)
+            return float(np.max(np.abs(a - b) / den)) if a.size else 0.0
+        max_rel = max(rel(full["coords"], ref.branches_coords[ds.branch_name]), rel(full["logl"], ref.log_like),
+                      rel(full["logp"], ref.log_prior), rel(full["betas"], ref.betas))
+        swaps_equal = bool(np.array_equal(swaps, tc1.swaps_accepted))
+        accepted_equal = bool(np.array_equal(acc, mv1.accepted))
+        out = dict(ok=bool(max_rel <= 1e-10 and swaps_equal and accepted_equal), max_rel=max_rel, swaps_equal=swaps_equal,
+                   accepted_equal=accepted_equal, ntemps=T, nwalkers=W, ndim=d, iterations=nit, comm=comm,
+                   against="the same chain run unsharded on rank 0's GPU (coords, logl, logp, betas, swap counts, accept counts)",
+                   swaps_accepted_head=[int(v) for v in swaps[:4]])
+    dist.barrier()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
 # ------------------------------------------------------------------------------------------------------
-def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm="fused"):
-    """Weak-scaling step of bench.py: the walker count grows with the number of GPUs (wl["W"]), the ladder is
-    sharded by temperature.  Returns the JSON dict on rank 0 (None elsewhere)."""
+def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm="split", with_e2e=True, with_k1=True,
+                      sustain_s=0.0):
+    """One workload of bench.py on all ranks: the ladder sharded by temperature, one captured graph per (move kind, buffer
+    parity) replayed per step.  Per-step CUDA events with an L2 flush between steps (outside the event pairs), summed,
+    MAX over ranks.  Returns the JSON dict on rank 0 (None elsewhere)."""
     import time
     import torch
     import torch.distributed as dist
@@ -401,7 +472,7 @@ def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm
     schedule = sched_rng.choice(nmoves, p=np.asarray(wl["weights"]) / np.sum(wl["weights"]), size=args.warmup + args.steps)
     stream = torch.cuda.Stream(device=dev)
 
-    # one iteration = move + publish + swap; the buffers flip every iteration, so a graph is captured per
+    # one iteration = move + (publish +) swap; the buffers flip every iteration, so a graph is captured per
     # (move kind, parity) and replayed according to the schedule
     graphs = {}
     use_graph = comm != "nccl"
@@ -461,11 +532,20 @@ def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm
         e1.record(stream)
         torch.cuda.synchronize()
         dist.barrier()
+        if sustain_s > 0:  # keep the GPUs under this load long enough for the clock sampler (same count on every rank)
+            per = max(e0.elapsed_time(e1) / args.steps * 1e-3, 1e-6)
+            tt = torch.tensor([per], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            n_sus = int(sustain_s / float(tt[0])) // 2 * 2
+            for i in range(n_sus):
+                one_step(args.warmup + (i % args.steps))
+            torch.cuda.synchronize()
+            dist.barrier()
     run.check()
     # the dominant kernel alone (this rank's temperatures): back-to-back stretch steps in one graph
     st_moves = [m for m in moves if isinstance(m, StretchMove)]
     k1_us = None
-    if st_moves:
+    if st_moves and with_k1:
         nrep = 50
         cnt = st_moves[0]._count_buffer(ctx, run.t_hi - run.t_lo, W)
         gk = torch.cuda.CUDAGraph()
@@ -489,40 +569,43 @@ def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm
     total_ms, resident_ms = float(tt[0]), float(tt[1]) / args.steps
 
     # ---- e2e: host buffers in, one iteration, host buffers out, every step (per rank: its own temperatures) ----
-    cur = run.current
-    h = dict(coords=cur.coords.cpu().pin_memory(), logl=cur.logl.cpu().pin_memory(), logp=cur.logp.cpu().pin_memory())
-    ne2e = max(20, min(args.steps, 100))
-    torch.cuda.synchronize()
-    dist.barrier()
-    with torch.cuda.stream(stream):
-        t0 = time.perf_counter()
-        for i in range(ne2e):
-            cur = run.current
-            cur.coords.copy_(h["coords"], non_blocking=True)
-            cur.logl.copy_(h["logl"], non_blocking=True)
-            cur.logp.copy_(h["logp"], non_blocking=True)
-            one_step(args.warmup + (i % args.steps))
-            cur = run.current
-            h["coords"].copy_(cur.coords, non_blocking=True)
-            h["logl"].copy_(cur.logl, non_blocking=True)
-            h["logp"].copy_(cur.logp, non_blocking=True)
-            stream.synchronize()
-        e2e_s = (time.perf_counter() - t0) / ne2e
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0])
-    run.check()
-    shard_bytes = sum(t.numel() * 8 for t in h.values())
+    e2e = None
+    if with_e2e:
+        cur = run.current
+        h = dict(coords=cur.coords.cpu().pin_memory(), logl=cur.logl.cpu().pin_memory(), logp=cur.logp.cpu().pin_memory())
+        ne2e = max(20, min(args.steps, 100))
+        torch.cuda.synchronize()
+        dist.barrier()
+        with torch.cuda.stream(stream):
+            t0 = time.perf_counter()
+            for i in range(ne2e):
+                cur = run.current
+                cur.coords.copy_(h["coords"], non_blocking=True)
+                cur.logl.copy_(h["logl"], non_blocking=True)
+                cur.logp.copy_(h["logp"], non_blocking=True)
+                one_step(args.warmup + (i % args.steps))
+                cur = run.current
+                h["coords"].copy_(cur.coords, non_blocking=True)
+                h["logl"].copy_(cur.logl, non_blocking=True)
+                h["logp"].copy_(cur.logp, non_blocking=True)
+                stream.synchronize()
+            e2e_s = (time.perf_counter() - t0) / ne2e
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te[0])
+        run.check()
+        shard_bytes = sum(t.numel() * 8 for t in h.values())
+        e2e = dict(value=T * W / e2e_s, ms_per_step=e2e_s * 1e3, h2d_bytes_per_step=int(shard_bytes * world),
+                   d2h_bytes_per_step=int(shard_bytes * world),
+                   api="per rank: pinned host shard -> H2D -> move + sharded swap pass -> D2H, every step")
     swaps = tc.swaps_accepted.tolist()[:4]
     betas = run.betas_all.cpu().numpy()
     out = None
     if rank == 0:
         out = dict(value=T * W * args.steps / (total_ms * 1e-3), ms_per_step=total_ms / args.steps,
-                   resident_ms=resident_ms, launches=int(launches), clocks=clocks,
-                   e2e=dict(value=T * W / e2e_s, ms_per_step=e2e_s * 1e3, h2d_bytes_per_step=int(shard_bytes * world),
-                            d2h_bytes_per_step=int(shard_bytes * world),
-                            api="per rank: pinned host shard -> H2D -> move + publish + sharded swap -> D2H, every step"),
+                   resident_ms=resident_ms, launches=int(launches), clocks=clocks, e2e=e2e,
                    swaps=swaps, betas=[float(betas[0]), float(betas[-1])], temp_begin=run.temp_begin, comm=comm,
                    graph=use_graph, k1_us=k1_us, local_temps=run.t_hi - run.t_lo)
     run.close()
+    del flush
     return out

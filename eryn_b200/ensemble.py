@@ -4,17 +4,21 @@ The host keeps what the reference keeps on the host — move schedule, State boo
 store — and the walkers live on the GPU between yields: `thin_by` iterations run back to back with
 no host synchronisation, and a host `State` is materialised only at yield/store points
 (ensemble.py:1013, :1045)."""
+import gc
 import warnings
+import weakref
 from collections.abc import Iterable
 
 import numpy as np
 import torch
 
+from . import _lib
 from .backend import Backend
 from .device import DeviceContext, DeviceState
 from .model import Model
 from .moves import StretchMove, TemperatureControl
 from .prior import ProbDistContainer
+from .staging import LazyState
 from .state import State
 
 __all__ = ["EnsembleSampler", "walkers_independent"]
@@ -187,6 +191,10 @@ class EnsembleSampler(object):
                                branch_names=self.branch_names, rj=self.has_reversible_jump, moves=self.move_keys,
                                key_order=self.key_order, **info)
         self._dstate = None
+        self._graphs, self._warm, self._ring, self._pending = {}, set(), None, []
+        self.force_eager = False  # True: launch every iteration eagerly and store synchronously (the checked baseline)
+        _weak_flush = weakref.WeakMethod(self._flush_store)  # no reference cycle sampler <-> backend
+        self.backend._flush_cb = lambda: (_weak_flush() or (lambda: None))()  # getters see every step that was yielded
 
     # ---- small mirrors ---------------------------------------------------------------------------------
     @property
@@ -271,7 +279,11 @@ class EnsembleSampler(object):
     # ---- the loop -------------------------------------------------------------------------------------
     def sample(self, initial_state, iterations=1, tune=False, skip_initial_state_check=True, thin_by=1, store=True,
                progress=False):
-        """Advance the chain as a generator (ensemble.py:808-1045)."""
+        """Advance the chain as a generator (ensemble.py:808-1045).
+
+        Production (philox) runs of the single-branch samplers take the device-resident fast path: the launches of
+        `thin_by` iterations are captured once into CUDA graphs and replayed, stored steps leave through the staging
+        ring (staging.py) and the yielded State materialises on the host only if the consumer looks at it."""
         if iterations is None and store:
             raise ValueError("'store' must be False when 'iterations' is None")
         state = State(initial_state, copy=True)
@@ -291,13 +303,15 @@ class EnsembleSampler(object):
                 tc.betas = state.betas.copy()  # ensemble.py:915-921
             else:
                 state.betas = tc.betas.copy()
-        need_eval = state.log_prior is None or state.log_like is None
-        d = self.ctx.upload(state, betas=None if tc is None else tc.betas_dev)
-        if need_eval:
+        d = self._upload_resident(state, None if tc is None else tc.betas_dev)
+        if state.log_prior is None or state.log_like is None:  # ensemble.py:898-912: only what is missing is evaluated
             keep_lp = None if state.log_prior is None else d.logp.clone()
-            self.ctx.eval_state(d)  # ensemble.py:898-912
+            keep_ll = None if state.log_like is None else d.logl.clone()
+            self.ctx.eval_state(d)
             if keep_lp is not None:
                 d.logp.copy_(keep_lp)
+            if keep_ll is not None:
+                d.logl.copy_(keep_ll)
         logl0, logp0 = d.logl.cpu().numpy(), d.logp.cpu().numpy()
         if np.shape(logl0) != (self.ntemps, self.nwalkers) or np.shape(logp0) != (self.ntemps, self.nwalkers):
             raise ValueError("incompatible input dimensions")
@@ -316,6 +330,80 @@ class EnsembleSampler(object):
             self.backend.grow(iterations, None)
         model = self.get_model()
         self._dstate = d
+        fast = (self.ctx.rng == "philox" and not self._mb and not tune and self.ctx.fused and not self.force_eager
+                and all(getattr(m, "graphable", False) for m in self.moves))
+        gen = self._sample_resident if fast else self._sample_eager
+        try:
+            yield from gen(model, d, iterations, thin_by, store, tune)
+        finally:
+            self._flush_store()
+        self._check_device_error()
+
+    def _upload_resident(self, state, betas_dev):
+        """the device state of this sampler keeps its buffers between calls (captured graphs stay valid)"""
+        d = self._dstate
+        br = state.branches[self.branch_names[0]]
+        if (self._mb or d is None or d.shape != tuple(br.coords.shape) or (d.inds is None) != bool(np.all(br.inds))
+                or d.betas is not betas_dev):
+            self._graphs, self._warm, self._ring = {}, set(), None
+            return self.ctx.upload(state, betas=betas_dev)
+        d.coords.copy_(torch.from_numpy(np.ascontiguousarray(br.coords, dtype=np.float64)))
+        if d.inds is not None:
+            d.inds.copy_(torch.from_numpy(np.ascontiguousarray(br.inds.astype(np.uint8))))
+        if state.log_like is not None:
+            d.logl.copy_(torch.from_numpy(np.ascontiguousarray(state.log_like, dtype=np.float64)))
+        if state.log_prior is not None:
+            d.logp.copy_(torch.from_numpy(np.ascontiguousarray(state.log_prior, dtype=np.float64)))
+        return d
+
+    def _check_device_error(self, ctrl_bytes=None):
+        """eb_ctrl.error is set by a kernel whose bounded wait ran out (a swap pass that never saw all its CTAs): the
+        chain is not trustworthy from that iteration on"""
+        err = int(self.ctx.read_ctrl().error) if ctrl_bytes is None else \
+            int(_lib.eb_ctrl.from_buffer_copy(ctrl_bytes.tobytes()).error)
+        if err:
+            raise _lib.ErynB200Error(f"device error {err} (EB_DEVERR_*) raised inside a kernel: a bounded wait of the "
+                                     "swap pass timed out; the chain after that iteration is invalid")
+
+    def _apply_host_edits(self, d, host, before=None):
+        """A consumer (update_fn, or the body of a `for state in sampler.sample(...)` loop) may edit the yielded state
+        in place, as with the reference, where the sampler carries the same object on (ensemble.py:1030-1045): bring
+        such edits back to the device.  `before` = pristine copies for states that were downloaded eagerly."""
+        tc = self.temperature_control
+        if isinstance(host, LazyState):
+            mod = host.modified()
+        else:
+            mod = {}
+            br = host.branches[self.branch_names[0]]
+            if not np.array_equal(br.coords, before["coords"], equal_nan=True):
+                mod["coords"] = br.coords
+            if not np.array_equal(host.log_like, before["logl"]):
+                mod["logl"] = host.log_like
+            if not np.array_equal(host.log_prior, before["logp"]):
+                mod["logp"] = host.log_prior
+            if before.get("inds") is not None and not np.array_equal(br.inds, before["inds"]):
+                mod["inds"] = br.inds
+            if host.betas is not None and before.get("betas") is not None and not np.array_equal(host.betas, before["betas"]):
+                mod["betas"] = host.betas
+        if not mod:
+            return
+        if "coords" in mod:
+            d.coords.copy_(torch.from_numpy(np.ascontiguousarray(mod["coords"], dtype=np.float64)).view_as(d.coords))
+        if "logl" in mod:
+            d.logl.copy_(torch.from_numpy(np.ascontiguousarray(mod["logl"], dtype=np.float64)))
+        if "logp" in mod:
+            d.logp.copy_(torch.from_numpy(np.ascontiguousarray(mod["logp"], dtype=np.float64)))
+        if "inds" in mod:
+            if d.inds is None:
+                raise NotImplementedError("the yielded state's leaf flags were edited, but the device state was uploaded "
+                                          "without leaf flags (all leaves active)")
+            d.inds.copy_(torch.from_numpy(np.ascontiguousarray(mod["inds"].astype(np.uint8))).view_as(d.inds))
+        if "betas" in mod and tc is not None:
+            tc.betas = mod["betas"]
+
+    # ---- eager path: replay mode, several branches / reversible jump, tuning ----------------------------------------
+    def _sample_eager(self, model, d, iterations, thin_by, store, tune):
+        tc = self.temperature_control
         acc_total = torch.zeros((self.ntemps, self.nwalkers), dtype=torch.int32, device=self.ctx.device)
         rj_total = torch.zeros((self.ntemps, self.nwalkers), dtype=torch.int32, device=self.ctx.device)
         in_model_swaps = None
@@ -339,22 +427,230 @@ class EnsembleSampler(object):
                         ri = self._random.choice(len(self.rj_moves), p=self.rj_weights)  # ensemble.py:990
                         d, racc = self.rj_moves[ri].propose(model, d)
                         rj_total += racc
+                if store and inner == thin_by - 1:  # ensemble.py:1013-1028
+                    host = self.ctx.download(d, random_state=self.random_state)
+                    maf = {k: m.acceptance_fraction for k, m in self.all_moves.items()} if self.track_moves else None
+                    swaps = tc.swaps_accepted if (tc is not None and self.ntemps > 1) else None
+                    if self.has_reversible_jump:
+                        swaps = in_model_swaps
+                    self.backend.save_step(host, acc_total.cpu().numpy(), swaps_accepted=swaps,
+                                           rj_accepted=rj_total.cpu().numpy() if self.has_reversible_jump else None,
+                                           moves_accepted_fraction=maf)
+                else:
+                    host = None
+                if (self.update_iterations > 0 and self.update_fn is not None
+                        and (i + 1) % self.update_iterations == 0):  # ensemble.py:1030-1036, every inner iteration
+                    if host is None:
+                        host = self.ctx.download(d, random_state=self.random_state)
+                    d = self._call_with_edits(d, host, lambda h: self.update_fn(i, h, self))
+                    host = None if inner != thin_by - 1 else host
                 i += 1
-            # ---- yield point: materialise a host State (ensemble.py:1013-1045)
-            host = self.ctx.download(d, random_state=self.random_state)
-            if store:
-                maf = {k: m.acceptance_fraction for k, m in self.all_moves.items()} if self.track_moves else None
-                swaps = tc.swaps_accepted if (tc is not None and self.ntemps > 1) else None
-                if self.has_reversible_jump:
-                    swaps = in_model_swaps
-                self.backend.save_step(host, acc_total.cpu().numpy(), swaps_accepted=swaps,
-                                       rj_accepted=rj_total.cpu().numpy() if self.has_reversible_jump else None,
-                                       moves_accepted_fraction=maf)
-            if self.update_iterations > 0 and self.update_fn is not None and i % self.update_iterations == 0:
-                self.update_fn(i, host, self)
+            self._check_device_error()
+            if host is None:
+                host = self.ctx.download(d, random_state=self.random_state)
+            before = self._pristine_of(host)
             yield host
-            if host.betas is not None and tc is not None and not np.array_equal(host.betas, tc.betas):
-                tc.betas = host.betas  # a caller may edit the yielded state's ladder
+            d = self._sync_edits(d, host, before)
+
+    def _pristine_of(self, host):
+        if self._mb:
+            return dict(coords={n: b.coords.copy() for n, b in host.branches.items()},
+                        inds={n: b.inds.copy() for n, b in host.branches.items()}, logl=host.log_like.copy(),
+                        logp=host.log_prior.copy(), betas=None if host.betas is None else host.betas.copy())
+        br = host.branches[self.branch_names[0]]
+        return dict(coords=br.coords.copy(), inds=br.inds.copy(), logl=host.log_like.copy(), logp=host.log_prior.copy(),
+                    betas=None if host.betas is None else host.betas.copy())
+
+    def _sync_edits(self, d, host, before):
+        """eager path: after a consumer had the host state, carry its edits to the device"""
+        tc = self.temperature_control
+        if self._mb:
+            same = all(np.array_equal(host.branches[n].coords, before["coords"][n], equal_nan=True)
+                       and np.array_equal(host.branches[n].inds, before["inds"][n]) for n in host.branches)
+            same = same and np.array_equal(host.log_like, before["logl"]) and np.array_equal(host.log_prior, before["logp"])
+            if not same:
+                d = self.ctx.upload(host, betas=None if tc is None else tc.betas_dev)
+            if host.betas is not None and tc is not None and not np.array_equal(host.betas, before["betas"]):
+                tc.betas = host.betas
+            return d
+        if d.inds is None and not bool(np.all(host.branches[self.branch_names[0]].inds)):
+            raise NotImplementedError("the yielded state's leaf flags were edited, but the device state was uploaded "
+                                      "without leaf flags (all leaves active)")
+        self._apply_host_edits(d, host, before)
+        return d
+
+    def _call_with_edits(self, d, host, fn):
+        before = self._pristine_of(host)
+        fn(host)
+        return self._sync_edits(d, host, before)
+
+    # ---- resident path: CUDA-graph replay + staged stores (production) ----------------------------------------------
+    _CHUNK = 32  # iterations per captured graph of a single-move sampler (bounds capture time and graph size)
+
+    def _graph(self, key, body):
+        """capture `body` (kernel launches only) once per key, then replay"""
+        g = self._graphs.get(key)
+        if g is None:
+            cap = getattr(self, "_capture_stream", None)
+            if cap is None:
+                cap = self._capture_stream = torch.cuda.Stream(device=self.ctx.device)
+            cap.wait_stream(torch.cuda.current_stream(self.ctx.device))
+            graph = torch.cuda.CUDAGraph()
+            l0 = self.ctx.launches
+            # Graphs of a dead sampler must not be destroyed while this capture is open (their reset is a CUDA call that
+            # invalidates it): collect garbage now and keep the collector off for the few launches of the capture.
+            gc.collect()
+            gc_was = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph, stream=cap):
+                    body()
+            finally:
+                if gc_was:
+                    gc.enable()
+            g = self._graphs[key] = (graph, self.ctx.launches - l0)
+            self.ctx.launches = l0
+        g[0].replay()
+        self.ctx.launches += g[1]
+
+    def _advance_resident(self, model, d, n):
+        """n inner iterations, device resident, no host synchronisation"""
+        R = self.num_repeats_in_model
+        mis = self._random.choice(len(self.moves), p=self.weights, size=n * R)  # ensemble.py:971, one uniform per move
+        if len(self.moves) == 1:
+            mv = self.moves[0]
+            todo = n * R
+            if 0 not in self._warm:  # first proposal eagerly: module load, scratch buffers, attribute setup
+                mv.propose(model, d)
+                self._warm.add(0)
+                todo -= 1
+            while todo > 0:
+                k = min(todo, self._CHUNK)
+
+                def body(k=k):
+                    for _ in range(k):
+                        mv.propose(model, d)
+                if (0, k) in self._graphs:
+                    mv._host_tick(k)
+                self._graph((0, k), body)
+                todo -= k
+            return
+        for mi in mis:
+            mi = int(mi)
+            mv = self.moves[mi]
+            if mi not in self._warm:
+                mv.propose(model, d)
+                self._warm.add(mi)
+                continue
+            if (mi, 1) in self._graphs:
+                mv._host_tick(1)
+            self._graph((mi, 1), lambda mv=mv: mv.propose(model, d))
+
+    def _sample_resident(self, model, d, iterations, thin_by, store, tune):
+        from .staging import StoreRing
+        tc = self.temperature_control
+        T, W = self.ntemps, self.nwalkers
+        name = self.branch_names[0]
+        leaf_moves = []
+        for m in self.moves:
+            leaf_moves += list(getattr(m, "moves", [m]))
+        counts = [m._count_buffer(self.ctx, T, W) for m in leaf_moves]
+        if self._ring is None:
+            self._ring = StoreRing(self.ctx, d, count_buffers=counts, nslots=4, fill=self.backend.store_missing_leaves)
+            self._ring.on_evict = self._drain_ticket
+        ring = self._ring
+        # `accepted` of a stored step = the accepts of its LAST inner iteration (ensemble.py:968).  With one mask-writing
+        # kernel per iteration that is the accept mask left in the scratch buffer; otherwise (CombineMove, repeats) the
+        # difference of the in-kernel counters around that iteration.
+        simple = self.num_repeats_in_model == 1 and all(not hasattr(m, "moves") for m in self.moves)
+        upd = self.update_iterations if (self.update_iterations > 0 and self.update_fn is not None) else 0
+        i = 0
+        it_range = iter(int, 1) if iterations is None else range(iterations)
+        def snapshot(copy):
+            ticket = ring.push(copy=copy)
+            lazy = LazyState(ticket, name, random_state=self.random_state)
+            ticket.state_ref = weakref.ref(lazy)
+            return ticket, lazy
+
+        for _ in it_range:
+            done = 0
+            pre = None
+            lazy = None
+            while done < thin_by:
+                seg = thin_by - done
+                if not simple and seg > 1:
+                    seg -= 1  # stop before the last inner iteration to take the counter snapshot
+                if upd:
+                    seg = min(seg, upd - (i % upd))
+                if not simple and done + seg == thin_by:
+                    pre = torch.stack(counts).sum(0, dtype=torch.int32)
+                self._advance_resident(model, d, seg)
+                i += seg
+                done += seg
+                if done == thin_by:
+                    # ---- stored step / yield point (ensemble.py:1013-1045): snapshot, async copy, lazy host State.  It
+                    #      comes BEFORE update_fn, as in the reference: the stored sample is the un-edited one
+                    acc_delta = None
+                    if not simple:
+                        acc_delta = torch.stack(counts).sum(0, dtype=torch.int32) - pre
+                    ticket, lazy = snapshot(copy=store)  # not stored: device snapshot only, copied if somebody looks
+                    if store:
+                        ticket.meta = dict(acc_delta=acc_delta, nprop=[m.num_proposals for m in leaf_moves],
+                                           base=[m._accepted.copy() for m in leaf_moves], random_state=lazy.random_state)
+                        self._pending.append(ticket)
+                        self._drain_ready()
+                if upd and i % upd == 0:  # ensemble.py:1030-1036 (every inner iteration, index of that iteration)
+                    st = lazy if done == thin_by else snapshot(copy=True)[1]
+                    self.update_fn(i - 1, st, self)
+                    self._apply_host_edits(d, st)
+            yield lazy
+            self._apply_host_edits(d, lazy)
+
+    # ---- deferred Backend.save_step -----------------------------------------------------------------------------------
+    def _drain_ticket(self, ticket):
+        """store every pending sample up to and including `ticket` (in order)"""
+        while self._pending and ticket in self._pending:
+            self._store_ticket(self._pending.pop(0))
+
+    def _drain_ready(self):
+        while self._pending and self._pending[0].ready():
+            self._store_ticket(self._pending.pop(0))
+
+    def _flush_store(self):
+        while self._pending:
+            self._store_ticket(self._pending.pop(0))
+
+    def _store_ticket(self, ticket):
+        a = ticket.views()
+        meta = ticket.meta
+        ctrl = _lib.eb_ctrl.from_buffer_copy(a["ctrl"].tobytes())
+        if ctrl.error:
+            self._check_device_error(a["ctrl"])
+        T, W = self.ntemps, self.nwalkers
+        name = self.branch_names[0]
+        acc = a["accepted"].astype(np.int64) if meta["acc_delta"] is None else meta["acc_delta"].cpu().numpy()
+        swaps = None
+        if self.temperature_control is not None and T > 1:
+            swaps = np.array(ctrl.swaps_accepted[: T - 1], dtype=np.float64)
+        maf = None
+        if self.track_moves:
+            per_leaf = {}
+            k = 0
+            for mv in self.moves:
+                for leaf in getattr(mv, "moves", [mv]):
+                    per_leaf[id(leaf)] = (meta["base"][k] + a[f"count{k}"]) / max(meta["nprop"][k], 1)
+                    k += 1
+            maf = {}
+            for key, mv in self.all_moves.items():
+                if hasattr(mv, "moves"):
+                    maf[key] = np.mean([per_leaf[id(leaf)] for leaf in mv.moves], axis=0)
+                else:
+                    maf[key] = per_leaf[id(mv)]
+        inds = a["inds"].astype(bool) if "inds" in a else None
+        self.backend.save_arrays({name: a["coords"]}, None if inds is None else {name: inds}, a["logl"], a["logp"],
+                                 a.get("betas"), acc, swaps_accepted=swaps, moves_accepted_fraction=maf,
+                                 random_state=meta["random_state"])
+        ticket.release()
 
     def run_mcmc(self, initial_state, nsteps, burn=None, post_burn_update=False, **kwargs):
         """ensemble.py:1047-1125"""
@@ -365,10 +661,13 @@ class EnsembleSampler(object):
         if burn is not None and burn != 0:
             bk = dict(kwargs)
             bk["store"] = False
-            bk["thin_by"] = 1
-            i = 0
-            for results in self.sample(initial_state, iterations=burn, **bk):
-                i += 1
+            # the reference iterates `burn` times with thin_by = 1 and drops every state but the last; one yield after
+            # `burn` inner iterations is the same chain (update_fn is checked per inner iteration either way) and keeps
+            # the walkers on the device throughout
+            bk["thin_by"] = int(burn)
+            i = int(burn)
+            for results in self.sample(initial_state, iterations=1, **bk):
+                pass
             if post_burn_update and self.update_fn is not None:
                 self.update_fn(i, results, self)
             initial_state = results

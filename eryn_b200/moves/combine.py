@@ -63,6 +63,14 @@ class CombineMove(Move):
             move.periodic = periodic
         self._periodic = periodic
 
+    @property
+    def graphable(self):
+        return all(getattr(m, "graphable", False) for m in self.moves)
+
+    def _host_tick(self, n=1):
+        for move in self.moves:
+            move._host_tick(n)
+
     def bind(self, ctx):
         Move.bind(self, ctx)
         for move in self.moves:

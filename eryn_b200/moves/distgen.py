@@ -19,6 +19,8 @@ class DistributionGenerate(Move):
         self.generate_dist = generate_dist
         super().__init__(*args, **kwargs)
 
+    graphable = True
+
     def propose(self, model, state):
         ctx, d, host_state = self._enter(state)
         if not ctx.fused:

@@ -32,6 +32,8 @@ class GaussianMove(Move):
                 self.all_proposal[name] = dict(kind="scalar", scale=np.sqrt(cov))
         super().__init__(**kwargs)
 
+    graphable = True
+
     def propose(self, model, state):
         ctx, d, host_state = self._enter(state)
         if not ctx.fused:

@@ -50,6 +50,13 @@ class Move(object):
     def tune(self, state, accepted):
         pass
 
+    # ---- CUDA-graph replay of the sampler loop (ensemble.py: EnsembleSampler._advance_resident) ------------------
+    graphable = False  # True: propose() on a DeviceState in philox mode only launches kernels (no host draws / syncs)
+
+    def _host_tick(self, n=1):
+        """the host-side bookkeeping of n proposals whose launches are replayed from a captured graph"""
+        self.num_proposals += n
+
     # ---- helpers ----------------------------------------------------------------------------------
     def bind(self, ctx):
         self.ctx = ctx

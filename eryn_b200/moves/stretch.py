@@ -21,6 +21,8 @@ class StretchMove(Move):
         self.live_dangerously = live_dangerously
         super().__init__(**kwargs)
 
+    graphable = True
+
     def propose(self, model, state):
         """(state, accepted) — ensemble.py:974.  `state` may be a host State or a DeviceState."""
         ctx, d, host_state = self._enter(state)

@@ -32,7 +32,7 @@ extern "C" {
 #define EB_API
 #endif
 
-#define EB_ABI_VERSION 5
+#define EB_ABI_VERSION 6
 #define EB_MAX_TEMPS 128
 #define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
 #define EB_MAX_RANKS 16 /* GPUs of one temperature-sharded run */
@@ -183,7 +183,7 @@ EB_API size_t eb_ctrl_size(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 eb_state, 1 eb_prior, 2 eb_like,
  * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job, 9 eb_shard,
  * 10 eb_publish, 11 eb_mb_layout, 12 eb_mb_state, 13 eb_pulse_data, 14 eb_mb_friends, 15 eb_mb_group_rng,
- * 16 eb_mb_rj_rng, 17 eb_split */
+ * 16 eb_mb_rj_rng, 17 eb_split, 18 eb_stage */
 EB_API size_t eb_struct_size(int which);
 
 /* ---- probability evaluation:  EnsembleSampler.compute_log_prior (ensemble.py:1127) and
@@ -295,6 +295,23 @@ typedef struct {
   uint64_t* flags_peer[EB_MAX_RANKS];     /* peer-mapped flag arrays of every rank */
 } eb_publish;
 EB_API int eb_publish_logl(const eb_publish* pub, eb_ctrl* ctrl, void* stream);
+
+/* ---- Backend.save_step staging (backends/backend.py:1014-1091; call site ensemble.py:1013-1028).
+ *      ONE kernel gathers every array of a stored step into one contiguous device staging slot (a snapshot: the
+ *      sampler runs on while a side stream copies the slot to pinned host memory): segment i = nbytes[i] bytes from
+ *      src[i] (8-byte aligned device pointers), packed back to back, each padded to a multiple of 8 bytes.  Segment 0
+ *      may be the coordinates [rows][mask_nleaves][mask_ndim] with `mask_inds` = the leaf flags [rows][mask_nleaves]:
+ *      coordinates of inactive leaves are then stored as `fill` (NaN in the reference, backend.py:1053-1059). */
+#define EB_STAGE_MAX_SEGMENTS 16
+typedef struct {
+  int32_t nseg, mask_nleaves, mask_ndim, _pad;
+  const void* src[EB_STAGE_MAX_SEGMENTS];
+  uint64_t nbytes[EB_STAGE_MAX_SEGMENTS];
+  const uint8_t* mask_inds;   /* nullable */
+  double fill;
+  void* dst; uint64_t dst_bytes;
+} eb_stage;
+EB_API int eb_stage_pack(const eb_stage* sg, void* stream);
 
 /* device memory that can be shared between the processes of one box (cudaMalloc + CUDA IPC):
  * the handle is the 64-byte cudaIpcMemHandle_t; eb_ipc_open maps a peer's allocation (peer access is

@@ -168,6 +168,9 @@ PHILOX_CASES = {
     "T40_d20": (40, 48, 20, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 4, -10, 10),
     "T70": (70, 32, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 5, -5, 5),
     "T128": (128, 32, 8, c2_like, [dict(kind="stretch", a=2.0)], [1.0], 4, -10, 10),
+    "gmix_d8": (4, 256, 8, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -10, 10),
+    "gmix_k6_d20": (3, 128, 20, lambda d: gmix_like(d, K=6, seed=8), [dict(kind="stretch", a=2.0)], [1.0], 5, -10, 10),
+    "gmix_tight_d20": (3, 128, 20, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -3.2, 3.2),
     "W_small": (3, 16, 3, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 10, -5, 5),
     "W_257": (2, 257, 5, lambda d: orc.RosenbrockLike(), [dict(kind="stretch", a=2.0)], [1.0], 6, -5, 5),
 }
@@ -249,6 +252,46 @@ def test_philox_accept_masks_bit_exact_c2():
     for _ in range(3):
         tot += o2.iterate(st)
     assert np.array_equal(smp.moves[0].accepted, tot)
+
+
+@pytest.fixture
+def k1_lanes(monkeypatch):
+    """force a variant of the stretch kernel (EB_K1_LPW is read at every launch): 1 = one thread per walker,
+    2 / 4 = the lane-split kernel (csrc/stretch_lanes.cuh) that the library picks by itself only for HBM-sized shapes"""
+    def force(lpw):
+        monkeypatch.setenv("EB_K1_LPW", str(lpw))
+    return force
+
+
+@pytest.mark.parametrize("lpw,name", [(4, "c2_full"), (2, "c2_full"), (4, "c3_full"), (2, "c3_full"), (4, "c4_slice"),
+                                      (4, "tight"), (2, "tight"), (4, "T40_d20"), (4, "gmix_d8"), (4, "gmix_k6_d20"),
+                                      (4, "gmix_tight_d20"), (2, "gmix_d8")])
+def test_lane_split_stretch_kernel_matches_oracle(k1_lanes, lpw, name):
+    """the lane-split stretch kernel (2 / 4 lanes per walker) against the oracle: every likelihood functor, priors tight
+    enough that many proposals leave the box, more mixture components than lanes, exact row lengths 8 and 20"""
+    k1_lanes(lpw)
+    run_philox_case(*PHILOX_CASES[name])
+
+
+@pytest.mark.parametrize("lpw", [2, 4])
+def test_lane_split_stretch_kernel_periodic_and_replay(k1_lanes, lpw):
+    k1_lanes(lpw)
+    d, T, W = 8, 4, 256
+    periods = np.zeros(d)
+    periods[[0, 2, d - 1]] = [3.0, 2 * np.pi, 1.5]
+    mu = np.linspace(0.1, 1.4, d)
+    run_philox_case(T, W, d, lambda dd: orc.GaussianLike(mu, np.eye(dd) / 0.3), [dict(kind="stretch", a=2.0)], [1.0], 10,
+                    0.0, 7.0, periods=periods)
+    for name in ("c2_small", "c2_tightprior"):   # replay mode against the reference's golden vectors (8-d)
+        test_replay_matches_reference_golden(name)
+
+
+def test_philox_config4_full_size():
+    """BASELINE config 4 at full size on one GPU: 32 temperatures x 16384 walkers x 20-d mixture of 4 Gaussians,
+    StretchMove + PT swaps + adaptation, production streams against the oracle (the lane-split stretch kernel is what
+    the library launches at this size; the swap pass moves 20-double rows over 32 rungs)."""
+    smp, osmp = run_philox_case(32, 16384, 20, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 2, -10, 10, seed=31)
+    assert osmp.swaps_accepted.sum() > 0
 
 
 # ----------------------------------------------------------------------------------------------------

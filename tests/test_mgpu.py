@@ -54,7 +54,7 @@ def _oracle(T, W, d, nit, seed, mix):
                                                 ("fused", 16, 4096, 0), ("p2p", 16, 4096, 0), ("fused", 72, 64, 0),
                                                 ("fused", 128, 48, 0), ("fused", 32, 16384, 0),
                                                 ("split", 4, 256, 0), ("split", 5, 99, 1), ("split", 16, 4096, 0),
-                                                ("split", 128, 48, 0)])
+                                                ("split", 128, 48, 0), ("split", 32, 16384, 0), ("split", 7, 1000, 1)])
 def test_sharded_run_matches_unsharded_oracle(tmp_path, comm, T, W, mix):
     _run_and_compare(tmp_path, comm, T, W, mix, nproc=2)
 

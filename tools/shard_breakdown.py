@@ -35,7 +35,7 @@ def main():
     P = np.linalg.inv(A @ A.T / d + np.eye(d))
     pri = ProbDistContainer({i: uniform_dist(-10.0, 10.0) for i in range(d)})
     prof = bool(os.environ.get("ERYN_B200_LIB"))
-    modes = os.environ.get("EB_BREAKDOWN_MODES", "fused,p2p").split(",")
+    modes = os.environ.get("EB_BREAKDOWN_MODES", "split,fused").split(",")
     for comm in modes:
         ctx = DeviceContext(pri, GaussianLikelihood(np.zeros(d), P), rng="philox", seed=1)
         run = ed.ShardedRun(ctx, T, W, comm=comm)
@@ -76,7 +76,8 @@ def main():
         if prof:
             mn, mx = (ctypes.c_uint64 * 64)(), (ctypes.c_uint64 * 64)()
             sn, sx = (ctypes.c_uint64 * 64)(), (ctypes.c_uint64 * 64)()
-            if run.lib.eb_debug_marks_swap_global(mn, mx, 0) == 0 and run.lib.eb_debug_marks_stretch_global(sn, sx, 0) == 0:
+            rd = "eb_debug_marks_split" if comm == "split" else "eb_debug_marks_swap"
+            if getattr(run.lib, rd + "_global")(mn, mx, 0) == 0 and run.lib.eb_debug_marks_stretch_global(sn, sx, 0) == 0:
                 base = sn[0]
                 f = lambda v: int(v) - int(base)
                 print(f"[{comm}] rank {rank} timeline ns: K1b start 0 end {f(sn[7])} lastCTA-end {f(sx[7])} | swap start {f(mn[16])} "
@@ -85,9 +86,9 @@ def main():
                       f"folded {f(mx[29])} betas {f(mx[30])} done {f(mx[23])}",
                       flush=True)
             cta = (ctypes.c_uint64 * (8 * 1024))()
-            if hasattr(run.lib, "eb_debug_marks_swap_cta") and run.lib.eb_debug_marks_swap_cta(cta) == 0:
+            if hasattr(run.lib, rd + "_cta") and getattr(run.lib, rd + "_cta")(cta) == 0:
                 a = np.frombuffer(cta, dtype=np.uint64).reshape(8, 1024).astype(np.int64)
-                nreal = (W + 7) // 8 if T > 16 else (W + 15) // 16
+                nreal = (W + 7) // 8 if (T > 16 or comm == "split") else (W + 15) // 16
                 names = {0: "start", 1: "keys", 2: "gathered", 3: "cascade", 4: "counts", 7: "mail-pushed", 5: "rows"}
                 txt = []
                 for slot in (0, 1, 2, 3, 4, 7, 5):
