@@ -514,7 +514,12 @@ def run_gpu(args):
         except Exception as e:  # reported, never silently dropped
             extra["c5"] = dict(error=f"{type(e).__name__}: {e}")
         extra["api"] = bench_api(wl, dev, store=True)
+        extra["api_thin100"] = bench_api(wl, dev, nsteps=10, thin_by=100, store=True)
         extra["api_not_stored"] = bench_api(wl, dev, store=False)
+        extra["api"]["note"] = ("stored: every 25th iteration leaves as a 5.3 MB sample; the GPU side is a pack kernel + an "
+                                "asynchronous copy, the host side is Backend.save_step's copy into freshly grown chain memory "
+                                "(first-touch page faults, ~1 us per 4 KiB page on one host thread) — the cost the reference's "
+                                "own save_step pays; api_thin100 stores 4x less often, api_not_stored not at all")
 
     # ---- e2e: C-ABI call with HOST buffers, one iteration per call ------------------------------------------
     lib = _lib.load()
@@ -673,7 +678,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--comm", default="split", choices=["fused", "split", "p2p", "nccl"], help="multi-GPU swap pass (N > 1)")
+    ap.add_argument("--comm", default="auto", choices=["auto", "fused", "split", "p2p", "nccl"],
+                    help="multi-GPU swap pass (N > 1); auto = fused at 2 GPUs, chain-split beyond")
     ap.add_argument("--profile", action="store_true", help="shorten the CPU-baseline leg and skip the extras (for runs under ncu)")
     a = ap.parse_args()
     if a.warmup < 3:

@@ -40,12 +40,14 @@ class eb_like(C.Structure):
 class eb_stretch_rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("randomize_split", C.c_int32), ("pdl_chain", C.c_int32), ("_pad", C.c_int32),
                 ("list", vp * 2), ("rint", vp * 2), ("u_z", vp * 2), ("u_acc", vp * 2),
-                ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+                ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64),
+                ("gibbs_mask", C.c_uint32), ("gibbs_ndim", C.c_int32), ("gibbs_index", C.c_int32), ("_pad2", C.c_int32)]
 
 
 class eb_gauss_rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("cov_kind", C.c_int32), ("scale", C.c_double), ("chol", vp), ("delta", vp),
-                ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+                ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64),
+                ("gibbs_mask", C.c_uint32), ("gibbs_index", C.c_int32)]
 
 
 class eb_swap_rng(C.Structure):
@@ -138,8 +140,9 @@ class eb_mb_group_rng(C.Structure):
 
 
 class eb_mb_rj_rng(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("_pad", C.c_int32), ("change", vp), ("leaf", vp), ("birth", vp * EB_MAX_BRANCHES),
-                ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+    _fields_ = [("mode", C.c_int32), ("branch_mask", C.c_uint32), ("change", vp), ("leaf", vp), ("birth", vp * EB_MAX_BRANCHES),
+                ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64),
+                ("gibbs_index", C.c_int32), ("_pad2", C.c_int32)]
 
 
 # every symbol include/eryn_b200.h declares: name -> (restype, argtypes)

@@ -6,7 +6,6 @@ from .state import State
 
 __all__ = ["Backend"]
 
-
 class Backend(object):
     def __init__(self, store_missing_leaves=np.nan):
         self.initialized = False
@@ -47,15 +46,22 @@ class Backend(object):
         return {n: (self.ntemps, self.nwalkers, self.nleaves_max[n], self.ndims[n]) for n in self.branch_names}
 
     def grow(self, ngrow, blobs=None):
+        """backend.py:993-1012.  The new part of every array is left untouched (np.empty, no concatenate with a dummy
+        block): its pages are first touched when a sample is stored."""
         i = ngrow - (len(self.log_like) - self.iteration)
         if i <= 0:
             return
+
+        def grown(arr):
+            new = np.empty((len(arr) + i,) + arr.shape[1:], dtype=arr.dtype)
+            new[:len(arr)] = arr
+            return new
         for n in self.branch_names:
-            self.chain[n] = np.concatenate([self.chain[n], np.empty((i,) + self.chain[n].shape[1:])], axis=0)
-            self.inds[n] = np.concatenate([self.inds[n], np.empty((i,) + self.inds[n].shape[1:], dtype=bool)], axis=0)
-        self.log_like = np.concatenate([self.log_like, np.empty((i, self.ntemps, self.nwalkers))], axis=0)
-        self.log_prior = np.concatenate([self.log_prior, np.empty((i, self.ntemps, self.nwalkers))], axis=0)
-        self.betas = np.concatenate([self.betas, np.empty((i, self.ntemps))], axis=0)
+            self.chain[n] = grown(self.chain[n])
+            self.inds[n] = grown(self.inds[n])
+        self.log_like = grown(self.log_like)
+        self.log_prior = grown(self.log_prior)
+        self.betas = grown(self.betas)
 
     def save_step(self, state, accepted, rj_accepted=None, swaps_accepted=None, moves_accepted_fraction=None):
         it = self.iteration

@@ -12,6 +12,7 @@ struct GaussArgs {
   int philox;
   uint32_t seed_lo, seed_hi; const unsigned long long* iter_dev; unsigned long long iter;
   uint8_t* accepted; uint32_t* accepted_count;
+  uint32_t gmask; int gidx;   // Gibbs split (mh.py:77-183): parameters that change (0 = all), index of the split
 };
 
 template <int DMAX, int LIKE, bool PHILOX, bool EXACT>
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
 #pragma unroll
     for (int j = 0; j < DMAX; j += 2) {
       if (EXACT || j < D) {
-        const uint4 r = stream(key, TAG_GAUSS, (uint32_t)(tid + c.t0 * c.W), (uint32_t)(j >> 1));
+        const uint4 r = stream(key, TAG_GAUSS, (uint32_t)(tid + c.t0 * c.W), (uint32_t)(j >> 1) | ((uint32_t)p.gidx << 16));
         const double rad = sqrt(-2.0 * log(u01_52(r.x, r.y)));
         double sn, cs;
         sincos(6.283185307179586 * u01_52(r.z, r.w), &sn, &cs);
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
           }
       }
     }
-    const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)(tid + c.t0 * c.W), 0u);
+    const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)(tid + c.t0 * c.W), (uint32_t)p.gidx << 16);
     u_acc = u01_52(ra.x, ra.y);
   } else {
     const double* dl = p.delta + (size_t)tid * D;
@@ -100,6 +101,12 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
 #pragma unroll
     for (int j = 0; j < DMAX; ++j)
       if ((EXACT || j < D) && sm[3 * D + j] > 0.0) q[j] = np_mod(q[j], sm[3 * D + j]);
+  }
+  if (p.gmask) {   // Gibbs split: the other parameters keep their values (cleanup_proposals_gibbs, move.py:302-307)
+    const double* old = c.coords + (size_t)tid * D;
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if ((EXACT || j < D) && !((p.gmask >> j) & 1u)) q[j] = old[j];
   }
   const double ll0 = c.logl[tid], lp0 = c.logp[tid];
   const bool tempered = c.betas != nullptr;
@@ -181,6 +188,10 @@ int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* l
   args.seed_lo = (uint32_t)(rng->seed & 0xFFFFFFFFull); args.seed_hi = (uint32_t)(rng->seed >> 32);
   args.iter_dev = (const unsigned long long*)rng->iter_dev; args.iter = rng->iter;
   args.accepted = accepted; args.accepted_count = accepted_count;
+  args.gmask = rng->gibbs_mask; args.gidx = rng->gibbs_index;
+  if (args.gmask && rng->cov_kind == 2) return fail(EB_ERR_UNSUPPORTED, "DistributionGenerate has no Gibbs splits on the device");
+  if (args.gmask && st->nleaves != 1) return fail(EB_ERR_UNSUPPORTED, "Gibbs splits address the parameters of one leaf");
+  if (args.gidx < 0 || args.gidx > 0xFFFF) return fail(EB_ERR_INVALID, "gibbs_index out of range");
   if (args.philox) {
     if (rng->cov_kind == 1 && !rng->chol) return fail(EB_ERR_INVALID, "matrix proposal needs the Cholesky factor");
     if (rng->cov_kind < 0 || rng->cov_kind > 2) return fail(EB_ERR_INVALID, "Invalid proposal scale dimensions");

@@ -31,6 +31,7 @@ struct MBArgs {
   const int32_t* pick; const double* u_z; const double* u_acc;
   const int32_t* change; const int32_t* leaf; const double* birth[EB_MAX_BRANCHES];
   uint8_t* accepted; uint32_t* accepted_count;
+  uint32_t bmask; int gidx;   // reversible jump: Gibbs split over branches (0 = all), index of the split (stream key)
 };
 
 struct WarpSm {
@@ -46,7 +47,7 @@ __device__ __forceinline__ int branch_of(const MBArgs& p, int j) {
 }
 
 // log-prior and gated log-like of the row in ws.q with the leaf flags in ws.flags; every lane gets the results
-__device__ __forceinline__ void mb_eval(const MBArgs& p, WarpSm& ws, int lane, double& lp, double& ll) {
+__device__ __forceinline__ void mb_eval(const MBArgs& p, WarpSm& ws, int lane, double& lp, double& ll, uint32_t bmask = 0u) {
   // ---- prior: one leaf per lane; parameters added in index order starting from 0.0 (prior.py:369-385)
   for (int j = lane; j < p.Ltot; j += 32) {
     const int b = branch_of(p, j);
@@ -73,6 +74,14 @@ __device__ __forceinline__ void mb_eval(const MBArgs& p, WarpSm& ws, int lane, d
       any_leaf |= ws.flags[p.loff[b] + l] != 0;
     }
     lp += sb;
+  }
+  if (bmask) {   // fix_logp_gibbs (move.py:369-402): leaves of the branches of this Gibbs split vs all leaves
+    bool here = false;
+    for (int b = 0; b < p.nb; ++b)
+      if ((bmask >> b) & 1u)
+        for (int l = 0; l < p.L[b]; ++l) here |= ws.flags[p.loff[b] + l] != 0;
+    if (any_leaf && !here) lp = neg_inf();    // no use in running because no change
+    if (!any_leaf && !here) lp = 0.0;         // there is nothing in the model currently
   }
   // ---- likelihood: not evaluated outside the prior or without leaves (ensemble.py:1279-1282, :1486-1513)
   if (isinf(lp) || !any_leaf) {
@@ -113,9 +122,9 @@ __device__ __forceinline__ void mb_load_walker(const MBArgs& p, WarpSm& ws, size
 
 // Metropolis test + Move.update (move.py:472-703) for the proposal staged in ws
 __device__ __forceinline__ void mb_accept(const MBArgs& p, WarpSm& ws, size_t slot, int t, int lane, double factors,
-                                          double u_acc, bool flags_changed) {
+                                          double u_acc, bool flags_changed, uint32_t bmask = 0u) {
   double lp, ll;
-  mb_eval(p, ws, lane, lp, ll);
+  mb_eval(p, ws, lane, lp, ll, bmask);
   const bool tempered = p.betas != nullptr;
   const double beta = tempered ? p.betas[t] : 1.0;
   const double logP = log_posterior(ll, lp, beta, tempered);
@@ -270,7 +279,7 @@ __global__ void __launch_bounds__(MB_THREADS) mb_rj_kernel(const __grid_constant
   // arms into ONE global load whose address may then point into parameter space)
   if (p.iter_dev) it = ld_volatile_u64(p.iter_dev);
     key = make_rng_key(p.seed_lo, p.seed_hi, it);
-    const uint4 r = stream(key, TAG_RJ, fw, 0u);
+    const uint4 r = stream(key, TAG_RJ, fw, (uint32_t)p.gidx << 8);
     u_acc = u01_52(r.z, r.w);
   } else {
     u_acc = p.u_acc[slot];
@@ -281,11 +290,12 @@ __global__ void __launch_bounds__(MB_THREADS) mb_rj_kernel(const __grid_constant
     for (int b = 0; b < p.nb; ++b) {
       const int L = p.L[b], nmin = p.nmin[b], nmax = L;
       if (nmin == nmax) continue;                                          // distgenrj.py:166-167
+      if (p.bmask && !((p.bmask >> b) & 1u)) continue;                     // not in this Gibbs split (rj.py:168-176)
       int nl = 0;
       for (int l = 0; l < L; ++l) nl += ws.flags[p.loff[b] + l] ? 1 : 0;
       int change, lf;
       if (p.philox) {
-        const uint4 r = stream(key, TAG_RJ, fw, (uint32_t)(8 * b));
+        const uint4 r = stream(key, TAG_RJ, fw, (uint32_t)(8 * b) | ((uint32_t)p.gidx << 8));
         change = (r.x & 1u) ? +1 : -1;                                     // distgenrj.py:62
         if (nl == nmin) change = +1;                                       // :67-71
         if (nl == nmax) change = -1;
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(MB_THREADS) mb_rj_kernel(const __grid_constant
         ws.flags[p.loff[b] + lf] = 1;
         for (int d = 0; d < p.D[b]; ++d) {
           if (p.philox) {
-            const uint4 r = stream(key, TAG_RJ, fw, (uint32_t)(8 * b + 1 + (d >> 1)));
+            const uint4 r = stream(key, TAG_RJ, fw, (uint32_t)(8 * b + 1 + (d >> 1)) | ((uint32_t)p.gidx << 8));
             const double u = (d & 1) ? u01_52(r.z, r.w) : u01_52(r.x, r.y);
             const double l = p.lo[p.poff[b] + d], h = p.hi[p.poff[b] + d];
             x[d] = u * (h - l) + l;                                        // prior.py:66
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(MB_THREADS) mb_rj_kernel(const __grid_constant
     s_factors[wid] = factors + edge;                                       // rj.py:273
   }
   __syncwarp();
-  mb_accept(p, ws, slot, t, lane, s_factors[wid], u_acc, true);
+  mb_accept(p, ws, slot, t, lane, s_factors[wid], u_acc, true, p.bmask);
 }
 
 static int fill_mb(MBArgs& a, const eb_mb_layout* lay, const eb_mb_state* st, const eb_prior* prior,
@@ -454,20 +464,25 @@ int eb_mb_rj_step(const eb_mb_layout* lay, const eb_mb_state* st, const eb_prior
   int rc = fill_mb(a, lay, st, prior, data, true);
   if (rc) return rc;
   if (!rng || !accepted) return fail(EB_ERR_INVALID, "rng/accepted is NULL");
+  const uint32_t bm = rng->branch_mask;
   if (rng->mode == EB_RNG_PHILOX) {
     fill_philox(a, rng->seed, rng->iter_dev, rng->iter);
   } else if (rng->mode == EB_RNG_REPLAY) {
     if (!rng->change || !rng->leaf || !rng->u_acc) return fail(EB_ERR_INVALID, "replay mode needs change, leaf, u_acc");
     a.change = rng->change; a.leaf = rng->leaf; a.u_acc = rng->u_acc;
     for (int b = 0; b < a.nb; ++b) {
-      if (a.nmin[b] != a.L[b] && !rng->birth[b]) return fail(EB_ERR_INVALID, "replay mode needs the birth draws of branch %d", b);
+      if (a.nmin[b] != a.L[b] && (!bm || ((bm >> b) & 1u)) && !rng->birth[b])
+        return fail(EB_ERR_INVALID, "replay mode needs the birth draws of branch %d", b);
       a.birth[b] = rng->birth[b];
     }
   } else {
     return fail(EB_ERR_INVALID, "unknown rng mode %d", rng->mode);
   }
+  a.bmask = rng->branch_mask; a.gidx = rng->gibbs_index;
+  if (a.nb < 32 && (a.bmask >> a.nb)) return fail(EB_ERR_INVALID, "branch_mask selects branches the layout does not have");
+  if (a.gidx < 0 || a.gidx > 0xFFFF) return fail(EB_ERR_INVALID, "gibbs_index out of range");
   bool any = false;
-  for (int b = 0; b < a.nb; ++b) any |= a.nmin[b] != a.L[b];
+  for (int b = 0; b < a.nb; ++b) any |= a.nmin[b] != a.L[b] && (!a.bmask || ((a.bmask >> b) & 1u));
   if (!any)
     return fail(EB_ERR_INVALID, "Right now, no models are getting a reversible jump proposal. Check nleaves_min and "
                                 "nleaves_max or do not use rj proposal.");

@@ -25,6 +25,8 @@ struct StretchArgs {
   int both;        // 1: both halves in this launch (one CTA per temperature); 0: only `split`
   int split;
   int pdl;         // this launch carries the programmatic-stream-serialization attribute
+  uint32_t gmask;  // Gibbs split: parameters that move (0 = all), number of them, index of the split in this propose call
+  int gndim, gidx;
   int Ns[2];
   // replay
   const int32_t* list[2]; const long long* rint[2]; const double* u_z[2]; const double* u_acc[2];
@@ -43,7 +45,7 @@ __device__ __forceinline__ void stretch_draw(const StretchArgs& p, const RngKey&
                                              int s, int& w, int& wc, double& u_z, double& u_acc) {
   if (PHILOX) {
     const uint32_t pos = 2u * (uint32_t)k + (uint32_t)s;                     // red_blue.py:121-124
-    const uint4 r = stream(key, TAG_STRETCH, pos, (uint32_t)(p.c.t0 + t));
+    const uint4 r = stream(key, TAG_STRETCH, pos, (uint32_t)(p.c.t0 + t) | ((uint32_t)p.gidx << 16));
     uint32_t rint;
     split_draw(r.x, r.y, (uint32_t)p.Ns[1 - s], rint, u_z);                  // stretch.py:93, :131
     u_acc = u01_52(r.z, r.w);                                                // red_blue.py:294
@@ -82,6 +84,8 @@ __device__ __forceinline__ void job_draw(const StretchArgs& p, const RngKey& key
   zz = zz * zz / p.a;
   j.zz = zz;
   j.factors = ((double)LD - 1.0) * log(zz);                                  // stretch.py:223
+  if (p.gmask && p.gndim != LD)                                              // stretch.py:55-72 adjust_factors (Gibbs split)
+    j.factors = j.factors / ((double)LD - 1.0) * ((double)p.gndim - 1.0);
   j.log_u = log(u_acc);                                                      // red_blue.py:294
 }
 
@@ -121,12 +125,16 @@ __device__ __forceinline__ void job_finish(const StretchArgs& p, const double* s
         }
         double v = cc[d] - diff * j.zz;                                       // stretch.py:145
         if (P > 0.0) v = np_mod(v, P);
+        if (p.gmask && !((p.gmask >> d) & 1u)) v = s0;                        // move.py:302-307 (Gibbs split)
         j.q[d] = v;
       }
   } else {
 #pragma unroll
     for (int d = 0; d < DMAX; ++d)
-      if (EXACT || d < LD) j.q[d] = cc[d] - (cc[d] - j.q[d]) * j.zz;         // stretch.py:143-145
+      if (EXACT || d < LD) {
+        const double v = cc[d] - (cc[d] - j.q[d]) * j.zz;                     // stretch.py:143-145
+        j.q[d] = (p.gmask && !((p.gmask >> d) & 1u)) ? j.q[d] : v;            // move.py:302-307 (Gibbs split)
+      }
   }
   double lp, ll;
   eval_point<DMAX, LIKE, EXACT>(j.q, c, sm, j.active, lp, ll);               // red_blue.py:260,270
@@ -138,9 +146,12 @@ __device__ __forceinline__ void job_finish(const StretchArgs& p, const double* s
     store_row<DMAX>(c.coords + slot * LD, LD, j.q);
     c.logl[slot] = ll;
     c.logp[slot] = isinf(lp) ? 0.0 : lp;
-    if (p.accepted_count) p.accepted_count[slot] += 1u;
   }
-  p.accepted[slot] = keep ? 1 : 0;
+  // from the second Gibbs split of a propose call on, the reported mask is the running OR over the splits and the counter
+  // grows by that OR (red_blue.py:296-309, :325)
+  const bool rep = keep || (p.gidx > 0 && p.accepted[slot] != 0);
+  if (p.accepted_count && rep) p.accepted_count[slot] += 1u;
+  p.accepted[slot] = rep ? 1 : 0;
 }
 
 // programmatic dependent launch (PDL): the next kernel in the stream may start its state-independent prologue once
@@ -339,7 +350,7 @@ static int launch_stretch_kernel(K kernel, const StretchArgs& a, size_t sb, cuda
 static int stretch_variant_for(const StretchArgs& a) {
   const char* env = getenv("EB_K1_LPW");
   const int forced = env ? atoi(env) : 0;
-  if (a.both || a.c.L != 1 || (a.c.LD != 8 && a.c.LD != 20)) return 0;
+  if (a.both || a.gmask || a.c.L != 1 || (a.c.LD != 8 && a.c.LD != 20)) return 0;
   if (forced == 1) return 0;
   if (forced == 2 && a.c.LD == 8) return 2;
   if (forced == 2 || forced == 4) return 4;
@@ -412,6 +423,14 @@ static int fill_stretch_args(StretchArgs& a, const eb_state* st, double stretch_
   a.q_out = nullptr; a.factors_out = nullptr; a.sub_out = nullptr;
   a.accepted = nullptr; a.accepted_count = nullptr;
   a.both = 0; a.split = 0; a.pdl = 0;
+  a.gmask = rng->gibbs_mask; a.gndim = rng->gibbs_ndim; a.gidx = rng->gibbs_index;
+  if (a.gmask) {
+    const int LD = st->nleaves * st->ndim;
+    if (st->nleaves != 1) return fail(EB_ERR_UNSUPPORTED, "Gibbs splits of the fused stretch kernel address the parameters of one leaf");
+    if (LD < 32 && (a.gmask >> LD)) return fail(EB_ERR_INVALID, "gibbs_mask selects parameters beyond ndim");
+    if (a.gndim != __builtin_popcount(a.gmask)) return fail(EB_ERR_INVALID, "gibbs_ndim must count the bits of gibbs_mask");
+  }
+  if (a.gidx < 0 || a.gidx > 0xFFFF) return fail(EB_ERR_INVALID, "gibbs_index out of range");
   if (rng->pdl_chain && rng->mode != EB_RNG_PHILOX) return fail(EB_ERR_INVALID, "pdl_chain is a philox-mode option");
   if (rng->mode == EB_RNG_REPLAY) {
     for (int s = 0; s < 2; ++s)
@@ -469,6 +488,7 @@ int eb_stretch_propose(const eb_state* st, double a, int32_t split, const eb_str
   rc = fill_stretch_args(args, st, a, rng, false);
   if (rc) return rc;
   if (split != 0 && split != 1) return fail(EB_ERR_INVALID, "split must be 0 or 1 (nsplits == 2)");
+  if (rng->gibbs_mask) return fail(EB_ERR_UNSUPPORTED, "Gibbs splits run in the fused kernels");
   if (!q || !factors || !sub_out) return fail(EB_ERR_INVALID, "q/factors/sub_out is NULL");
   args.split = split;
   args.q_out = q; args.factors_out = factors; args.sub_out = sub_out;

@@ -41,6 +41,7 @@ struct Args {
   Common c;                       // destination (alternate) buffers of this rank: rungs [t_lo, t_hi)
   int T, world, rank, t_lo, t_hi, permute, Wr;   // Wr = chains a rank resolves at most = ceil(W / world)
   int gpc;                        // chain groups per CTA (shared-memory layout)
+  int nl;                         // lanes per chain in the phases A / C1 / C2 (4..32): a warp takes 32 / nl chains at a time
   int temp_begin[EB_MAX_RANKS + 1];
   const double* coords_cur; const double* logl_cur; const double* logp_cur;   // this rank's CURRENT buffers
   double* betas;                  // [T] local copy of the full ladder, adapted identically on every rank
@@ -57,16 +58,16 @@ struct Layout {  // byte offsets into dynamic shared memory
   size_t betas, dts, ll, lu, keys, pos, sel, cnt, band, rej, total;
 };
 // gpc = chain groups per CTA (the grid is capped at what is resident; a CTA loops over its groups phase by phase)
-__host__ __device__ inline Layout layout(int T, int nown, int gpc) {
+__host__ __device__ inline Layout layout(int T, int nown, int gpc, int cpw) {
   Layout s;
   size_t o = 0;
   s.betas = o; o += sizeof(double) * T;
   s.dts = o; o += sizeof(double) * T;
   s.ll = o; o += sizeof(double) * T * CPB;
   s.lu = o; o += sizeof(double) * T * CPB;
-  s.sel = o; o += sizeof(unsigned long long) * 2 * CPB * gpc;
+  s.sel = o; o += sizeof(unsigned long long) * 2 * CPB * cpw * gpc;
   s.keys = o; o += sizeof(uint32_t) * FEISTEL_ROUNDS * nown;
-  s.pos = o; o += sizeof(int) * nown * CPB * gpc;
+  s.pos = o; o += sizeof(int) * nown * CPB * cpw * gpc;
   s.cnt = o; o += sizeof(int) * T;
   s.band = o; o += (size_t)T * CPB;
   s.rej = o; o += (size_t)T * CPB;
@@ -220,12 +221,12 @@ __device__ __forceinline__ void adapt_cta_work(const Args& p, int nreal, unsigne
 
 // One chain's share of phase A: positions on this rank's rungs, and the log-likelihood found there goes to the chain's
 // resolver.  `pos` (shared memory, nown ints) is kept for phases C1 / C2.
-__device__ __forceinline__ void phase_a(const Args& p, const uint32_t* s_keys, int chain, int lane, int nown, uint32_t tag,
-                                        int* pos) {
+__device__ __forceinline__ void phase_a(const Args& p, const uint32_t* s_keys, int chain, int sub, int nl, int nown,
+                                        uint32_t tag, int* pos) {
   const int W = p.c.W;
   const int h = chain % p.world;
   const size_t cslot = (size_t)(chain / p.world);
-  for (int k = lane; k < nown; k += 32) {
+  for (int k = sub; k < nown; k += nl) {
     int pz = chain;
     if (p.permute) {
       Feistel sig;
@@ -354,7 +355,8 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
   const Common& c = p.c;
   const int T = p.T, W = c.W, LD = c.LD;
   const int nown = p.t_hi - p.t_lo;
-  const Layout lay = layout(T, nown, p.gpc);
+  const int NL = p.nl, CPW = 32 / NL, GC = CPB * CPW;   // lanes per chain, chains per warp, chains per group
+  const Layout lay = layout(T, nown, p.gpc, CPW);
   double* s_betas = reinterpret_cast<double*>(smraw + lay.betas);
   double* s_dts = reinterpret_cast<double*>(smraw + lay.dts);
   uint32_t* s_keys = reinterpret_cast<uint32_t*>(smraw + lay.keys);
@@ -362,7 +364,8 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
 
   const bool adapt_cta = blockIdx.x == gridDim.x - 1;   // one extra CTA without chains (D)
   const int nctas = (int)gridDim.x - 1;
-  const int ngroups = (W + CPB - 1) / CPB;
+  const int ngroups = (W + GC - 1) / GC;
+  const int sub = (threadIdx.x & 31) % NL, cw = (threadIdx.x & 31) / NL;   // lane within its chain, chain within the warp
   const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
   eb_ctrl* ctrl = p.ctrl;
   long long time_now = 0;
@@ -391,8 +394,8 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
   double* lu = reinterpret_cast<double*>(smraw + lay.lu) + (size_t)g * T;
   unsigned char* sband = smraw + lay.band + (size_t)g * T;
   unsigned char* s_rej = smraw + lay.rej + (size_t)g * T;
-  int* pos_all = reinterpret_cast<int*>(smraw + lay.pos);                            // [gpc][CPB][nown]
-  unsigned long long* sel_all = reinterpret_cast<unsigned long long*>(smraw + lay.sel);   // [gpc][CPB][2]
+  int* pos_all = reinterpret_cast<int*>(smraw + lay.pos);                            // [gpc][GC][nown]
+  unsigned long long* sel_all = reinterpret_cast<unsigned long long*>(smraw + lay.sel);   // [gpc][GC][2]
   bool ok = *reinterpret_cast<volatile unsigned int*>(&ctrl->error) == 0u;
   const long long t_start = clock64();
 
@@ -400,8 +403,8 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
   if (!adapt_cta) {
     int gi = 0;
     for (int grp = blockIdx.x; grp < ngroups; grp += nctas, ++gi) {
-      const int chain = grp * CPB + g;
-      if (chain < W) phase_a(p, s_keys, chain, lane, nown, tag, pos_all + ((size_t)gi * CPB + g) * nown);
+      const int ci = g * CPW + cw, chain = grp * GC + ci;
+      if (chain < W) phase_a(p, s_keys, chain, sub, NL, nown, tag, pos_all + ((size_t)gi * GC + ci) * nown);
     }
   }
   __syncwarp();               // pos[] of the chain is read by all lanes below
@@ -410,11 +413,12 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
 
   // ---- B ----
   if (!adapt_cta) {
-    for (int grp = blockIdx.x; grp < ngroups; grp += nctas) {
-      const int chain = grp * CPB + g;
-      if (chain < W && (chain % p.world) == p.rank)    // uniform over the warp
-        phase_b(p, key, chain, lane, tag, ok, t_start, s_dts, ll, lu, sband, s_rej, s_cnt);
-    }
+    for (int grp = blockIdx.x; grp < ngroups; grp += nctas)
+      for (int c2 = 0; c2 < CPW; ++c2) {               // the whole warp resolves one chain at a time
+        const int chain = grp * GC + g * CPW + c2;
+        if (chain < W && (chain % p.world) == p.rank)  // uniform over the warp
+          phase_b(p, key, chain, lane, tag, ok, t_start, s_dts, ll, lu, sband, s_rej, s_cnt);
+      }
   }
   EB_MARK(19);
 
@@ -441,22 +445,22 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
   {
     int gi = 0;
     for (int grp = blockIdx.x; grp < ngroups; grp += nctas, ++gi) {
-      const int chain = grp * CPB + g;
+      const int ci = g * CPW + cw, chain = grp * GC + ci;
       if (chain >= W) continue;
-      const int* pos = pos_all + ((size_t)gi * CPB + g) * nown;
+      const int* pos = pos_all + ((size_t)gi * GC + ci) * nown;
       const uint4 a = poll_unit(p.bits_in + 2 * (size_t)chain, tag, ok, t_start, ctrl);
       const uint4 b = poll_unit(p.bits_in + 2 * (size_t)chain + 1, tag, ok, t_start, ctrl);
       const unsigned long long sel_lo = ((unsigned long long)a.z << 32) | a.x;
       const unsigned long long sel_hi = ((unsigned long long)b.z << 32) | b.x;
-      if (lane == 0) {
-        sel_all[((size_t)gi * CPB + g) * 2] = sel_lo;
-        sel_all[((size_t)gi * CPB + g) * 2 + 1] = sel_hi;
+      if (sub == 0) {
+        sel_all[((size_t)gi * GC + ci) * 2] = sel_lo;
+        sel_all[((size_t)gi * GC + ci) * 2 + 1] = sel_hi;
       }
       if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {          // up: my top rung's walker moves to rung t_hi
         const int gd = owner_of(p, p.t_hi);
         const size_t sslot = (size_t)(nown - 1) * W + pos[nown - 1];
         uint4* box = p.mail_dst[gd] + ((size_t)0 * W + chain) * MU;
-        for (int e = lane; e < MU; e += 32) {
+        for (int e = sub; e < MU; e += NL) {
           const double v = e < LD ? p.coords_cur[sslot * LD + e] : e == LD ? p.logp_cur[sslot] : p.logl_cur[sslot];
           st_volatile_u4(box + e, unit_of(v, tag));
         }
@@ -470,14 +474,14 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
           const int gd = owner_of(p, d);
           const size_t sslot = (size_t)(o - p.t_lo) * W + pos[o - p.t_lo];
           uint4* box = p.mail_dst[gd] + ((size_t)1 * W + chain) * MU;
-          for (int e = lane; e < MU; e += 32) {
+          for (int e = sub; e < MU; e += NL) {
             const double v = e < LD ? p.coords_cur[sslot * LD + e] : e == LD ? p.logp_cur[sslot] : p.logl_cur[sslot];
             st_volatile_u4(box + e, unit_of(v, tag));
           }
         }
       }
       // every owned slot is rewritten into the alternate buffers; sources on this rank are copied here
-      for (int r = p.t_lo + lane; r < p.t_hi; r += 32) {
+      for (int r = p.t_lo + sub; r < p.t_hi; r += NL) {
         const int s = swap_source(sel_lo, sel_hi, r, T);
         if (s < p.t_lo || s >= p.t_hi) continue;
         const size_t sslot = (size_t)(s - p.t_lo) * W + pos[s - p.t_lo];
@@ -496,11 +500,11 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
   {
     int gi = 0;
     for (int grp = blockIdx.x; grp < ngroups; grp += nctas, ++gi) {
-      const int chain = grp * CPB + g;
+      const int ci = g * CPW + cw, chain = grp * GC + ci;
       if (chain >= W) continue;
-      const int* pos = pos_all + ((size_t)gi * CPB + g) * nown;
-      const unsigned long long sel_lo = sel_all[((size_t)gi * CPB + g) * 2];
-      const unsigned long long sel_hi = sel_all[((size_t)gi * CPB + g) * 2 + 1];
+      const int* pos = pos_all + ((size_t)gi * GC + ci) * nown;
+      const unsigned long long sel_lo = sel_all[((size_t)gi * GC + ci) * 2];
+      const unsigned long long sel_hi = sel_all[((size_t)gi * GC + ci) * 2 + 1];
       int dest[2] = {-1, -1};
       if (p.t_lo >= 1 && sel_bit(sel_lo, sel_hi, p.t_lo)) dest[0] = p.t_lo;
       if (p.t_hi < T && sel_bit(sel_lo, sel_hi, p.t_hi)) {
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(THREADS) pt_swap_split_kernel(const __grid_con
         if (dest[dir] < 0) continue;
         const size_t dslot = (size_t)(dest[dir] - p.t_lo) * W + pos[dest[dir] - p.t_lo];
         const uint4* box = p.mail_in + ((size_t)dir * W + chain) * MU;
-        for (int e = lane; e < MU; e += 32) {
+        for (int e = sub; e < MU; e += NL) {
           const double x = unit_double(poll_unit(box + e, tag, ok, t_start, ctrl));
           if (e < LD) c.coords[dslot * LD + e] = x;
           else if (e == LD) c.logp[dslot] = x;
@@ -578,14 +582,17 @@ int eb_pt_swap_split(const eb_split* sp, const eb_state* dst, const eb_swap_rng*
   // Every CTA both feeds remote resolvers (A) and waits for remote ones (B, C): the grid must be resident at once, or
   // ranks would wait for each other's unscheduled CTAs.  A CTA takes gpc chain groups; gpc is the smallest count whose
   // grid fits (the shared-memory footprint grows with gpc, hence the loop).  Every rank computes the same grid.
-  const int ngroups = (a.c.W + split::CPB - 1) / split::CPB;
+  const int nown = a.t_hi - a.t_lo;
+  a.nl = nown <= 4 ? 4 : nown <= 8 ? 8 : nown <= 16 ? 16 : 32;   // lanes per chain where a lane works on one of the rank's rungs
+  const int cpw = 32 / a.nl;
+  const int ngroups = (a.c.W + split::CPB * cpw - 1) / (split::CPB * cpw);
   int dev = 0, sms = 0;
   EB_CUDA(cudaGetDevice(&dev));
   EB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   size_t sb = 0;
   unsigned grid = 0;
   for (int gpc = 1;; ++gpc) {
-    sb = split::layout(T, a.t_hi - a.t_lo, gpc).total;
+    sb = split::layout(T, nown, gpc, cpw).total;
     if (sb > 200 * 1024) return fail(EB_ERR_UNSUPPORTED, "chain-split pass: nwalkers %d does not fit a resident grid", a.c.W);
     rc = set_smem(split::pt_swap_split_kernel, sb);
     if (rc) return rc;

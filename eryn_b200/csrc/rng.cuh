@@ -55,18 +55,22 @@ __device__ __forceinline__ void split_draw(uint32_t lo, uint32_t hi, uint32_t n,
   frac = __dmul_rn(__dadd_rn((double)(f >> 12), 0.5), 2.220446049250313e-16);
 }
 
-// Keyed bijection of [0, n): 4-round balanced Feistel network on 2*hb bits + cycle walking.  The four
-// round keys are one Philox block.
+// Keyed bijection of [0, n): balanced Feistel network on 2*hb bits + cycle walking.  The four round keys are one Philox
+// block.  Domains of up to 6 bits (n <= 64) take eight rounds — rounds 4..7 reuse the keys offset by the golden-ratio
+// constant — because four rounds of a 1..3-bit round function reach too few permutations: the frequencies
+// P(sigma(p) = w) were measurably non-uniform there (chi-square test in tests/test_host_logic_cpu.py).  MCMC validity
+// needs only that the pairing is independent of the walkers' state; fairness is what the extra rounds buy.
 constexpr int FEISTEL_ROUNDS = 4;
 struct Feistel {
   uint32_t k[FEISTEL_ROUNDS];
-  uint32_t n, hb, mask;
+  uint32_t n, hb, mask, nr;
 
   __device__ __forceinline__ void set_size(uint32_t n_) {
     n = n_;
     uint32_t bits = (n_ <= 2u) ? 1u : (32u - (uint32_t)__clz((int)(n_ - 1u)));
     hb = (bits + 1u) >> 1;
     mask = (1u << hb) - 1u;
+    nr = hb <= 3u ? 8u : 4u;
   }
   // round keys of bijection number `idx` of stream `tag`
   static __device__ __forceinline__ void make_keys(const RngKey& key, uint32_t tag, uint32_t idx, uint32_t* k4) {
@@ -83,15 +87,18 @@ struct Feistel {
     for (int r = 0; r < FEISTEL_ROUNDS; ++r) k[r] = k4[r];
     set_size(n_);
   }
+  __device__ __forceinline__ uint32_t round_key(int r) const { return k[r & 3] + 0x9E3779B9u * (uint32_t)(r >> 2); }
   // inverse bijection: rounds undone last to first, cycle walking on the inverse permutation
   __device__ __forceinline__ uint32_t inv(uint32_t x) const {
     if (n <= 1u) return 0u;
     do {
       uint32_t L = x >> hb, R = x & mask;
 #pragma unroll
-      for (int r = FEISTEL_ROUNDS - 1; r >= 0; --r) {
-        uint32_t pl = R ^ (fmix32(L ^ k[r]) & mask);
-        R = L; L = pl;
+      for (int r = 2 * FEISTEL_ROUNDS - 1; r >= 0; --r) {
+        if ((uint32_t)r < nr) {
+          uint32_t pl = R ^ (fmix32(L ^ round_key(r)) & mask);
+          R = L; L = pl;
+        }
       }
       x = (L << hb) | R;
     } while (x >= n);
@@ -103,8 +110,15 @@ struct Feistel {
       uint32_t L = x >> hb, R = x & mask;
 #pragma unroll
       for (int r = 0; r < FEISTEL_ROUNDS; ++r) {
-        uint32_t nr = L ^ (fmix32(R ^ k[r]) & mask);
-        L = R; R = nr;
+        uint32_t nr_ = L ^ (fmix32(R ^ k[r]) & mask);
+        L = R; R = nr_;
+      }
+      if (nr > (uint32_t)FEISTEL_ROUNDS) {   // small domains only: four more rounds
+#pragma unroll
+        for (int r = FEISTEL_ROUNDS; r < 2 * FEISTEL_ROUNDS; ++r) {
+          uint32_t nr_ = L ^ (fmix32(R ^ round_key(r)) & mask);
+          L = R; R = nr_;
+        }
       }
       x = (L << hb) | R;
     } while (x >= n);

@@ -247,12 +247,16 @@ class DeviceContext(object):
                 r.u_z[s], r.u_acc[s] = _ptr(keep["u_z"][s]), _ptr(keep["u_acc"][s])
         return r, keep
 
-    def stretch_step(self, d, a, randomize_split=True, replay=None, accepted_count=None):
-        """StretchMove step, both halves fused (red_blue.py:148-323 + stretch.py:74-231 + move.py:472)."""
+    def stretch_step(self, d, a, randomize_split=True, replay=None, accepted_count=None, gibbs=None):
+        """StretchMove step, both halves fused (red_blue.py:148-323 + stretch.py:74-231 + move.py:472).
+        gibbs = (parameter mask bits, number of selected parameters, index of the split in this propose call)."""
         self._require_fused()
         T, W, L, D = d.shape
         st = d.c_struct()
         r, keep = self._stretch_rng(randomize_split, replay)
+        if gibbs is not None:
+            r.gibbs_mask, r.gibbs_ndim, r.gibbs_index = int(gibbs[0]), int(gibbs[1]), int(gibbs[2])
+            r.pdl_chain = 0 if gibbs[2] > 0 else r.pdl_chain  # only the first split follows the swap pass
         acc = self.accepted_mask(T, W)
         _lib.check(self.lib.eb_stretch_step(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c),
                                             float(a), C.byref(r), _ptr(acc), _ptr(accepted_count),
@@ -286,12 +290,14 @@ class DeviceContext(object):
             self.launches += 3
         return acc
 
-    def gaussian_step(self, d, proposal, replay=None, accepted_count=None):
-        """GaussianMove step, fused (mh.py:56-193 + gaussian.py:68-195)."""
+    def gaussian_step(self, d, proposal, replay=None, accepted_count=None, gibbs=None):
+        """GaussianMove step, fused (mh.py:56-193 + gaussian.py:68-195).  gibbs = (parameter mask bits, split index)."""
         self._require_fused()
         T, W, L, D = d.shape
         st = d.c_struct()
         r = _lib.eb_gauss_rng()
+        if gibbs is not None:
+            r.gibbs_mask, r.gibbs_index = int(gibbs[0]), int(gibbs[1])
         keep = None
         if replay is None:
             r.mode = _lib.EB_RNG_PHILOX

@@ -138,13 +138,18 @@ class ShardedRun(object):
     """One rank of a temperature-sharded run: the shared arena, the peer mappings and the two
     (current, alternate) DeviceStates."""
 
-    def __init__(self, ctx, ntemps, nwalkers, nleaves=1, group=None, comm="fused", mail=True):
+    def __init__(self, ctx, ntemps, nwalkers, nleaves=1, group=None, comm="auto", mail=True):
         import torch
         import torch.distributed as dist
         from . import _lib
         from .device import DeviceState
-        if comm not in ("fused", "split", "p2p", "nccl"):
-            raise ValueError("comm must be 'fused', 'split', 'p2p' or 'nccl'")
+        if comm not in ("auto", "fused", "split", "p2p", "nccl"):
+            raise ValueError("comm must be 'auto', 'fused', 'split', 'p2p' or 'nccl'")
+        if comm == "auto":
+            # two ranks: every rank resolves the whole ladder (two NVLink hops, the redundant half of the ladder is cheap);
+            # more ranks: every rank resolves 1/N of the chains (three hops, but work and inbound volume per rank do not
+            # grow with N) — measured crossover between N = 2 and N = 4 (profiles/README.md)
+            comm = "fused" if dist.get_world_size(group) <= 2 else "split"
         if ctx.rng != "philox":
             raise ValueError("temperature-sharded runs use the philox streams (replay mode is single-GPU)")
         self.ctx, self.group, self.comm = ctx, group, comm
@@ -367,7 +372,7 @@ def __getattr__(name):
 # ------------------------------------------------------------------------------------------------------
 # parity self-check of a sharded run (bench.py --gpus N prints it; tests/test_mgpu.py checks it against the oracle)
 # ------------------------------------------------------------------------------------------------------
-def sharded_parity_check(rank, world, local, comm="split", ntemps=None, nwalkers=256, ndim=8, nit=6, seed=4242,
+def sharded_parity_check(rank, world, local, comm="auto", ntemps=None, nwalkers=256, ndim=8, nit=6, seed=4242,
                          like=None, lo=-10.0, hi=10.0):
     """Run a short temperature-sharded chain over all ranks and the SAME chain unsharded on rank 0's GPU (same seed,
     same counter-based streams keyed by global temperature / chain) and compare every array of the final state.
@@ -401,6 +406,7 @@ def sharded_parity_check(rank, world, local, comm="split", ntemps=None, nwalkers
     full = run.gather()
     swaps = tc.swaps_accepted
     acc = gather_rows(mv.accepted, run.temp_begin)
+    comm_used = run.comm
     run.close()
     out = None
     if rank == 0:
@@ -426,7 +432,7 @@ def sharded_parity_check(rank, world, local, comm="split", ntemps=None, nwalkers
         swaps_equal = bool(np.array_equal(swaps, tc1.swaps_accepted))
         accepted_equal = bool(np.array_equal(acc, mv1.accepted))
         out = dict(ok=bool(max_rel <= 1e-10 and swaps_equal and accepted_equal), max_rel=max_rel, swaps_equal=swaps_equal,
-                   accepted_equal=accepted_equal, ntemps=T, nwalkers=W, ndim=d, iterations=nit, comm=comm,
+                   accepted_equal=accepted_equal, ntemps=T, nwalkers=W, ndim=d, iterations=nit, comm=comm_used,
                    against="the same chain run unsharded on rank 0's GPU (coords, logl, logp, betas, swap counts, accept counts)",
                    swaps_accepted_head=[int(v) for v in swaps[:4]])
     dist.barrier()
@@ -436,7 +442,7 @@ def sharded_parity_check(rank, world, local, comm="split", ntemps=None, nwalkers
 # ------------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
 # ------------------------------------------------------------------------------------------------------
-def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm="split", with_e2e=True, with_k1=True,
+def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm="auto", with_e2e=True, with_k1=True,
                       sustain_s=0.0):
     """One workload of bench.py on all ranks: the ladder sharded by temperature, one captured graph per (move kind, buffer
     parity) replayed per step.  Per-step CUDA events with an L2 flush between steps (outside the event pairs), summed,
@@ -606,6 +612,7 @@ def run_sharded_bench(args, wl, rank, world, local, clock_sampler_cls=None, comm
                    resident_ms=resident_ms, launches=int(launches), clocks=clocks, e2e=e2e,
                    swaps=swaps, betas=[float(betas[0]), float(betas[-1])], temp_begin=run.temp_begin, comm=comm,
                    graph=use_graph, k1_us=k1_us, local_temps=run.t_hi - run.t_lo)
+        out["comm"] = run.comm
     run.close()
     del flush
     return out

@@ -148,9 +148,19 @@ class EnsembleSampler(object):
                     self.rj_moves = [DistributionGenerateRJ(priors, nleaves_max=self.nleaves_max,
                                                             nleaves_min=self.nleaves_min,
                                                             temperature_control=self.temperature_control)]
+                elif rj_moves == "iterate_branches":  # ensemble.py:434-449: the branches one after the other in ONE move
+                    self.rj_moves = [DistributionGenerateRJ(priors, nleaves_max=self.nleaves_max,
+                                                            nleaves_min=self.nleaves_min,
+                                                            temperature_control=self.temperature_control,
+                                                            gibbs_sampling_setup=list(self.branch_names))]
+                elif rj_moves == "separate_branches":  # ensemble.py:451-472: one move per branch, one chosen per iteration
+                    self.rj_moves = [DistributionGenerateRJ(priors, nleaves_max=self.nleaves_max,
+                                                            nleaves_min=self.nleaves_min,
+                                                            temperature_control=self.temperature_control,
+                                                            gibbs_sampling_setup=[bn]) for bn in self.branch_names]
                 elif isinstance(rj_moves, str):
-                    raise NotImplementedError("rj_moves='iterate_branches' / 'separate_branches' need Gibbs splits "
-                                              "(DESIGN.md §7); use rj_moves=True")
+                    raise ValueError("When providing a str for rj_moves, must be 'together', 'iterate_branches', or "
+                                     f"'separate_branches'. Input is {rj_moves}")
                 else:
                     self.rj_moves = list(rj_moves) if isinstance(rj_moves, Iterable) else [rj_moves]
                 self.rj_weights = np.ones(len(self.rj_moves)) / len(self.rj_moves)

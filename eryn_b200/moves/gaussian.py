@@ -41,20 +41,31 @@ class GaussianMove(Move):
         T, W, L, D = d.shape
         prop = self.all_proposal[d.branch_name]
         cnt = self._count_buffer(ctx, T, W)
-        if ctx.rng == "numpy-replay":
-            n = T * W * L if d.inds is None else int(d.inds.sum().item())
-            if prop["kind"] == "scalar":  # gaussian.py:166-167
-                inc = 1.0 * prop["scale"] * model.random.randn(n, D)
-            else:  # gaussian.py:192-195
-                inc = 1.0 * model.random.multivariate_normal(np.zeros(D), prop["cov"], size=n)
-            if d.inds is None:
-                delta = inc.reshape(T, W, L, D)
+        splits = self._single_branch_splits(d.branch_name, L, D)
+        self._nsplits_run = len(splits)
+        acc = None
+        for gi, bits, gnd in splits:  # mh.py:77-183: one Metropolis step per split
+            kw = {} if (bits == 0 and gi == 0) else dict(gibbs=(bits, gi))
+            if ctx.rng == "numpy-replay":
+                n = T * W * L if d.inds is None else int(d.inds.sum().item())
+                if prop["kind"] == "scalar":  # gaussian.py:166-167
+                    inc = 1.0 * prop["scale"] * model.random.randn(n, D)
+                else:  # gaussian.py:192-195
+                    inc = 1.0 * model.random.multivariate_normal(np.zeros(D), prop["cov"], size=n)
+                if d.inds is None:
+                    delta = inc.reshape(T, W, L, D)
+                else:
+                    delta = np.zeros((T, W, L, D))
+                    delta[d.inds.cpu().numpy().astype(bool)] = inc
+                u_acc = model.random.rand(T, W)  # mh.py:171
+                acc = ctx.gaussian_step(d, prop, replay=(delta, u_acc), accepted_count=cnt, **kw)
             else:
-                delta = np.zeros((T, W, L, D))
-                delta[d.inds.cpu().numpy().astype(bool)] = inc
-            u_acc = model.random.rand(T, W)  # mh.py:171
-            acc = ctx.gaussian_step(d, prop, replay=(delta, u_acc), accepted_count=cnt)
-        else:
-            acc = ctx.gaussian_step(d, prop, accepted_count=cnt)
-        self.num_proposals += 1
+                acc = ctx.gaussian_step(d, prop, accepted_count=cnt, **kw)
+            self.num_proposals += 1  # mh.py:188: per Gibbs split
+        if acc is None:
+            acc = ctx.accepted_mask(T, W)
+            acc.zero_()
         return self._exit(ctx, d, host_state, acc)
+
+    def _host_tick(self, n=1):
+        self.num_proposals += n * getattr(self, "_nsplits_run", 1)

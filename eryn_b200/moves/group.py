@@ -23,6 +23,8 @@ __all__ = ["GroupStretchMove"]
 class GroupStretchMove(Move):
     def __init__(self, nfriends=None, n_iter_update=100, a=2.0, friend_key=1, live_dangerously=False, **kwargs):
         super().__init__(**kwargs)
+        if self.gibbs_sampling_setup is not None:
+            raise NotImplementedError("Gibbs splits of the group move are not part of the device path (DESIGN.md)")
         if nfriends is None:
             raise TypeError("int() argument must be a string, a bytes-like object or a real number, not 'NoneType'")  # group.py:43
         self.nfriends = int(nfriends)

@@ -52,41 +52,63 @@ class DistributionGenerateRJ(ReversibleJumpMove):
             d = ctx.upload(state, betas=None if tc is None else tc.betas_dev)
         T, W = d.shape[:2]
         cnt = self._count_buffer(ctx, T, W)
-        if ctx.rng == "numpy-replay":
-            flags = d.flags_host()
-            nb = len(lay.branch_names)
-            change_all = np.zeros((nb, T, W), dtype=np.int32)
-            leaf_all = np.zeros((nb, T, W), dtype=np.int32)
-            for b, n in enumerate(lay.branch_names):                         # distgenrj.py:160-173
-                nmin, nmax = lay.nleaves_min[n], lay.nleaves_max[n]
-                if nmin == nmax:
-                    continue
-                f = flags[n]
-                nleaves = f.sum(axis=-1)
-                change = model.random.choice([-1, +1], size=nleaves.shape)   # :62
-                change = change * ((nleaves != nmin) & (nleaves != nmax)) + (+1) * (nleaves == nmin) \
-                    + (-1) * (nleaves == nmax)                               # :67-71
-                for t in range(T):                                           # :85-121, same draw order
-                    for w in range(W):
-                        if change[t, w] == +1:
-                            leaf_all[b, t, w] = model.random.choice(np.where(~f[t, w])[0])
-                        elif change[t, w] == -1:
-                            leaf_all[b, t, w] = model.random.choice(np.where(f[t, w])[0])
-                change_all[b] = change
-            births = []
-            for b, n in enumerate(lay.branch_names):                         # distgenrj.py:176-219
-                nmin, nmax = lay.nleaves_min[n], lay.nleaves_max[n]
-                if nmin == nmax:
-                    births.append(None)
-                    continue
-                sel = change_all[b] == +1
-                full = np.zeros((T, W, lay.ndims[n]))
-                full[sel] = self.generate_dist[n].rvs(size=int(sel.sum()))   # prior.py:56-71: GLOBAL stream
-                births.append(full)
-            u_acc = model.random.rand(T, W)                                  # rj.py:332
-            acc = ctx.rj_step(d, replay=(change_all, leaf_all, births, u_acc), accepted_count=cnt)
-        else:
-            acc = ctx.rj_step(d, accepted_count=cnt)
+        # Gibbs splits over branches (rj.py:168-343; rj_moves="iterate_branches" / "separate_branches" set them up,
+        # ensemble.py:434-470): each split is a full birth/death proposal + Metropolis step restricted to its branches
+        splits = []
+        for split in self.gibbs_splits:
+            if split is None:
+                splits.append(list(lay.branch_names))
+                continue
+            for n, m in split.items():
+                if n not in lay.branch_names:
+                    raise KeyError(f"gibbs_sampling_setup names branch {n!r}; the sampler has {lay.branch_names}")
+                if m is not None:
+                    raise ValueError("inputting gibbs indexing at the leaf/parameter level is not allowed with an RJ "
+                                     "proposal. Only branch names.")
+            splits.append(list(split.keys()))
+        acc = None
+        for gi, names_run in enumerate(splits):
+            mask = 0 if len(names_run) == len(lay.branch_names) and gi == 0 and len(splits) == 1 else \
+                sum(1 << lay.branch_names.index(n) for n in names_run)
+            last = gi == len(splits) - 1
+            # rj.py:385-386: the move counts the accepts of the LAST split only
+            kw = dict(accepted_count=cnt if last else None, branch_mask=mask, gibbs_index=gi)
+            if ctx.rng == "numpy-replay":
+                flags = d.flags_host()
+                nb = len(lay.branch_names)
+                change_all = np.zeros((nb, T, W), dtype=np.int32)
+                leaf_all = np.zeros((nb, T, W), dtype=np.int32)
+                for n in names_run:                                              # distgenrj.py:160-173
+                    b = lay.branch_names.index(n)
+                    nmin, nmax = lay.nleaves_min[n], lay.nleaves_max[n]
+                    if nmin == nmax:
+                        continue
+                    f = flags[n]
+                    nleaves = f.sum(axis=-1)
+                    change = model.random.choice([-1, +1], size=nleaves.shape)   # :62
+                    change = change * ((nleaves != nmin) & (nleaves != nmax)) + (+1) * (nleaves == nmin) \
+                        + (-1) * (nleaves == nmax)                               # :67-71
+                    for t in range(T):                                           # :85-121, same draw order
+                        for w in range(W):
+                            if change[t, w] == +1:
+                                leaf_all[b, t, w] = model.random.choice(np.where(~f[t, w])[0])
+                            elif change[t, w] == -1:
+                                leaf_all[b, t, w] = model.random.choice(np.where(f[t, w])[0])
+                    change_all[b] = change
+                births = [None] * nb
+                for n in names_run:                                              # distgenrj.py:176-219
+                    b = lay.branch_names.index(n)
+                    nmin, nmax = lay.nleaves_min[n], lay.nleaves_max[n]
+                    if nmin == nmax:
+                        continue
+                    sel = change_all[b] == +1
+                    full = np.zeros((T, W, lay.ndims[n]))
+                    full[sel] = self.generate_dist[n].rvs(size=int(sel.sum()))   # prior.py:56-71: GLOBAL stream
+                    births[b] = full
+                u_acc = model.random.rand(T, W)                                  # rj.py:332
+                acc = ctx.rj_step(d, replay=(change_all, leaf_all, births, u_acc), **kw)
+            else:
+                acc = ctx.rj_step(d, **kw)
         self.num_proposals += 1
         tc = self.temperature_control
         if tc is not None:

@@ -204,10 +204,12 @@ class MBContext(DeviceContext):
         self.launches += 1
         return acc
 
-    def rj_step(self, d, replay=None, accepted_count=None):
+    def rj_step(self, d, replay=None, accepted_count=None, branch_mask=0, gibbs_index=0):
+        """DistributionGenerateRJ step; branch_mask / gibbs_index: the Gibbs split over branches of this call (rj.py:168)"""
         T, W = d.shape[:2]
         st = d.mb_struct()
         r = _lib.eb_mb_rj_rng()
+        r.branch_mask, r.gibbs_index = int(branch_mask), int(gibbs_index)
         keep = None
         if replay is None:
             r.mode, r.seed, r.iter_dev = _lib.EB_RNG_PHILOX, self.seed, self.iter_ptr

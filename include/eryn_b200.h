@@ -116,6 +116,16 @@ typedef struct {
   uint64_t seed;           /* philox */
   const uint64_t* iter_dev; /* philox: device iteration counter (eb_ctrl.iter) or NULL */
   uint64_t iter;           /* philox: used when iter_dev == NULL */
+  /* Gibbs split of this call (Move.gibbs_sampling_setup, moves/move.py:113-402; red_blue.py:127-325):
+   * gibbs_mask  bit j set = parameter j of the (single) leaf moves, the others keep their values
+   *             (cleanup_proposals_gibbs, move.py:302-307); 0 = no Gibbs split, every parameter moves
+   * gibbs_ndim  number of selected parameters: factors = (gibbs_ndim - 1) log zz, computed the way adjust_factors does
+   *             (stretch.py:55-72)
+   * gibbs_index index of the split inside one propose() call: the philox streams are keyed by it; from the second
+   *             split on `accepted` is the running OR over the splits and accepted_count is incremented by that OR,
+   *             which is what the reference adds to Move.accepted per split (red_blue.py:296-309, :325) */
+  uint32_t gibbs_mask;
+  int32_t gibbs_ndim, gibbs_index, _pad2;
 } eb_stretch_rng;
 
 /* Random inputs of one Gaussian Metropolis step (gaussian.py:68-195, mh.py:171). */
@@ -131,6 +141,10 @@ typedef struct {
   uint64_t seed;
   const uint64_t* iter_dev;
   uint64_t iter;
+  /* Gibbs split (mh.py:77-183): only the parameters in gibbs_mask change (0 = all); gibbs_index keys the philox streams
+   * of the split.  `accepted` is the mask of this split (mh.py:171), accepted_count its sum over splits (:187). */
+  uint32_t gibbs_mask;
+  int32_t gibbs_index;
 } eb_gauss_rng;
 
 /* Random inputs of one swap pass (tempering.py:525-535). */
@@ -386,12 +400,18 @@ typedef struct {
 } eb_mb_group_rng;
 
 typedef struct {
-  int32_t mode, _pad;
+  int32_t mode;
+  uint32_t branch_mask;    /* Gibbs split over branches (rj.py:168-343 with gibbs_sampling_setup = branch names, as
+                              rj_moves="iterate_branches" / "separate_branches" set it up, ensemble.py:434-470): bit b set =
+                              branch b gets a birth/death proposal in this call; 0 = all branches.  With a mask the prior of
+                              a proposal that leaves the selected branches empty is fixed up as fix_logp_gibbs does
+                              (move.py:369-402). */
   const int32_t* change;   /* replay [B][T][W] +1 / -1 / 0 after the edge fix-up (distgenrj.py:61-71) */
   const int32_t* leaf;     /* replay [B][T][W] leaf that is born or dies (distgenrj.py:97,111) */
   const double* birth[EB_MAX_BRANCHES]; /* replay [T][W][ndim_b] prior draws for the births (prior.py:56-71) */
   const double* u_acc;     /* replay [T][W]  rj.py:332 */
   uint64_t seed; const uint64_t* iter_dev; uint64_t iter;
+  int32_t gibbs_index, _pad2; /* index of the split inside one propose() call: keys the philox streams */
 } eb_mb_rj_rng;
 
 /* compute_log_prior + compute_log_like of the whole state (ensemble.py:898-912) */

@@ -221,7 +221,7 @@ def periodic_wrap(q, periods):
     return q
 
 
-def stretch_half_step(state, sub, comp, rint, u_z, u_acc, a, betas, prior, like, periods=None):
+def stretch_half_step(state, sub, comp, rint, u_z, u_acc, a, betas, prior, like, periods=None, gibbs_mask=None):
     """One red/blue half step (red_blue.py:148-323 + stretch.py:74-231).
 
     sub [T,Ns] / comp [T,Nc]: walker ids of the moving subset / the complement, in the order
@@ -236,6 +236,13 @@ def stretch_half_step(state, sub, comp, rint, u_z, u_acc, a, betas, prior, like,
     else:
         q = c_temp - (c_temp - s) * zz[:, :, None, None]  # stretch.py:143-145
     factors = (L * D - 1.0) * np.log(zz)  # stretch.py:223
+    if gibbs_mask is not None:
+        # Gibbs split (move.py:113-402): only the selected parameters move (cleanup_proposals_gibbs, move.py:302-307) and
+        # the detailed-balance factor counts them only (red_blue.py:196-207, stretch.py:55-72 adjust_factors)
+        q[:, :, ~gibbs_mask] = s[:, :, ~gibbs_mask]
+        g = float(gibbs_mask.sum())
+        if g != L * D:
+            factors = factors / (L * D - 1.0) * (g - 1.0)
     new_inds = np.take_along_axis(state.inds, sub[:, :, None], axis=1)
     logp = box_log_prior(prior, q, new_inds)  # red_blue.py:260
     logl = log_like(like, q, new_inds, logp)  # red_blue.py:270
@@ -250,7 +257,7 @@ def stretch_half_step(state, sub, comp, rint, u_z, u_acc, a, betas, prior, like,
     return keep, dict(q=q, logl=logl, logp=logp, zz=zz, lnpdiff=lnpdiff)
 
 
-def gaussian_step(state, delta, u_acc, betas, prior, like, periods=None):
+def gaussian_step(state, delta, u_acc, betas, prior, like, periods=None, gibbs_mask=None):
     """MH step with an additive proposal (mh.py:56-193, gaussian.py:68-131).
 
     delta [T,W,L,D] is the proposal increment (scale*randn or multivariate_normal draw) for
@@ -260,6 +267,8 @@ def gaussian_step(state, delta, u_acc, betas, prior, like, periods=None):
     q[state.inds] = (state.coords + delta)[state.inds]  # gaussian.py:99-108
     if periods is not None:
         periodic_wrap(q, periods)  # gaussian.py:111-129
+    if gibbs_mask is not None:  # cleanup_proposals_gibbs (move.py:302-307): the other parameters keep their values
+        q[:, :, ~gibbs_mask] = state.coords[:, :, ~gibbs_mask]
     logp = box_log_prior(prior, q, state.inds)
     logl = log_like(like, q, state.inds, logp)
     logP = tempered_log_posterior(logl, logp, betas)
@@ -369,13 +378,13 @@ class NumpyStreams:
         ids = np.tile(np.arange(W), (T, 1))
         return [ids[labels == s].reshape(T, -1) for s in (0, 1)]  # :150-154 ascending ids
 
-    def stretch(self, it, split, T, Ns, Nc, sub):
+    def stretch(self, it, split, T, Ns, Nc, sub, gidx=0):
         rint = self.private.randint(Nc, size=(T, Ns))  # stretch.py:93
         u_z = self.private.rand(T, Ns)  # stretch.py:131
         u_acc = self.private.rand(T, Ns)  # red_blue.py:294
         return rint, u_z, u_acc
 
-    def gauss_increment(self, it, inds, D, proposal):
+    def gauss_increment(self, it, inds, D, proposal, gidx=0):
         n = int(inds.sum())
         if proposal["kind"] == "scalar":  # gaussian.py:166-167
             d = 1.0 * proposal["scale"] * self.private.randn(n, D)
@@ -391,7 +400,7 @@ class NumpyStreams:
         out[inds] = prior.rvs(int(inds.sum()), self.glob)
         return out
 
-    def accept_uniforms(self, it, slot, T, W):
+    def accept_uniforms(self, it, slot, T, W, gidx=0):
         return self.private.rand(T, W)  # mh.py:171
 
     def swap_draws(self, it, T, W, permute=True):
@@ -431,19 +440,19 @@ class PhiloxStreams:
             subs1[t] = sig[1::2][:n1]
         return [subs0, subs1]
 
-    def stretch(self, it, split, T, Ns, Nc, sub):
-        # one Philox block per walker, keyed by (position in the split permutation, temperature)
+    def stretch(self, it, split, T, Ns, Nc, sub, gidx=0):
+        # one Philox block per walker, keyed by (position in the split permutation, temperature | Gibbs split << 16)
         pos = (2 * np.arange(Ns) + split)[None, :].repeat(T, axis=0)
         t = self.t0 + np.arange(T)[:, None].repeat(Ns, axis=1)
-        return px.stretch_draws(it, self.seed, t, pos, Nc)
+        return px.stretch_draws(it, self.seed, t | (int(gidx) << 16), pos, Nc)
 
     def accept_for(self, it, slot, flat_walker):
         return px.accept_draws(it, self.seed, flat_walker, slot)
 
-    def gauss_increment(self, it, inds, D, proposal):
+    def gauss_increment(self, it, inds, D, proposal, gidx=0):
         T, W, L = inds.shape
         flat = np.arange(T * W * L, dtype=np.uint32) + np.uint32(self.t0 * W * L)
-        z = px.gauss_draws(it, self.seed, flat, D)
+        z = px.gauss_draws(it, self.seed, flat, D, gidx=gidx)
         if proposal["kind"] == "scalar":
             d = proposal["scale"] * z
         else:
@@ -466,9 +475,9 @@ class PhiloxStreams:
         out[~inds] = 0.0
         return out
 
-    def accept_uniforms(self, it, slot, T, W):
+    def accept_uniforms(self, it, slot, T, W, gidx=0):
         flat = np.arange(T * W, dtype=np.uint32) + np.uint32(self.t0 * W)
-        return px.accept_draws(it, self.seed, flat, slot).reshape(T, W)
+        return px.accept_draws(it, self.seed, flat, slot | (int(gidx) << 16)).reshape(T, W)
 
     def swap_draws(self, it, T, W, permute=True):
         iperms, i1perms, us = [None] * T, [None] * T, [None] * T
@@ -537,23 +546,40 @@ class OracleSampler:
         it = self.iteration
         st = self.streams
         accepted = np.zeros((T, W), dtype=bool)
+        # Gibbs splits (move.py:113-402): {"gibbs": [mask [L, D] bool | None, ...]} — every split has its own draws,
+        # Metropolis test and update inside this one propose call; the tempering tail runs once, after the last split
+        gibbs = move.get("gibbs") or [None]
+        self.last_nsplits = len(gibbs)
+        self.last_accept_sum = np.zeros((T, W), dtype=np.int64)  # what the reference adds to move.accepted in this call
         if move["kind"] == "stretch":
-            lists = st.split_lists(it, T, W)
-            for split in (0, 1):
-                sub, comp = lists[split], lists[1 - split]
-                Ns, Nc = sub.shape[1], comp.shape[1]
-                rint, u_z, u_acc = st.stretch(it, split, T, Ns, Nc, sub)
-                if u_acc is None:
-                    flat = (np.arange(T)[:, None] * W + sub).astype(np.uint32)
-                    u_acc = st.accept_for(it, split, flat)
-                keep, _ = stretch_half_step(state, sub, comp, rint, u_z, u_acc, move.get("a", 2.0),
-                                            self.betas, self.prior, self.like, self.periods)
-                np.put_along_axis(accepted, sub, keep, axis=1)
+            lists = st.split_lists(it, T, W)  # red_blue.py:118-124: one red/blue labelling for all Gibbs splits
+            for gi, gmask in enumerate(gibbs):
+                if gmask is not None and not np.any(state.inds[:, :, gmask.any(axis=-1)]):
+                    continue  # setup_proposals: no leaf to propose for (red_blue.py:142-143)
+                for split in (0, 1):
+                    sub, comp = lists[split], lists[1 - split]
+                    Ns, Nc = sub.shape[1], comp.shape[1]
+                    rint, u_z, u_acc = st.stretch(it, split, T, Ns, Nc, sub, gidx=gi)
+                    if u_acc is None:
+                        flat = (np.arange(T)[:, None] * W + sub).astype(np.uint32)
+                        u_acc = st.accept_for(it, split, flat)
+                    keep, _ = stretch_half_step(state, sub, comp, rint, u_z, u_acc, move.get("a", 2.0),
+                                                self.betas, self.prior, self.like, self.periods, gibbs_mask=gmask)
+                    # red_blue.py:296-309: `accepted` ORs the halves AND the Gibbs splits of this call
+                    cur = np.take_along_axis(accepted, sub, axis=1)
+                    np.put_along_axis(accepted, sub, cur | keep, axis=1)
+                self.last_accept_sum += accepted  # red_blue.py:325: self.accepted += accepted (the running OR), per split
         elif move["kind"] == "gaussian":
-            delta = st.gauss_increment(it, state.inds, D, move["proposal"])
-            u_acc = st.accept_uniforms(it, 0, T, W)
-            keep, _ = gaussian_step(state, delta, u_acc, self.betas, self.prior, self.like, self.periods)
-            accepted = keep
+            for gi, gmask in enumerate(gibbs):
+                inds_go = state.inds if gmask is None else state.inds & gmask.any(axis=-1)[None, None, :]
+                if not np.any(inds_go):
+                    continue
+                delta = st.gauss_increment(it, inds_go, D, move["proposal"], gidx=gi)
+                u_acc = st.accept_uniforms(it, 0, T, W, gidx=gi)
+                keep, _ = gaussian_step(state, delta, u_acc, self.betas, self.prior, self.like, self.periods,
+                                        gibbs_mask=gmask)
+                accepted = keep  # mh.py:171: the mask of the LAST split is what propose returns
+                self.last_accept_sum += keep  # mh.py:187
         elif move["kind"] == "distgen":
             new_points = st.prior_draws(it, state.inds, self.prior)
             u_acc = st.accept_uniforms(it, 0, T, W)

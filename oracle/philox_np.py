@@ -110,8 +110,9 @@ def feistel_perm(x, n, keys):
         v = x[todo]
         L = v >> hb
         R = v & mask
-        for r in range(FEISTEL_ROUNDS):
-            L, R = R, L ^ (_fmix32(R ^ keys[r]) & mask)
+        for r in range(8 if int(hb) <= 3 else FEISTEL_ROUNDS):  # small domains: eight rounds (rng.cuh)
+            k = np.uint32((int(keys[r & 3]) + 0x9E3779B9 * (r >> 2)) & 0xFFFFFFFF)
+            L, R = R, L ^ (_fmix32(R ^ k) & mask)
         v = (L << hb) | R
         x[todo] = v
         todo = x >= np.uint32(n)
@@ -158,11 +159,11 @@ def accept_draws(it, seed, flat_walker, slot):
     return u01_52(r0, r1)
 
 
-def gauss_draws(it, seed, flat_leaf, D):
-    """Standard normals [N, D] for flat leaf ids; counter (flat_leaf, pair j); Box–Muller."""
+def gauss_draws(it, seed, flat_leaf, D, gidx=0):
+    """Standard normals [N, D] for flat leaf ids; counter (flat_leaf, pair j | Gibbs split << 16); Box–Muller."""
     flat_leaf = np.asarray(flat_leaf, dtype=np.uint32)
     npair = (D + 1) // 2
-    j = np.arange(npair, dtype=np.uint32)[None, :]
+    j = np.arange(npair, dtype=np.uint32)[None, :] | np.uint32(int(gidx) << 16)
     r0, r1, r2, r3 = _stream(TAG_GAUSS, it, seed, flat_leaf[:, None], j)
     u1 = u01_52(r0, r1)
     u2 = u01_52(r2, r3)

@@ -139,12 +139,13 @@ class NumpyStreamsMB(orc.NumpyStreams):
                 u_z = self.private.rand(T, W)  # stretch.py:131, first branch only
         return picks, u_z, None  # u_acc is drawn after the likelihood: accept_uniforms()
 
-    def rj_draws(self, it, inds, nmin, nmax, priors):
-        """distgenrj.py:35-122 for every branch, then the births from the priors (prior.py:56-71, global stream)"""
+    def rj_draws(self, it, inds, nmin, nmax, priors, branches=None, gidx=0):
+        """distgenrj.py:35-122 for every branch of the Gibbs split (`branches`, default all), then the births from the
+        priors (prior.py:56-71, global stream)"""
         T, W = inds[0].shape[:2]
         changes = []
         for b, i in enumerate(inds):
-            if nmin[b] == nmax[b]:
+            if nmin[b] == nmax[b] or (branches is not None and b not in branches):
                 changes.append(None)
                 continue
             nleaves = i.sum(axis=-1)
@@ -198,16 +199,17 @@ class PhiloxStreamsMB(orc.PhiloxStreams):
             j0 += L
         return picks, u_z, u_acc
 
-    def rj_draws(self, it, inds, nmin, nmax, priors):
+    def rj_draws(self, it, inds, nmin, nmax, priors, branches=None, gidx=0):
         T, W = inds[0].shape[:2]
         fw = self._fw(T, W)
+        g = np.uint32(int(gidx) << 8)   # the Gibbs split of the propose call keys the streams (csrc/k_rj.cu)
         changes, births = [], []
         for b, i in enumerate(inds):
-            if nmin[b] == nmax[b]:
+            if nmin[b] == nmax[b] or (branches is not None and b not in branches):
                 changes.append(None)
                 births.append(None)
                 continue
-            r0, r1, _, _ = px._stream(px.TAG_RJ, it, self.seed, fw, np.uint32(8 * b))
+            r0, r1, _, _ = px._stream(px.TAG_RJ, it, self.seed, fw, np.uint32(8 * b) | g)
             nleaves = i.sum(axis=-1)
             change = np.where(r0 & np.uint32(1), 1, -1)
             change = change * ((nleaves != nmin[b]) & (nleaves != nmax[b])) + (+1) * (nleaves == nmin[b]) \
@@ -223,7 +225,7 @@ class PhiloxStreamsMB(orc.PhiloxStreams):
             D = len(priors[b].lo)
             full = np.zeros((T, W, D))
             for d in range(D):
-                q = px._stream(px.TAG_RJ, it, self.seed, fw, np.uint32(8 * b + 1 + d // 2))
+                q = px._stream(px.TAG_RJ, it, self.seed, fw, np.uint32(8 * b + 1 + d // 2) | g)
                 u = px.u01_52(q[2], q[3]) if d % 2 else px.u01_52(q[0], q[1])
                 full[:, :, d] = u * (priors[b].hi[d] - priors[b].lo[d]) + priors[b].lo[d]
             full[change != 1] = 0.0
@@ -231,8 +233,8 @@ class PhiloxStreamsMB(orc.PhiloxStreams):
             births.append(full)
         return changes, births
 
-    def rj_accept(self, it, T, W):
-        _, _, r2, r3 = px._stream(px.TAG_RJ, it, self.seed, self._fw(T, W), np.uint32(0))
+    def rj_accept(self, it, T, W, gidx=0):
+        _, _, r2, r3 = px._stream(px.TAG_RJ, it, self.seed, self._fw(T, W), np.uint32(int(gidx) << 8))
         return px.u01_52(r2, r3)
 
 
@@ -262,7 +264,13 @@ class OracleSamplerMB:
     """One iteration = GroupStretch move (+ swaps + adaptation) then the RJ move (+ swaps, no adaptation):
     ensemble.py:965-1006 with group.py:122-281 and rj.py:145-388."""
 
-    def __init__(self, priors, like, nmin, nmax, streams, betas, nfriends, n_iter_update, a=2.0, key_index=1):
+    def __init__(self, priors, like, nmin, nmax, streams, betas, nfriends, n_iter_update, a=2.0, key_index=1,
+                 rj_mode="together"):
+        # rj_mode (ensemble.py:410-470): "together" = one RJ move over all branches; "iterate_branches" = one RJ move whose
+        # Gibbs splits are the branches, one after the other; "separate_branches" = one RJ move per branch, one of them
+        # chosen per iteration
+        self.rj_mode = rj_mode
+        self.last_rj_move = 0
         self.priors, self.like, self.nmin, self.nmax = priors, like, list(nmin), list(nmax)
         self.streams, self.betas = streams, np.asarray(betas, dtype=np.float64).copy()
         self.a, self.n_iter_update = a, n_iter_update
@@ -275,8 +283,13 @@ class OracleSamplerMB:
     def _post(self, logl, logp):
         return orc.tempered_log_posterior(logl, logp, self.betas)
 
-    def _accept(self, state, q, new_inds, factors, u_acc):
+    def _accept(self, state, q, new_inds, factors, u_acc, branches_run=None):
         logp = mb_log_prior(self.priors, q, new_inds)
+        if branches_run is not None:  # fix_logp_gibbs, move.py:369-402
+            here = sum(new_inds[b].sum(axis=-1) for b in branches_run)
+            total = sum(i.sum(axis=-1) for i in new_inds)
+            logp[(total != 0) & (here == 0)] = -np.inf  # no use in running because no change
+            logp[(total == 0) & (here == 0)] = 0.0      # there is nothing in the model currently
         logl = mb_log_like(self.like, q, new_inds, logp)
         lnpdiff = factors + self._post(logl, logp) - self._post(state.logl, state.logp)
         keep = lnpdiff > np.log(u_acc)
@@ -331,38 +344,51 @@ class OracleSamplerMB:
         it = self.iteration
         st = self.streams
         T, W = state.shape
-        if hasattr(st, "private"):
-            st.private.choice(1, p=[1.0])  # ensemble.py:990
-        changes, births = st.rj_draws(it, state.inds, self.nmin, self.nmax, self.priors)
-        q = [c.copy() for c in state.coords]
-        new_inds = [i.copy() for i in state.inds]
-        factors = np.zeros((T, W))
-        tt, ww = np.meshgrid(np.arange(T), np.arange(W), indexing="ij")
-        for b, ch in enumerate(changes):
-            if ch is None:
-                continue
-            change, leaf = ch
-            dm = change == -1
-            new_inds[b][tt[dm], ww[dm], leaf[dm]] = False
-            factors[dm] += +1 * self.priors[b].logpdf(q[b][tt[dm], ww[dm], leaf[dm]])
-            bm = change == +1
-            new_inds[b][tt[bm], ww[bm], leaf[bm]] = True
-            q[b][tt[bm], ww[bm], leaf[bm]] = births[b][bm]
-            factors[bm] += -1 * self.priors[b].logpdf(q[b][tt[bm], ww[bm], leaf[bm]])
-        edge = np.zeros((T, W))
-        for b in range(len(q)):
-            if self.nmin[b] == self.nmax[b] or self.nmin[b] + 1 == self.nmax[b]:
-                continue
-            old_n, new_n = state.inds[b].sum(axis=-1), new_inds[b].sum(axis=-1)
-            edge[old_n == self.nmin[b]] += np.log(1 / 2.0)
-            edge[old_n == self.nmax[b]] += np.log(1 / 2.0)
-            edge[new_n == self.nmin[b]] -= np.log(1 / 2.0)
-            edge[new_n == self.nmax[b]] -= np.log(1 / 2.0)
-        factors += edge
-        u_acc = st.rj_accept(it, T, W) if hasattr(st, "rj_accept") else st.accept_uniforms(it, 1, T, W)
-        keep = self._accept(state, q, new_inds, factors, u_acc)
-        self._swaps(state, it, adapt=False)
-        return keep
+        nb = len(state.coords)
+        if self.rj_mode == "separate_branches":  # ensemble.py:990: one of the per-branch moves
+            if hasattr(st, "private"):
+                self.last_rj_move = int(st.private.choice(nb, p=np.ones(nb) / nb))
+            else:
+                self.last_rj_move = int(st.sched.choice(nb, p=np.ones(nb) / nb))
+            splits = [[self.last_rj_move]]
+        else:
+            if hasattr(st, "private"):
+                st.private.choice(1, p=[1.0])  # ensemble.py:990
+            splits = [None] if self.rj_mode == "together" else [[b] for b in range(nb)]
+        keep = None
+        for gi, branches in enumerate(splits):  # rj.py:168-343, one pass per Gibbs split
+            changes, births = st.rj_draws(it, state.inds, self.nmin, self.nmax, self.priors, branches=branches, gidx=gi)
+            q = [c.copy() for c in state.coords]
+            new_inds = [i.copy() for i in state.inds]
+            factors = np.zeros((T, W))
+            tt, ww = np.meshgrid(np.arange(T), np.arange(W), indexing="ij")
+            for b, ch in enumerate(changes):
+                if ch is None:
+                    continue
+                change, leaf = ch
+                dm = change == -1
+                new_inds[b][tt[dm], ww[dm], leaf[dm]] = False
+                factors[dm] += +1 * self.priors[b].logpdf(q[b][tt[dm], ww[dm], leaf[dm]])
+                bm = change == +1
+                new_inds[b][tt[bm], ww[bm], leaf[bm]] = True
+                q[b][tt[bm], ww[bm], leaf[bm]] = births[b][bm]
+                factors[bm] += -1 * self.priors[b].logpdf(q[b][tt[bm], ww[bm], leaf[bm]])
+            edge = np.zeros((T, W))
+            for b in range(len(q)):
+                if branches is not None and b not in branches:  # rj.py:236-237
+                    continue
+                if self.nmin[b] == self.nmax[b] or self.nmin[b] + 1 == self.nmax[b]:
+                    continue
+                old_n, new_n = state.inds[b].sum(axis=-1), new_inds[b].sum(axis=-1)
+                edge[old_n == self.nmin[b]] += np.log(1 / 2.0)
+                edge[old_n == self.nmax[b]] += np.log(1 / 2.0)
+                edge[new_n == self.nmin[b]] -= np.log(1 / 2.0)
+                edge[new_n == self.nmax[b]] -= np.log(1 / 2.0)
+            factors += edge
+            u_acc = st.rj_accept(it, T, W, gidx=gi) if hasattr(st, "rj_accept") else st.accept_uniforms(it, 1, T, W)
+            keep = self._accept(state, q, new_inds, factors, u_acc, branches_run=branches)
+        self._swaps(state, it, adapt=False)  # rj.py:381-382, once, after the last split
+        return keep  # rj.py:385: the accepts of the LAST split are what the move counts
 
     def initialise(self, state):
         if state.logp is None:

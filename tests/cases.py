@@ -14,6 +14,13 @@ def corr_prec(d, seed=99):
     return np.linalg.inv(cov)
 
 
+def gmask(d, *params):
+    """Gibbs split of a single-leaf branch: boolean [nleaves_max = 1, ndim] with the given parameters selected"""
+    m = np.zeros((1, d), dtype=bool)
+    m[0, list(params)] = True
+    return m
+
+
 COV3 = np.array([[0.04, 0.01, 0.0], [0.01, 0.09, -0.02], [0.0, -0.02, 0.01]])
 
 # name -> (likelihood factory(ndim), moves, weights, tempering extras)
@@ -39,6 +46,11 @@ CASES = {
     "combine_sg": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                        moves=[dict(kind="combine", moves=[dict(kind="stretch", a=2.0),
                                                           dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.25)))])]),
+    "gibbs_mix": dict(like=lambda d: orc.GaussianLike(np.zeros(d), corr_prec(d)),
+                      moves=[dict(kind="stretch", a=2.0, gibbs=[gmask(4, 0, 1), gmask(4, 2, 3)]),
+                             dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.09)),
+                                  gibbs=[gmask(4, 0), gmask(4, 1, 2), None])],
+                      weights=[0.5, 0.5]),
     "noadapt_noperm": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                            moves=[dict(kind="stretch", a=2.0)], adaptive=False, permute=False),
 }

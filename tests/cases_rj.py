@@ -7,13 +7,18 @@ from oracle import eryn_oracle as orc
 from oracle import rj_oracle as rjo
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["c5_small", "c5_wide"]
+NAMES = ["c5_small", "c5_wide", "c5_iter", "c5_sep"]   # the last two: rj_moves="iterate_branches" / "separate_branches"
 PRIOR_BOUNDS = {  # tests/test_eryn.py:416-427
     "gauss": lambda t: ([2.5, t.min(), 0.01], [3.5, t.max(), 0.21]),
     "sine": lambda t: ([0.5, 1.0, 0.0], [1.5, 20.0, 2 * np.pi]),
 }
 GINJ = np.array([[3.3, -0.2, 0.1], [2.6, -0.1, 0.1], [3.4, 0.0, 0.1], [2.9, 0.3, 0.1]])
 SINJ = np.array([[1.3, 10.1, 1.0], [0.8, 4.6, 1.2]])
+
+
+def rj_mode(g):
+    m = str(g["rj_mode"]) if "rj_mode" in g else "True"
+    return "together" if m == "True" else m
 
 
 def load(name):
@@ -57,4 +62,5 @@ def oracle_sampler(g, streams, t=None):
     ndim_total = 3 * (int(g["Lg"]) + int(g["Ls"]))
     # ensemble.py:321-334: the ladder is built for the total dimension over all branches
     return rjo.OracleSamplerMB(priors_for(t), like, [0, 0], [int(g["Lg"]), int(g["Ls"])], streams,
-                               betas=orc.make_ladder_default(ndim_total, T), nfriends=int(g["nfriends"]), n_iter_update=int(g["n_iter_update"]))
+                               betas=orc.make_ladder_default(ndim_total, T), nfriends=int(g["nfriends"]),
+                               n_iter_update=int(g["n_iter_update"]), rj_mode=rj_mode(g))

@@ -16,6 +16,7 @@ The cases mirror BASELINE.json's configs at sizes small enough to commit (<300 K
   gauss_matrix   3 temps x 24 walkers x 3-d, GaussianMove(full covariance) + PT
   odd_walkers    1 temp x 99 walkers x 5-d (tests/test_eryn.py:96 test_base shape), a=1.5
   noadapt_noperm 4 temps x 32 walkers, adaptive=False, permute=False
+  gibbs_mix      (`gibbs`) 3 temps x 24 walkers x 4-d, Stretch and Gaussian moves with parameter-level Gibbs splits
 """
 import os
 import sys
@@ -161,6 +162,22 @@ if __name__ == "__main__":
         # CombineMove (combine.py): a stretch move then a Gaussian move per iteration, each with its own tempering tail
         run_case("combine_sg", 57, 3, 24, 3, 30, ll_gauss_vec, [np.zeros(3), np.eye(3)], True, -5.0, 5.0,
                  moves_factory=lambda: [(CombineMove([StretchMove(), GaussianMove({"model_0": 0.25})]), 1.0)])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gibbs":
+        # Gibbs splits at the parameter level (moves/move.py:113-402): a stretch move that updates parameters {0,1} then
+        # {2,3}, and a Gaussian move over {0}, {1,2} and the whole leaf — the splits of one move run inside ONE propose
+        # call, each with its own draws, Metropolis test and update, and one tempering tail at the end
+        def masks(*sets):
+            out = []
+            for s_ in sets:
+                m = np.zeros((1, 4), dtype=bool)
+                m[0, list(s_)] = True
+                out.append(("model_0", m))
+            return out
+        run_case("gibbs_mix", 19, 4, 24, 3, 30, ll_gauss_vec, [np.zeros(4), corr_prec(4)], True, -5.0, 5.0,
+                 moves_factory=lambda: [(StretchMove(gibbs_sampling_setup=masks((0, 1), (2, 3))), 0.5),
+                                        (GaussianMove({"model_0": 0.09},
+                                                      gibbs_sampling_setup=masks((0,), (1, 2)) + ["model_0"]), 0.5)])
         sys.exit(0)
     run_case("c1_kat1", 42, 5, 32, None, 100, ll_single, [np.zeros(5), np.eye(5)], False, -5.0, 5.0)
     run_case("pt_kat2", 42, 3, 16, 4, 50, ll_single, [np.zeros(3), np.eye(3)], False, -5.0, 5.0)

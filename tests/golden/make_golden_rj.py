@@ -107,7 +107,7 @@ class NearestFriendsGroupMove(GroupStretchMove):
         return friends
 
 
-def run_case(name, seed, T, W, L, nt, nfriends, n_iter_update, nits, sigma):
+def run_case(name, seed, T, W, L, nt, nfriends, n_iter_update, nits, sigma, rj_moves=True):
     np.random.seed(seed)
     branch_names = ["gauss", "sine"]
     ndims = {"gauss": 3, "sine": 3}
@@ -130,7 +130,7 @@ def run_case(name, seed, T, W, L, nt, nfriends, n_iter_update, nits, sigma):
     move = NearestFriendsGroupMove(nfriends=nfriends, n_iter_update=n_iter_update)
     sampler = EnsembleSampler(W, ndims, log_like_fn_gauss_and_sine, priors, args=[t, y, sigma],
                               tempering_kwargs=dict(ntemps=T), nbranches=2, branch_names=branch_names,
-                              nleaves_max=nleaves_max, nleaves_min=nleaves_min, moves=move, rj_moves=True)
+                              nleaves_max=nleaves_max, nleaves_min=nleaves_min, moves=move, rj_moves=rj_moves)
     lp = sampler.compute_log_prior(coords, inds=inds)
     ll = sampler.compute_log_like(coords, inds=inds, logp=lp)[0]
     supp = {k: BranchSupplemental({"inds_closest": np.zeros(inds[k].shape + (nfriends,), dtype=int)},
@@ -140,7 +140,9 @@ def run_case(name, seed, T, W, L, nt, nfriends, n_iter_update, nits, sigma):
     rec = {k: [] for k in ("cg", "cs", "ig", "is", "logl", "logp", "betas", "acc", "rjacc", "swaps")}
     prev_acc = np.zeros((T, W))
     prev_rj = np.zeros((T, W))
-    rjm = sampler.rj_moves[0]
+    rjms = list(sampler.rj_moves)
+    rec["rjmove"] = []
+    prev_np = [0 for _ in rjms]
     for state in sampler.sample(state0, iterations=nits, store=False, skip_initial_state_check=True):
         rec["cg"].append(state.branches["gauss"].coords.copy())
         rec["cs"].append(state.branches["sine"].coords.copy())
@@ -150,12 +152,15 @@ def run_case(name, seed, T, W, L, nt, nfriends, n_iter_update, nits, sigma):
         rec["logp"].append(state.log_prior.copy())
         rec["betas"].append(sampler.temperature_control.betas.copy())
         rec["acc"].append((move.accepted - prev_acc).astype(bool))
-        rec["rjacc"].append((rjm.accepted - prev_rj).astype(bool))
-        prev_acc, prev_rj = move.accepted.copy(), rjm.accepted.copy()
+        rj_total = sum(m.accepted for m in rjms)
+        rec["rjacc"].append((rj_total - prev_rj).astype(bool))
+        rec["rjmove"].append(np.int64([k for k, m in enumerate(rjms) if m.num_proposals != prev_np[k]][0]))
+        prev_np = [m.num_proposals for m in rjms]
+        prev_acc, prev_rj = move.accepted.copy(), rj_total.copy()
         rec["swaps"].append(np.asarray(sampler.temperature_control.swaps_accepted).copy())
     out = dict(seed=seed, T=T, W=W, Lg=L["gauss"], Ls=L["sine"], nt=nt, nfriends=nfriends, n_iter_update=n_iter_update,
                nits=nits, sigma=sigma, t=t, y=y, cg0=coords["gauss"], cs0=coords["sine"], ig0=inds["gauss"],
-               is0=inds["sine"], logl0=ll, logp0=lp)
+               is0=inds["sine"], logl0=ll, logp0=lp, rj_mode=str(rj_moves))
     for k, v in rec.items():
         a = np.stack(v)
         out[k] = np.packbits(a, axis=-1) if a.dtype == bool else a
@@ -167,5 +172,10 @@ def run_case(name, seed, T, W, L, nt, nfriends, n_iter_update, nits, sigma):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gibbs":
+        # rj_moves="iterate_branches" / "separate_branches" (ensemble.py:434-470): the branches as Gibbs splits of the RJ move
+        run_case("c5_iter", 31, 3, 12, {"gauss": 4, "sine": 3}, 48, 5, 4, 20, 2.0, rj_moves="iterate_branches")
+        run_case("c5_sep", 32, 2, 16, {"gauss": 5, "sine": 3}, 32, 6, 3, 20, 3.0, rj_moves="separate_branches")
+        sys.exit(0)
     run_case("c5_small", 2024, 3, 12, {"gauss": 4, "sine": 3}, 48, 5, 4, 24, 2.0)
     run_case("c5_wide", 7, 2, 16, {"gauss": 6, "sine": 2}, 32, 8, 3, 16, 3.0)

@@ -40,15 +40,18 @@ def dev_moves(moves, priors=None):
     from eryn_b200.moves import CombineMove, DistributionGenerate, GaussianMove, StretchMove
     out = []
     for m in moves:
+        kw = {}
+        if m.get("gibbs") is not None:  # the reference's input form: a list of (branch, mask) tuples / branch names
+            kw["gibbs_sampling_setup"] = [("model_0", g) if g is not None else "model_0" for g in m["gibbs"]]
         if m["kind"] == "combine":
             out.append(CombineMove(dev_moves(m["moves"], priors)))
         elif m["kind"] == "stretch":
-            out.append(StretchMove(a=m.get("a", 2.0)))
+            out.append(StretchMove(a=m.get("a", 2.0), **kw))
         elif m["kind"] == "distgen":
             out.append(DistributionGenerate({"model_0": priors}))
         else:
             p = m["proposal"]
-            out.append(GaussianMove({"model_0": p["scale"] ** 2 if p["kind"] == "scalar" else p["cov"]}))
+            out.append(GaussianMove({"model_0": p["scale"] ** 2 if p["kind"] == "scalar" else p["cov"]}, **kw))
     return out
 
 
@@ -171,6 +174,13 @@ PHILOX_CASES = {
     "gmix_d8": (4, 256, 8, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -10, 10),
     "gmix_k6_d20": (3, 128, 20, lambda d: gmix_like(d, K=6, seed=8), [dict(kind="stretch", a=2.0)], [1.0], 5, -10, 10),
     "gmix_tight_d20": (3, 128, 20, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -3.2, 3.2),
+    # Gibbs splits at the parameter level (move.py:113-402) in the exact-length (D = 8) and the padded (D = 5) kernels
+    "gibbs_d8": (3, 64, 8, c2_like,
+                 [dict(kind="stretch", a=2.0, gibbs=[cases.gmask(8, 0, 1, 2), cases.gmask(8, 3, 4, 5, 6, 7)]),
+                  dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.3),
+                       gibbs=[cases.gmask(8, 7), None, cases.gmask(8, 0, 2, 4, 6)])], [0.5, 0.5], 10, -10, 10),
+    "gibbs_d5": (2, 32, 5, lambda d: orc.RosenbrockLike(),
+                 [dict(kind="stretch", a=2.0, gibbs=[cases.gmask(5, 4), cases.gmask(5, 0, 1, 2, 3), None])], [1.0], 8, -5, 5),
     "W_small": (3, 16, 3, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 10, -5, 5),
     "W_257": (2, 257, 5, lambda d: orc.RosenbrockLike(), [dict(kind="stretch", a=2.0)], [1.0], 6, -5, 5),
 }

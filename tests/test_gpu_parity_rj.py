@@ -19,7 +19,7 @@ def close(a, b, what):
     np.testing.assert_allclose(a, b, rtol=RTOL, atol=1e-300, err_msg=what)
 
 
-def make_sampler(t, y, sigma, T, W, Lg, Ls, nfriends, n_iter_update, rng, seed=None):
+def make_sampler(t, y, sigma, T, W, Lg, Ls, nfriends, n_iter_update, rng, seed=None, rj_moves=True):
     from eryn_b200 import EnsembleSampler
     from eryn_b200.moves import GroupStretchMove
     from eryn_b200.multibranch import PulseLikelihood
@@ -32,7 +32,7 @@ def make_sampler(t, y, sigma, T, W, Lg, Ls, nfriends, n_iter_update, rng, seed=N
     move = GroupStretchMove(nfriends=nfriends, n_iter_update=n_iter_update)
     return EnsembleSampler(W, {"gauss": 3, "sine": 3}, like, priors, tempering_kwargs=dict(ntemps=T), nbranches=2,
                            branch_names=["gauss", "sine"], nleaves_max={"gauss": Lg, "sine": Ls},
-                           nleaves_min={"gauss": 0, "sine": 0}, moves=move, rj_moves=True, rng=rng, seed=seed), move
+                           nleaves_min={"gauss": 0, "sine": 0}, moves=move, rj_moves=rj_moves, rng=rng, seed=seed), move
 
 
 @pytest.mark.parametrize("name", cases_rj.NAMES)
@@ -41,8 +41,9 @@ def test_rj_replay_matches_reference_golden(name):
     g = cases_rj.load(name)
     t, coords, inds, _, _ = cases_rj.replay_setup(g)  # leaves the GLOBAL stream where the reference's sampler started
     T, W, Lg, Ls = int(g["T"]), int(g["W"]), int(g["Lg"]), int(g["Ls"])
+    mode = cases_rj.rj_mode(g)   # "together", "iterate_branches" or "separate_branches" (ensemble.py:410-470)
     smp, move = make_sampler(t, g["y"], float(g["sigma"]), T, W, Lg, Ls, int(g["nfriends"]), int(g["n_iter_update"]),
-                             "numpy-replay")
+                             "numpy-replay", rj_moves=True if mode == "together" else mode)
     cd = {"gauss": coords[0], "sine": coords[1]}
     idd = {"gauss": inds[0], "sine": inds[1]}
     lp = smp.compute_log_prior(cd, inds=idd)
@@ -50,10 +51,9 @@ def test_rj_replay_matches_reference_golden(name):
     np.testing.assert_array_equal(lp, g["logp0"])
     close(ll, g["logl0"], "initial logl")
     st0 = State(cd, inds=idd, log_like=ll, log_prior=lp)
-    rjm = smp.rj_moves[0]
     pa, pr = np.zeros((T, W)), np.zeros((T, W))
     for it, state in enumerate(smp.sample(st0, iterations=int(g["nits"]), store=False)):
-        a, r = move.accepted, rjm.accepted
+        a, r = move.accepted, sum(m.accepted for m in smp.rj_moves)
         assert np.array_equal((a - pa).astype(bool), g["acc"][it]), f"in-model accept mask differs at iteration {it}"
         assert np.array_equal((r - pr).astype(bool), g["rjacc"][it]), f"rj accept mask differs at iteration {it}"
         pa, pr = a.copy(), r.copy()
@@ -67,6 +67,18 @@ def test_rj_replay_matches_reference_golden(name):
         assert np.array_equal(smp.temperature_control.swaps_accepted, g["swaps"][it]), f"swaps it {it}"
 
 
+class _RJSched(object):
+    """the device sampler's private MT19937 stream in philox mode: one draw for the in-model move (ensemble.py:971), one
+    for the rj move (:990) per iteration; the oracle asks only for the rj choice of 'separate_branches'."""
+
+    def __init__(self, rs, mode):
+        self.rs, self.mode = rs, mode
+
+    def choice(self, n, p):
+        self.rs.choice(1, p=[1.0])           # the in-model move of this iteration
+        return self.rs.choice(n, p=p)        # the rj move
+
+
 def random_start(T, W, Lg, Ls, t, seed):
     r = np.random.RandomState(seed)
     coords, inds = [], []
@@ -78,26 +90,33 @@ def random_start(T, W, Lg, Ls, t, seed):
     return coords, inds
 
 
-@pytest.mark.parametrize("T,W,Lg,Ls,nt,nfriends,nup,nits", [(3, 32, 4, 3, 48, 6, 3, 7), (8, 2048, 10, 10, 64, 16, 2, 2)])
-def test_rj_philox_matches_oracle(T, W, Lg, Ls, nt, nfriends, nup, nits):
+@pytest.mark.parametrize("T,W,Lg,Ls,nt,nfriends,nup,nits,mode", [
+    (3, 32, 4, 3, 48, 6, 3, 7, "together"), (8, 2048, 10, 10, 64, 16, 2, 2, "together"),
+    (3, 32, 4, 3, 48, 6, 3, 7, "iterate_branches"), (3, 32, 4, 3, 48, 6, 3, 9, "separate_branches"),
+    (4, 512, 10, 10, 64, 16, 2, 3, "iterate_branches")])
+def test_rj_philox_matches_oracle(T, W, Lg, Ls, nt, nfriends, nup, nits, mode):
     from eryn_b200.state import State
     seed = 31337
     t = np.linspace(-1, 1, nt)
     y = 3.0 * np.exp(-((t + 0.2) ** 2) / 0.02) + np.sin(2 * np.pi * 4.6 * t + 1.2) + np.random.RandomState(5).randn(nt)
     coords, inds = random_start(T, W, Lg, Ls, t, 11)
     like = rjo.PulseLike(t, y, 2.0, [0, 1])
-    osmp = rjo.OracleSamplerMB(cases_rj.priors_for(t), like, [0, 0], [Lg, Ls], rjo.PhiloxStreamsMB(seed),
-                               betas=orc.make_ladder_default(3 * (Lg + Ls), T), nfriends=nfriends, n_iter_update=nup)
+    np.random.seed(77)  # the sampler's private stream (choice among the per-branch rj moves) = copy of the global state
+    sched = np.random.RandomState(77)
+    osmp = rjo.OracleSamplerMB(cases_rj.priors_for(t), like, [0, 0], [Lg, Ls],
+                               rjo.PhiloxStreamsMB(seed, schedule_random=_RJSched(sched, mode)),
+                               betas=orc.make_ladder_default(3 * (Lg + Ls), T), nfriends=nfriends, n_iter_update=nup,
+                               rj_mode=mode)
     ost = osmp.initialise(rjo.MBState(coords, inds))
-    smp, move = make_sampler(t, y, 2.0, T, W, Lg, Ls, nfriends, nup, "philox", seed=seed)
+    smp, move = make_sampler(t, y, 2.0, T, W, Lg, Ls, nfriends, nup, "philox", seed=seed,
+                             rj_moves=True if mode == "together" else mode)
     st0 = State({"gauss": coords[0], "sine": coords[1]}, inds={"gauss": inds[0], "sine": inds[1]})
-    rjm = smp.rj_moves[0]
     pa, pr = np.zeros((T, W)), np.zeros((T, W))
     for it, state in enumerate(smp.sample(st0, iterations=nits, store=False)):
         if it == 0:
             pass
         oa, orj = osmp.iterate(ost)
-        a, r = move.accepted, rjm.accepted
+        a, r = move.accepted, sum(m.accepted for m in smp.rj_moves)
         assert np.array_equal((a - pa).astype(bool), oa), f"in-model accept mask differs at iteration {it}"
         assert np.array_equal((r - pr).astype(bool), orj), f"rj accept mask differs at iteration {it}"
         pa, pr = a.copy(), r.copy()

@@ -177,3 +177,35 @@ def test_combine_move_surface():
     assert len(mv.acceptance_fraction_separate) == 2
     with pytest.raises(ValueError):
         CombineMove([])
+
+
+def test_swap_and_split_bijections_have_uniform_pair_frequencies():
+    """The production streams pair walkers through keyed bijections (4-round Feistel + cycle walking, csrc/rng.cuh)
+    instead of NumPy permutations.  A 4-round Feistel network on <= 14 bits does not reach every permutation, and MCMC
+    validity does not need it: the pairing only has to be independent of the state and fair.  What the sampler relies on
+    is checked here as frequencies over many iterations (chi-square against the uniform law, 5-sigma bounds):
+      * swap pass: walker a of rung i meets walker b of rung i-1 with probability 1/W for every (a, b)
+        (tempering.py:526-527 pairs iperm[k] with i1perm[k]);
+      * red/blue split: every walker lands in split 0 with probability Ns0/W, and an ordered pair of walkers is
+        (moving walker, one of its possible partners) equally often (red_blue.py:121-124, stretch.py:93)."""
+    from oracle import philox_np as px
+    for W in (7, 16, 50):
+        nit = 400 * W
+        pair = np.zeros((W, W))
+        in0 = np.zeros(W)
+        pos = np.zeros((W, W))
+        for it in range(nit):
+            s_hi, s_lo = px.swap_perm(it, 12345, 3, W), px.swap_perm(it, 12345, 2, W)
+            pair[s_hi, s_lo] += 1          # chain k: slot sigma_3(k) of rung 3 with slot sigma_2(k) of rung 2
+            sp = px.split_perm(it, 12345, 1, W)
+            in0[sp[0::2]] += 1
+            pos[np.arange(W), sp] += 1     # position -> walker
+        for counts, cells in ((pair, W * W), (pos, W * W)):
+            exp = nit / W
+            chi2 = ((counts - exp) ** 2 / exp).sum()
+            dof = (W - 1) ** 2             # doubly stochastic table
+            assert abs(chi2 - dof) < 5.0 * np.sqrt(2.0 * dof) + 0.05 * dof, (W, chi2, dof)
+        n0 = (W + 1) // 2
+        exp0 = nit * n0 / W
+        z = (in0 - exp0) / np.sqrt(nit * (n0 / W) * (1 - n0 / W))
+        assert np.abs(z).max() < 5.0, (W, z)

@@ -54,7 +54,8 @@ def _oracle(T, W, d, nit, seed, mix):
                                                 ("fused", 16, 4096, 0), ("p2p", 16, 4096, 0), ("fused", 72, 64, 0),
                                                 ("fused", 128, 48, 0), ("fused", 32, 16384, 0),
                                                 ("split", 4, 256, 0), ("split", 5, 99, 1), ("split", 16, 4096, 0),
-                                                ("split", 128, 48, 0), ("split", 32, 16384, 0), ("split", 7, 1000, 1)])
+                                                ("split", 128, 48, 0), ("split", 32, 16384, 0), ("split", 7, 1000, 1),
+                                                ("split", 8, 16384, 0), ("split", 24, 333, 1), ("auto", 6, 128, 0)])
 def test_sharded_run_matches_unsharded_oracle(tmp_path, comm, T, W, mix):
     _run_and_compare(tmp_path, comm, T, W, mix, nproc=2)
 
@@ -68,8 +69,6 @@ def test_split_pass_single_rank_matches_oracle(tmp_path, T, W):
 def _run_and_compare(tmp_path, comm, T, W, mix, nproc):
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
-    if comm == "split" and os.environ.get("EB_TEST_SPLIT") != "1":
-        pytest.skip("the chain-split pass (k_swap_split.cu) is experimental (no multi-rank GPU run yet): EB_TEST_SPLIT=1 enables its cases")
     d, nit, seed = 8, 6, 4242
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--out",

@@ -18,6 +18,8 @@ def test_rj_oracle_reproduces_reference(name):
         acc, racc = smp.iterate(st)
         assert np.array_equal(acc, g["acc"][it]), f"in-model accept mask differs at iteration {it}"
         assert np.array_equal(racc, g["rjacc"][it]), f"rj accept mask differs at iteration {it}"
+        if "rjmove" in g:
+            assert smp.last_rj_move == int(g["rjmove"][it]), f"rj move choice differs at iteration {it}"
         assert np.array_equal(st.inds[0], g["ig"][it]) and np.array_equal(st.inds[1], g["is"][it]), f"inds it {it}"
         np.testing.assert_allclose(st.coords[0], g["cg"][it], rtol=1e-13, atol=1e-300, err_msg=f"gauss coords it {it}")
         np.testing.assert_allclose(st.coords[1], g["cs"][it], rtol=1e-13, atol=1e-300, err_msg=f"sine coords it {it}")

@@ -1,0 +1,3 @@
+# 2 GPUs: the whole GPU suite (single-GPU parity + API + the 2-GPU sharded cases)
+mkdir -p gpurun_out
+timeout 1700 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r02_pytest_gpu_n2.log; cat gpurun_out/r02_pytest_gpu_n2.log
