@@ -47,7 +47,8 @@ class eb_stretch_rng(C.Structure):
 class eb_gauss_rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("cov_kind", C.c_int32), ("scale", C.c_double), ("chol", vp), ("delta", vp),
                 ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64),
-                ("gibbs_mask", C.c_uint32), ("gibbs_index", C.c_int32)]
+                ("gibbs_mask", C.c_uint32), ("gibbs_index", C.c_int32), ("dim_mode", C.c_int32), ("_pad3", C.c_int32),
+                ("log_factor", C.c_double)]
 
 
 class eb_swap_rng(C.Structure):
@@ -103,6 +104,11 @@ class eb_stage(C.Structure):
     _fields_ = [("nseg", C.c_int32), ("mask_nleaves", C.c_int32), ("mask_ndim", C.c_int32), ("_pad", C.c_int32),
                 ("src", vp * EB_STAGE_MAX_SEGMENTS), ("nbytes", C.c_uint64 * EB_STAGE_MAX_SEGMENTS),
                 ("mask_inds", vp), ("fill", C.c_double), ("dst", vp), ("dst_bytes", C.c_uint64)]
+
+
+class eb_mt_rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("num_try", C.c_int32), ("tries", vp), ("u_sel", vp), ("u_acc", vp),
+                ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
 
 
 class eb_publish(C.Structure):
@@ -179,11 +185,12 @@ SYMBOLS = {
     "eb_box_log_prior": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, P(eb_prior), vp, vp]),
     "eb_run_host": (C.c_int, [P(eb_host_job), C.c_int32]),
     "eb_stage_pack": (C.c_int, [P(eb_stage), vp]),
+    "eb_mt_distgen_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), P(eb_mt_rng), vp, vp, vp]),
 }
 
 STRUCTS = [eb_state, eb_prior, eb_like, eb_stretch_rng, eb_gauss_rng, eb_swap_rng, eb_ctrl, eb_adapt, eb_host_job,
            eb_shard, eb_publish, eb_mb_layout, eb_mb_state, eb_pulse_data, eb_mb_friends, eb_mb_group_rng, eb_mb_rj_rng,
-           eb_split, eb_stage]
+           eb_split, eb_stage, eb_mt_rng]
 
 _lib = None
 

@@ -152,6 +152,7 @@ size_t eb_struct_size(int which) {
     case 16: return sizeof(eb_mb_rj_rng);
     case 17: return sizeof(eb_split);
     case 18: return sizeof(eb_stage);
+    case 19: return sizeof(eb_mt_rng);
     default: return 0;
   }
 }

@@ -2,14 +2,19 @@
 //
 // Kernels:
 //   K0  eval_state_kernel         log-prior + log-like of the whole state            (abi_core.cu)
-//   K1  stretch_step_kernel       fused, both red/blue halves per launch (cluster per temperature):
+//   K1  stretch_step_kernel       fused, one launch per red/blue half chained by programmatic dependent launch:
 //                                 draw -> gather complement -> stretch -> prior/like ->
 //                                 tempered Metropolis test -> in-place update        (k_stretch.cu, hot kernel)
+//       stretch_lanes_kernel      the same step with a walker spread over 2 / 4 lanes (HBM-sized shapes, stretch_lanes.cuh)
 //   K2  gaussian_step_kernel      fused Gaussian Metropolis step over all walkers    (k_gauss.cu)
 //   K3  pt_swap_kernel            chain-parallel swap ladder (decide on logl, then move only the rows
 //                                 that changed rung, in place) + last-block ladder adaptation (k_swap.cu)
 //   K3r pt_pairmap_kernel         replay mode: host permutations -> per-position pair map
 //   K4  stretch_propose_kernel / accept_update_kernel / box_prior_kernel   (split path)
+//   K3s pt_swap_split_kernel      the swap pass of a temperature-sharded run, chains split over the ranks (k_swap_split.cu)
+//   K6-K9 multi-branch kernels    reversible jump + group stretch (k_rj.cu)
+//   K10 stage_pack_kernel         snapshot of a stored sample for the staged Backend.save_step (k_stage.cu)
+//   K11 mt_distgen_kernel         multiple-try Metropolis with an independent proposal (k_mt.cu)
 //
 // Built with --fmad=false so that +,-,*,/ round exactly like the NumPy reference.
 #pragma once

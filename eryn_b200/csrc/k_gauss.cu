@@ -13,6 +13,7 @@ struct GaussArgs {
   uint32_t seed_lo, seed_hi; const unsigned long long* iter_dev; unsigned long long iter;
   uint8_t* accepted; uint32_t* accepted_count;
   uint32_t gmask; int gidx;   // Gibbs split (mh.py:77-183): parameters that change (0 = all), index of the split
+  int dim_mode; double log_factor;   // gaussian.py:134-181: 1 = one random dimension per walker; scale factor exp(U(-lf, lf))
 };
 
 template <int DMAX, int LIKE, bool PHILOX, bool EXACT>
@@ -69,11 +70,20 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
         z[j] = 0.0; z[j + 1] = 0.0;
       }
     }
+    const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)(tid + c.t0 * c.W), (uint32_t)p.gidx << 16);
+    u_acc = u01_52(ra.x, ra.y);
+    double f = 1.0;
+    if (p.log_factor > 0.0) {   // get_factor (gaussian.py:161-164): one draw per call, the same for every walker
+      const uint4 rf = stream(key, TAG_GAUSS, 0xFFFFFFFFu, 0xFFFFu | ((uint32_t)p.gidx << 16));
+      f = exp(-p.log_factor + (p.log_factor - (-p.log_factor)) * u01_52(rf.x, rf.y));   // rng.uniform(-lf, lf)
+    }
     if (active) {
       if (p.cov_kind == 0) {
+        const double fs = f * p.scale;
+        const int dsel = p.dim_mode == 1 ? (int)__umulhi(ra.z, (uint32_t)D) : -1;       // gaussian.py:172-173
 #pragma unroll
         for (int j = 0; j < DMAX; ++j)
-          if (EXACT || j < D) q[j] = q[j] + p.scale * z[j];                          // gaussian.py:166-167
+          if ((EXACT || j < D) && (dsel < 0 || j == dsel)) q[j] = q[j] + fs * z[j];     // gaussian.py:166-167
       } else {
 #pragma unroll
         for (int i = 0; i < DMAX; ++i)
@@ -82,12 +92,10 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
 #pragma unroll
             for (int j = 0; j < DMAX; ++j)
               if (j <= i && j < D) acc += s_chol[i * D + j] * z[j];
-            q[i] = q[i] + acc;                                               // gaussian.py:192-195
+            q[i] = q[i] + f * acc;                                           // gaussian.py:192-195
           }
       }
     }
-    const uint4 ra = stream(key, TAG_ACCEPT, (uint32_t)(tid + c.t0 * c.W), (uint32_t)p.gidx << 16);
-    u_acc = u01_52(ra.x, ra.y);
   } else {
     const double* dl = p.delta + (size_t)tid * D;
     if (active) {
@@ -189,6 +197,10 @@ int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* l
   args.iter_dev = (const unsigned long long*)rng->iter_dev; args.iter = rng->iter;
   args.accepted = accepted; args.accepted_count = accepted_count;
   args.gmask = rng->gibbs_mask; args.gidx = rng->gibbs_index;
+  args.dim_mode = rng->dim_mode; args.log_factor = rng->log_factor;
+  if (args.dim_mode != 0 && (args.dim_mode != 1 || rng->cov_kind != 0))
+    return fail(EB_ERR_INVALID, "dim_mode must be 0 (vector) or, for scalar proposals, 1 (random)");
+  if (args.log_factor < 0.0) return fail(EB_ERR_INVALID, "'factor' must be >= 1.0");
   if (args.gmask && rng->cov_kind == 2) return fail(EB_ERR_UNSUPPORTED, "DistributionGenerate has no Gibbs splits on the device");
   if (args.gmask && st->nleaves != 1) return fail(EB_ERR_UNSUPPORTED, "Gibbs splits address the parameters of one leaf");
   if (args.gidx < 0 || args.gidx > 0xFFFF) return fail(EB_ERR_INVALID, "gibbs_index out of range");

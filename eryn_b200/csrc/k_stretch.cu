@@ -8,16 +8,18 @@
 namespace eb {
 
 // ================================================================================================
-// K1: fused StretchMove step (both red/blue halves in one launch)
+// K1: fused StretchMove step — one launch per red/blue half, chained by programmatic dependent launch
 // ================================================================================================
-// Within a half, thread k of a temperature moves the k-th walker of the active split (dense warps:
-// every lane does a proposal).  Half 1 reads what half 0 wrote within the same temperature only
-// (red_blue.py:183-197 gathers along the walker axis), so the barrier between the halves is a
-// thread-block-cluster barrier over the CTAs that own that temperature, not a grid barrier.
-// Production (philox) mode, per walker: ONE Philox block gives the partner index + stretch uniform
-// (split_draw) and the accept uniform; the random red/blue split of the temperature is a keyed
-// bijection sigma_t of [0, W) (even positions = split 0), so the moving walker is sigma_t(2k+s) and
-// its partner sigma_t(2*rint+1-s): no index lists in memory.
+// Within a half, thread k of a temperature moves the k-th walker of the active split (dense warps: every lane does a
+// proposal).  Half 1 reads what half 0 wrote, inside the same temperature only (red_blue.py:183-197 gathers along the
+// walker axis): it is launched as a programmatic dependent of half 0 — its draws (and the loads of its own rows, which
+// half 0 does not touch) run while half 0 still evaluates, only its `finish` stage waits (griddepcontrol.wait).  Small
+// ensembles (Ns <= 128) run both halves in one CTA per temperature with a block barrier in between.  (A thread-block
+// cluster per temperature with a cluster barrier between the halves was measured and dropped)
+// Production (philox) mode, per walker: ONE Philox block gives the partner index + stretch uniform (split_draw) and the
+// accept uniform; the random red/blue split of the temperature is a keyed bijection sigma_t of [0, W) (even positions =
+// split 0), so the moving walker is sigma_t(2k+s) and its partner sigma_t(2*rint+1-s): no index lists in memory.
+// HBM-sized shapes take the lane-split variant of this kernel (stretch_lanes.cuh).
 struct StretchArgs {
   Common c;
   double a;

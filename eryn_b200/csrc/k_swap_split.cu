@@ -2,11 +2,9 @@
 //
 // K3s: the swap pass of a temperature-sharded run with the CHAINS split over the ranks.
 //
-// EXPERIMENTAL — written at the end of round 1 when the GPU budget of the round was nearly spent.  Its one GPU run so far
-// (single rank, 16 temps x 4096 walkers, 6 iterations, tests/test_mgpu.py::test_split_pass_single_rank_matches_oracle)
-// reproduced the oracle's coords / logl / logp; the ladder differed by 2e-6 because the adaptation clock reached
-// thread 0 only — fixed since (s_time), not re-run.  No multi-rank run yet.  `comm="fused"` (k_swap.cu, validated) stays
-// the default; this pass is selected with `comm="split"` and its GPU cases are skipped unless EB_TEST_SPLIT=1.
+// Validated on 2 GPUs against the unsharded oracle (tests/test_mgpu.py: uneven partitions, a Stretch/Gaussian mix, W = 16384
+// chains where a CTA takes several chain groups, 128 rungs, config 4 at full size) and on 8 GPUs by the parity check bench.py
+// runs after its timed region; `ShardedRun(comm="auto")` selects it beyond 2 ranks (measurements: profiles/README.md).
 //
 // Why: the fused sharded pass (k_swap.cu) resolves the WHOLE ladder on every rank — every rank draws positions and
 // log u for all T rungs of all W chains and receives the logl of every other rank, so its cost grows with the number

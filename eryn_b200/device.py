@@ -290,12 +290,14 @@ class DeviceContext(object):
             self.launches += 3
         return acc
 
-    def gaussian_step(self, d, proposal, replay=None, accepted_count=None, gibbs=None):
-        """GaussianMove step, fused (mh.py:56-193 + gaussian.py:68-195).  gibbs = (parameter mask bits, split index)."""
+    def gaussian_step(self, d, proposal, replay=None, accepted_count=None, gibbs=None, dim_mode=0, log_factor=0.0):
+        """GaussianMove step, fused (mh.py:56-193 + gaussian.py:68-195).  gibbs = (parameter mask bits, split index);
+        dim_mode 1 = one random dimension per walker, log_factor = log of GaussianMove's `factor` (philox mode)."""
         self._require_fused()
         T, W, L, D = d.shape
         st = d.c_struct()
         r = _lib.eb_gauss_rng()
+        r.dim_mode, r.log_factor = int(dim_mode), float(log_factor)
         if gibbs is not None:
             r.gibbs_mask, r.gibbs_index = int(gibbs[0]), int(gibbs[1])
         keep = None
@@ -321,6 +323,27 @@ class DeviceContext(object):
         acc = self.accepted_mask(T, W)
         _lib.check(self.lib.eb_gaussian_step(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c), C.byref(r),
                                              _ptr(acc), _ptr(accepted_count), self.stream()), "eb_gaussian_step")
+        self.launches += 1
+        return acc
+
+    def mt_distgen_step(self, d, num_try, replay=None, accepted_count=None):
+        """MTDistGenMove step (multipletry.py:238-514 + mtdistgen.py inside mh.py:56-193), all walkers in one launch.
+        replay = (tries [T*W, num_try, D], u_sel [T*W], u_acc [T, W]) drawn on the host in the reference's order."""
+        self._require_fused()
+        T, W, L, D = d.shape
+        st = d.c_struct()
+        r = _lib.eb_mt_rng()
+        r.num_try = int(num_try)
+        keep = None
+        if replay is None:
+            r.mode, r.seed, r.iter_dev = _lib.EB_RNG_PHILOX, self.seed, self.iter_ptr
+        else:
+            keep = [self.to_dev(x, np.float64) for x in replay]
+            r.mode = _lib.EB_RNG_REPLAY
+            r.tries, r.u_sel, r.u_acc = [_ptr(x) for x in keep]
+        acc = self.accepted_mask(T, W)
+        _lib.check(self.lib.eb_mt_distgen_step(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c), C.byref(r),
+                                               _ptr(acc), _ptr(accepted_count), self.stream()), "eb_mt_distgen_step")
         self.launches += 1
         return acc
 

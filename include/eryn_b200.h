@@ -145,6 +145,11 @@ typedef struct {
    * of the split.  `accepted` is the mask of this split (mh.py:171), accepted_count its sum over splits (:187). */
   uint32_t gibbs_mask;
   int32_t gibbs_index;
+  /* philox mode, scalar proposals (gaussian.py:134-181): dim_mode 0 = "vector" (all dimensions), 1 = "random" (one
+   * uniformly drawn dimension per walker; "sequential" is gibbs_mask with one bit, advanced by the host);
+   * log_factor > 0: the scale is multiplied by exp(U(-log_factor, log_factor)), one draw per call (get_factor). */
+  int32_t dim_mode, _pad3;
+  double log_factor;
 } eb_gauss_rng;
 
 /* Random inputs of one swap pass (tempering.py:525-535). */
@@ -197,7 +202,7 @@ EB_API size_t eb_ctrl_size(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 eb_state, 1 eb_prior, 2 eb_like,
  * 3 eb_stretch_rng, 4 eb_gauss_rng, 5 eb_swap_rng, 6 eb_ctrl, 7 eb_adapt, 8 eb_host_job, 9 eb_shard,
  * 10 eb_publish, 11 eb_mb_layout, 12 eb_mb_state, 13 eb_pulse_data, 14 eb_mb_friends, 15 eb_mb_group_rng,
- * 16 eb_mb_rj_rng, 17 eb_split, 18 eb_stage */
+ * 16 eb_mb_rj_rng, 17 eb_split, 18 eb_stage, 19 eb_mt_rng */
 EB_API size_t eb_struct_size(int which);
 
 /* ---- probability evaluation:  EnsembleSampler.compute_log_prior (ensemble.py:1127) and
@@ -206,9 +211,11 @@ EB_API size_t eb_struct_size(int which);
 EB_API int eb_eval_state(const eb_state* st, const eb_prior* prior, const eb_like* like, void* stream);
 
 /* ---- StretchMove.propose without the tempering tail: BOTH red/blue half steps of
- *      red_blue.py:148-323 + stretch.py:74-231 + Move.update (move.py:472-703), fused into one
- *      launch (a thread-block cluster owns a temperature; a cluster barrier separates the halves;
- *      shapes with too few temperatures for that fall back to one launch per half).
+ *      red_blue.py:148-323 + stretch.py:74-231 + Move.update (move.py:472-703): one launch per half, the second a
+ *      programmatic dependent of the first (its draws overlap the first half's evaluation); small ensembles
+ *      (ceil(W/2) <= 128) run both halves in one CTA per temperature.  Shapes that fill the GPU (exact row lengths 8 and
+ *      20) take the lane-split kernel (csrc/stretch_lanes.cuh): same draws, same results up to the summation order of
+ *      the likelihood.
  *      `accepted` [T][W] uint8 gets the accept flag of every walker; `accepted_count` (nullable,
  *      [T][W] uint32) is incremented (Move.accepted, move.py:404). */
 EB_API int eb_stretch_step(const eb_state* st, const eb_prior* prior, const eb_like* like, double a,
@@ -309,6 +316,19 @@ typedef struct {
   uint64_t* flags_peer[EB_MAX_RANKS];     /* peer-mapped flag arrays of every rank */
 } eb_publish;
 EB_API int eb_publish_logl(const eb_publish* pub, eb_ctrl* ctrl, void* stream);
+
+/* ---- MTDistGenMove(generate_dist = priors, num_try, independent=True): multiple-try Metropolis, one launch over all
+ *      walkers = moves/multipletry.py:238-514 + moves/mtdistgen.py:8-133 inside MHMove.propose (mh.py:56-193).
+ *      replay: `tries` [T][W][num_try][D] are the host draws of mtdistgen.py:58 (one global rand(n, num_try) per
+ *      parameter), `u_sel` [T][W] the global uniform that picks a try (multipletry.py:51), `u_acc` [T][W] the private
+ *      Metropolis uniform (mh.py:171).  philox: everything from (seed, *iter_dev, walker, try). */
+typedef struct {
+  int32_t mode, num_try;
+  const double* tries; const double* u_sel; const double* u_acc;
+  uint64_t seed; const uint64_t* iter_dev; uint64_t iter;
+} eb_mt_rng;
+EB_API int eb_mt_distgen_step(const eb_state* st, const eb_prior* prior, const eb_like* like, const eb_mt_rng* rng,
+                       uint8_t* accepted, uint32_t* accepted_count, void* stream);
 
 /* ---- Backend.save_step staging (backends/backend.py:1014-1091; call site ensemble.py:1013-1028).
  *      ONE kernel gathers every array of a stored step into one contiguous device staging slot (a snapshot: the

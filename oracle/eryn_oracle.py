@@ -302,6 +302,59 @@ def distgen_step(state, new_points, u_acc, betas, prior, like):
     return keep, dict(q=q, logl=logl, logp=logp, lnpdiff=lnpdiff)
 
 
+def _mt_logsumexp(a):
+    """multipletry.py:25-31: max, exp of the differences summed, log"""
+    mx = np.max(a, axis=-1)
+    return mx + np.log(np.exp(a - mx[:, None]).sum(axis=-1))
+
+
+def mt_distgen_step(state, tries, u_sel, u_acc, betas, prior, like):
+    """MTDistGenMove(generate_dist = priors, num_try, independent=True): multiple-try Metropolis
+    (multipletry.py:238-514, mtdistgen.py:8-133) inside MHMove.propose (mh.py:56-193).
+
+    tries [T,W,NT,D]: the draws from the priors (mtdistgen.py:58), u_sel [T,W]: the uniform that picks a try by
+    importance weight (multipletry.py:51, GLOBAL stream), u_acc [T,W]: the Metropolis uniform (mh.py:171)."""
+    T, W, L, D = state.coords.shape
+    assert L == 1 and bool(np.all(state.inds)), "multiple try works on one (present) leaf per walker (multipletry.py:548)"
+    NT = tries.shape[2]
+    n = T * W
+    pts = tries.reshape(n, NT, D)
+    cur = state.coords.reshape(n, D)
+    b = np.ones(T) if betas is None else betas
+    beta_w = np.repeat(b, W)                                                  # multipletry.py:553-556
+    lpp = prior.logpdf(pts.reshape(n * NT, D)).reshape(n, NT)                 # mtdistgen.py:62-64
+    ll = like(pts.reshape(n * NT, D)).reshape(n, NT)                          # :334 (no prior gate: no logp is passed)
+    ll[np.isnan(ll)] = FILL                                                   # :339-341
+    lp = prior.logpdf(pts.reshape(n * NT, D)).reshape(n, NT)                  # :344
+    logP = beta_w[:, None] * ll + lp                                          # :354, get_mt_log_posterior :205-236
+    log_w = logP - lpp                                                        # get_mt_computations :34-55 (not symmetric)
+    lsw = _mt_logsumexp(log_w)
+    probs = np.exp(log_w - lsw[:, None])
+    keep_idx = (probs.cumsum(1) > u_sel.reshape(n)[:, None]).argmax(1)
+    it = (np.arange(n), keep_idx)
+    lp_out, ll_out, logP_out = lp[it], ll[it], logP[it]
+    q = pts[it].copy()
+    lpp_out = lpp[it]
+    # independent proposal: the auxiliary set repeats the tries, with the current point in place of the chosen one (:383-416)
+    aux_ll, aux_lp, aux_lpp = ll.copy(), lp.copy(), lpp.copy()
+    aux_ll[it] = state.logl.reshape(n)
+    aux_lp[it] = state.logp.reshape(n)
+    aux_lpp[it] = prior.logpdf(cur)
+    aux_logP = beta_w[:, None] * aux_ll + aux_lp
+    aux_lsw = _mt_logsumexp(aux_logP - aux_lpp)
+    aux_logP_out, aux_lpp_out = aux_logP[it], aux_lpp[it]
+    factors = ((aux_logP_out - aux_lsw) - aux_lpp_out + aux_lpp_out) - ((logP_out - lsw) - lpp_out + lpp_out)  # :467-471
+    # mh.py:146-171 with the stored multiple-try values (mt_ll, mt_lp)
+    logl, logp = ll_out.reshape(T, W), lp_out.reshape(T, W)
+    logP2 = tempered_log_posterior(logl, logp, betas)
+    prev_logP = tempered_log_posterior(state.logl, state.logp, betas)
+    lnpdiff = factors.reshape(T, W) + logP2 - prev_logP
+    keep = lnpdiff > np.log(u_acc)
+    sub = np.tile(np.arange(W), (T, 1))
+    update_subset(state, sub, q.reshape(T, W, 1, D), logl, logp, keep)
+    return keep, dict(q=q, factors=factors, chosen=keep_idx.reshape(T, W), lnpdiff=lnpdiff)
+
+
 # ----------------------------------------------------------------------------------
 # parallel tempering
 # ----------------------------------------------------------------------------------
@@ -386,10 +439,26 @@ class NumpyStreams:
 
     def gauss_increment(self, it, inds, D, proposal, gidx=0):
         n = int(inds.sum())
+        f = 1.0
+        if proposal.get("factor") is not None:  # gaussian.py:161-164: ONE scale factor per call, drawn first
+            lf = np.log(proposal["factor"])
+            f = np.exp(self.private.uniform(-lf, lf))
         if proposal["kind"] == "scalar":  # gaussian.py:166-167
-            d = 1.0 * proposal["scale"] * self.private.randn(n, D)
+            d = f * proposal["scale"] * self.private.randn(n, D)
         else:  # gaussian.py:192-195
-            d = 1.0 * self.private.multivariate_normal(np.zeros(D), proposal["cov"], size=n)
+            d = f * self.private.multivariate_normal(np.zeros(D), proposal["cov"], size=n)
+        mode = proposal.get("mode", "vector")
+        if mode == "random":  # gaussian.py:172-173: one random dimension per walker
+            m = self.private.randint(D, size=n)
+            keep = np.zeros((n, D), dtype=bool)
+            keep[np.arange(n), m] = True
+            d = np.where(keep, d, 0.0)
+        elif mode == "sequential":  # gaussian.py:174-176: the same, next dimension for everybody
+            idx = proposal.get("_index", 0)
+            keep = np.zeros((n, D), dtype=bool)
+            keep[:, idx % D] = True
+            d = np.where(keep, d, 0.0)
+            proposal["_index"] = (idx + 1) % D
         delta = np.zeros(inds.shape + (D,))
         delta[inds] = d
         return delta
@@ -399,6 +468,12 @@ class NumpyStreams:
         out = np.zeros(inds.shape + (len(prior.lo),))
         out[inds] = prior.rvs(int(inds.sum()), self.glob)
         return out
+
+    def mt_draws(self, it, T, W, NT, prior):
+        """mtdistgen.py:58: generate_dist.rvs(size=(n, num_try)) — one global rand(n, num_try) per parameter — then the
+        global rand(n) that picks the try (multipletry.py:51)"""
+        tries = prior.rvs((T * W, NT), self.glob).reshape(T, W, NT, len(prior.lo))
+        return tries, self.glob.rand(T * W).reshape(T, W)
 
     def accept_uniforms(self, it, slot, T, W, gidx=0):
         return self.private.rand(T, W)  # mh.py:171
@@ -453,10 +528,28 @@ class PhiloxStreams:
         T, W, L = inds.shape
         flat = np.arange(T * W * L, dtype=np.uint32) + np.uint32(self.t0 * W * L)
         z = px.gauss_draws(it, self.seed, flat, D, gidx=gidx)
+        f = 1.0
+        if proposal.get("factor") is not None:  # one factor per call: TAG_GAUSS block (0xFFFFFFFF, 0xFFFF | gidx << 16)
+            lf = np.log(proposal["factor"])
+            r = px._stream(px.TAG_GAUSS, it, self.seed, np.uint32(0xFFFFFFFF), np.uint32(0xFFFF | (int(gidx) << 16)))
+            f = np.exp(-lf + (lf - (-lf)) * float(px.u01_52(r[0], r[1])))
         if proposal["kind"] == "scalar":
-            d = proposal["scale"] * z
+            d = (f * proposal["scale"]) * z
         else:
-            d = z @ proposal["chol"].T
+            d = f * (z @ proposal["chol"].T)
+        mode = proposal.get("mode", "vector")
+        if mode == "random":  # dimension = high word of (third word of the walker's accept block) x D
+            ra = px._stream(px.TAG_ACCEPT, it, self.seed, flat, np.uint32(int(gidx) << 16))
+            m = ((ra[2].astype(np.uint64) * np.uint64(D)) >> np.uint64(32)).astype(np.int64)
+            keep = np.zeros(d.shape, dtype=bool)
+            keep[np.arange(d.shape[0]), m] = True
+            d = np.where(keep, d, 0.0)
+        elif mode == "sequential":
+            idx = proposal.get("_index", 0)
+            keep = np.zeros(d.shape, dtype=bool)
+            keep[:, idx % D] = True
+            d = np.where(keep, d, 0.0)
+            proposal["_index"] = (idx + 1) % D
         delta = d.reshape(T, W, L, D)
         delta[~inds] = 0.0
         return delta
@@ -474,6 +567,20 @@ class PhiloxStreams:
         out = out.reshape(T, W, L, D)
         out[~inds] = 0.0
         return out
+
+    def mt_draws(self, it, T, W, NT, prior):
+        """try j, parameter d of flat walker f: TAG_MT block (f, j * 16 + d // 2), word pair d % 2; the selection uniform:
+        block (f, 0xFFFF), first pair (csrc/k_mt.cu)"""
+        D = len(prior.lo)
+        flat = np.arange(T * W, dtype=np.uint32) + np.uint32(self.t0 * W)
+        tries = np.zeros((T * W, NT, D))
+        for j in range(NT):
+            for d in range(D):
+                r = px._stream(px.TAG_MT, it, self.seed, flat, np.uint32(j * 16 + d // 2))
+                u = px.u01_52(r[2], r[3]) if d % 2 else px.u01_52(r[0], r[1])
+                tries[:, j, d] = u * (prior.hi[d] - prior.lo[d]) + prior.lo[d]
+        r = px._stream(px.TAG_MT, it, self.seed, flat, np.uint32(0xFFFF))
+        return tries.reshape(T, W, NT, D), px.u01_52(r[0], r[1]).reshape(T, W)
 
     def accept_uniforms(self, it, slot, T, W, gidx=0):
         flat = np.arange(T * W, dtype=np.uint32) + np.uint32(self.t0 * W)
@@ -505,7 +612,8 @@ class OracleSampler:
                  adaptation_lag=10000, adaptation_time=100, stop_adaptation=-1, permute=True, periods=None):
         self.periods = None if periods is None else np.asarray(periods, dtype=np.float64)
         self.prior, self.like = prior, like
-        self.moves = moves
+        import copy
+        self.moves = copy.deepcopy(moves)  # a sequential-mode Gaussian proposal keeps its dimension counter in its dict
         w = np.atleast_1d(np.asarray(weights, dtype=float))
         self.weights = w / w.sum()  # ensemble.py:376-377
         self.streams = streams
@@ -580,6 +688,11 @@ class OracleSampler:
                                         gibbs_mask=gmask)
                 accepted = keep  # mh.py:171: the mask of the LAST split is what propose returns
                 self.last_accept_sum += keep  # mh.py:187
+        elif move["kind"] == "mt":  # MTDistGenMove(priors, num_try, independent=True)
+            tries, u_sel = st.mt_draws(it, T, W, int(move["num_try"]), self.prior)
+            u_acc = st.accept_uniforms(it, 0, T, W)
+            keep, _ = mt_distgen_step(state, tries, u_sel, u_acc, self.betas, self.prior, self.like)
+            accepted = keep
         elif move["kind"] == "distgen":
             new_points = st.prior_draws(it, state.inds, self.prior)
             u_acc = st.accept_uniforms(it, 0, T, W)

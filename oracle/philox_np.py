@@ -35,6 +35,7 @@ TAG_ACCEPT = 4
 TAG_SWAP_KEY = 5
 TAG_SWAP_U = 6
 TAG_RJ = 7
+TAG_MT = 9   # (8 = the group move's tag, oracle/rj_oracle.py)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

@@ -51,6 +51,13 @@ CASES = {
                              dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.09)),
                                   gibbs=[gmask(4, 0), gmask(4, 1, 2), None])],
                       weights=[0.5, 0.5]),
+    "gauss_modes": dict(like=lambda d: orc.GaussianLike(np.zeros(d), corr_prec(d)),
+                        moves=[dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.16), mode="random", factor=2.0)),
+                               dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.25), mode="sequential")),
+                               dict(kind="gaussian", proposal=dict(kind="scalar", scale=np.sqrt(0.04), mode="vector"))],
+                        weights=[0.5, 0.3, 0.2]),
+    "mt_mix": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d) / 0.25),
+                   moves=[dict(kind="stretch", a=2.0), dict(kind="mt", num_try=6)], weights=[0.4, 0.6]),
     "noadapt_noperm": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                            moves=[dict(kind="stretch", a=2.0)], adaptive=False, permute=False),
 }

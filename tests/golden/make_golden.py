@@ -16,6 +16,8 @@ The cases mirror BASELINE.json's configs at sizes small enough to commit (<300 K
   gauss_matrix   3 temps x 24 walkers x 3-d, GaussianMove(full covariance) + PT
   odd_walkers    1 temp x 99 walkers x 5-d (tests/test_eryn.py:96 test_base shape), a=1.5
   noadapt_noperm 4 temps x 32 walkers, adaptive=False, permute=False
+  gauss_modes    (`gauss_modes`) GaussianMove modes random / sequential / vector and `factor`
+  mt_mix         (`mt`) 3 temps x 16 walkers x 3-d, MTDistGenMove(num_try=6, independent) mixed with StretchMove
   gibbs_mix      (`gibbs`) 3 temps x 24 walkers x 4-d, Stretch and Gaussian moves with parameter-level Gibbs splits
 """
 import os
@@ -49,7 +51,7 @@ import warnings  # noqa: E402
 
 warnings.filterwarnings("ignore")
 from eryn.ensemble import EnsembleSampler  # noqa: E402
-from eryn.moves import CombineMove, DistributionGenerate, GaussianMove, StretchMove  # noqa: E402
+from eryn.moves import CombineMove, DistributionGenerate, GaussianMove, MTDistGenMove, StretchMove  # noqa: E402
 from eryn.prior import ProbDistContainer, uniform_dist  # noqa: E402
 from eryn.state import State  # noqa: E402
 
@@ -162,6 +164,20 @@ if __name__ == "__main__":
         # CombineMove (combine.py): a stretch move then a Gaussian move per iteration, each with its own tempering tail
         run_case("combine_sg", 57, 3, 24, 3, 30, ll_gauss_vec, [np.zeros(3), np.eye(3)], True, -5.0, 5.0,
                  moves_factory=lambda: [(CombineMove([StretchMove(), GaussianMove({"model_0": 0.25})]), 1.0)])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gauss_modes":
+        # GaussianMove(mode="random" | "sequential", factor) (gaussian.py:134-181): one random / the next dimension per
+        # call, proposal scale multiplied by exp(U(-log factor, log factor))
+        run_case("gauss_modes", 41, 4, 24, 3, 40, ll_gauss_vec, [np.zeros(4), corr_prec(4)], True, -5.0, 5.0,
+                 moves_factory=lambda: [(GaussianMove({"model_0": 0.16}, mode="random", factor=2.0), 0.5),
+                                        (GaussianMove({"model_0": 0.25}, mode="sequential"), 0.3),
+                                        (GaussianMove({"model_0": 0.04}, mode="vector"), 0.2)])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mt":
+        # multiple-try Metropolis with an independent proposal (multipletry.py:238-514 + mtdistgen.py): num_try draws from
+        # the priors per walker, one chosen by importance weight, balanced against the auxiliary set; mixed with stretch
+        run_case("mt_mix", 23, 3, 16, 3, 30, ll_gauss_vec, [np.zeros(3), np.eye(3) / 0.25], True, -2.0, 2.0,
+                 moves_factory=lambda: [(StretchMove(), 0.4), (MTDistGenMove(run_case.priors, num_try=6, independent=True), 0.6)])
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gibbs":
         # Gibbs splits at the parameter level (moves/move.py:113-402): a stretch move that updates parameters {0,1} then

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--nit", type=int, default=6)
     ap.add_argument("--seed", type=int, default=4242)
     ap.add_argument("--mix", type=int, default=0, help="1: stretch/gaussian schedule")
+    ap.add_argument("--like", default="gauss", help="gauss: correlated Gaussian; gmix: BASELINE config 4's mixture of 4 Gaussians")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -27,14 +28,18 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from eryn_b200 import dist as ed
     from eryn_b200.device import DeviceContext
-    from eryn_b200.likelihood import GaussianLikelihood
+    from eryn_b200.likelihood import GaussianLikelihood, GaussianMixtureLikelihood
     from eryn_b200.moves import GaussianMove, StretchMove
     from eryn_b200.prior import ProbDistContainer, uniform_dist
     T, W, d = a.ntemps, a.nwalkers, a.ndim
     A = np.random.RandomState(99).randn(d, d)
     P = np.linalg.inv(A @ A.T / d + np.eye(d))
     pri = ProbDistContainer({i: uniform_dist(-10.0, 10.0) for i in range(d)})
-    ctx = DeviceContext(pri, GaussianLikelihood(np.zeros(d), P), rng="philox", seed=a.seed)
+    like = GaussianLikelihood(np.zeros(d), P)
+    if a.like == "gmix":
+        r = np.random.RandomState(5)
+        like = GaussianMixtureLikelihood(r.uniform(-5, 5, size=(4, d)), r.uniform(0.5, 1.5, size=4), np.full(4, 0.25))
+    ctx = DeviceContext(pri, like, rng="philox", seed=a.seed)
     run = ed.ShardedRun(ctx, T, W, comm=a.comm)
     tc = ed.ShardedTemperatureControl(run, d, W)
     moves = [StretchMove(a=2.0), GaussianMove({"model_0": 0.01})]

@@ -37,7 +37,7 @@ def _acc(mv):  # CombineMove.accepted is the list of its sub-moves' counters (co
 
 
 def dev_moves(moves, priors=None):
-    from eryn_b200.moves import CombineMove, DistributionGenerate, GaussianMove, StretchMove
+    from eryn_b200.moves import CombineMove, DistributionGenerate, GaussianMove, MTDistGenMove, StretchMove
     out = []
     for m in moves:
         kw = {}
@@ -49,8 +49,14 @@ def dev_moves(moves, priors=None):
             out.append(StretchMove(a=m.get("a", 2.0), **kw))
         elif m["kind"] == "distgen":
             out.append(DistributionGenerate({"model_0": priors}))
+        elif m["kind"] == "mt":  # generate_dist as a bare ProbDistContainer, as the reference's test passes it
+            out.append(MTDistGenMove(priors, num_try=m["num_try"], independent=True))
         else:
             p = m["proposal"]
+            if p.get("mode") is not None:
+                kw["mode"] = p["mode"]
+            if p.get("factor") is not None:
+                kw["factor"] = p["factor"]
             out.append(GaussianMove({"model_0": p["scale"] ** 2 if p["kind"] == "scalar" else p["cov"]}, **kw))
     return out
 
@@ -174,6 +180,18 @@ PHILOX_CASES = {
     "gmix_d8": (4, 256, 8, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -10, 10),
     "gmix_k6_d20": (3, 128, 20, lambda d: gmix_like(d, K=6, seed=8), [dict(kind="stretch", a=2.0)], [1.0], 5, -10, 10),
     "gmix_tight_d20": (3, 128, 20, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -3.2, 3.2),
+    # GaussianMove modes and factor (gaussian.py:134-181)
+    "gauss_modes_d8": (3, 64, 8, c2_like,
+                       [dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.4, mode="random", factor=3.0)),
+                        dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.5, mode="sequential")),
+                        dict(kind="gaussian", proposal=dict(kind="matrix", cov=np.eye(8) * 0.01, chol=np.eye(8) * 0.1,
+                                                            factor=1.5))], [0.4, 0.4, 0.2], 12, -10, 10),
+    # multiple-try Metropolis (multipletry.py + mtdistgen.py): few and many tries, every likelihood functor
+    "mt_d4": (3, 64, 4, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d) / 0.25),
+              [dict(kind="stretch", a=2.0), dict(kind="mt", num_try=5)], [0.5, 0.5], 12, -2, 2),
+    "mt_25_d8": (4, 128, 8, c2_like, [dict(kind="mt", num_try=25)], [1.0], 6, -3, 3),
+    "mt_gmix_d20": (2, 64, 20, gmix_like, [dict(kind="mt", num_try=40), dict(kind="stretch", a=2.0)], [0.5, 0.5], 6, -6, 6),
+    "mt_rosen_d5": (2, 64, 5, lambda d: orc.RosenbrockLike(), [dict(kind="mt", num_try=9)], [1.0], 8, -2, 2),
     # Gibbs splits at the parameter level (move.py:113-402) in the exact-length (D = 8) and the padded (D = 5) kernels
     "gibbs_d8": (3, 64, 8, c2_like,
                  [dict(kind="stretch", a=2.0, gibbs=[cases.gmask(8, 0, 1, 2), cases.gmask(8, 3, 4, 5, 6, 7)]),

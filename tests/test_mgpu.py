@@ -29,9 +29,12 @@ def _free_port():
     return p
 
 
-def _oracle(T, W, d, nit, seed, mix):
+def _oracle(T, W, d, nit, seed, mix, like_kind="gauss"):
     A = np.random.RandomState(99).randn(d, d)
     like = orc.GaussianLike(np.zeros(d), np.linalg.inv(A @ A.T / d + np.eye(d)))
+    if like_kind == "gmix":
+        r = np.random.RandomState(5)
+        like = orc.GaussianMixtureLike(r.uniform(-5, 5, size=(4, d)), r.uniform(0.5, 1.5, size=4), np.full(4, 0.25))
     prior = orc.BoxPrior(np.full(d, -10.0), np.full(d, 10.0))
     moves = [dict(kind="stretch", a=2.0), dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.1))]
     weights = [0.5, 0.5] if mix else [1.0, 0.0]
@@ -66,18 +69,25 @@ def test_split_pass_single_rank_matches_oracle(tmp_path, T, W):
     _run_and_compare(tmp_path, "split", T, W, 0, nproc=1)
 
 
-def _run_and_compare(tmp_path, comm, T, W, mix, nproc):
+@pytest.mark.parametrize("comm", ["fused", "split"])
+def test_config4_full_size_sharded(tmp_path, comm):
+    """BASELINE config 4 at full size (32 temperatures x 16384 walkers x 20-d mixture of 4 Gaussians), the ladder sharded
+    over 2 GPUs, against the unsharded oracle"""
+    _run_and_compare(tmp_path, comm, 32, 16384, 0, nproc=2, d=20, nit=2, like_kind="gmix")
+
+
+def _run_and_compare(tmp_path, comm, T, W, mix, nproc, d=8, nit=6, like_kind="gauss"):
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
-    d, nit, seed = 8, 6, 4242
+    seed = 4242
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--out",
            str(tmp_path), "--comm", comm, "--ntemps", str(T), "--nwalkers", str(W), "--ndim", str(d), "--nit", str(nit), "--seed",
-           str(seed), "--mix", str(mix)]
+           str(seed), "--mix", str(mix), "--like", like_kind]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     got = np.load(tmp_path / f"mgpu_{comm}.npz")
-    smp, st, acc = _oracle(T, W, d, nit, seed, mix)
+    smp, st, acc = _oracle(T, W, d, nit, seed, mix, like_kind)
     np.testing.assert_allclose(got["coords"], st.coords, rtol=1e-10, atol=1e-300)
     np.testing.assert_allclose(got["logl"], st.logl, rtol=1e-10)
     np.testing.assert_allclose(got["logp"], st.logp, rtol=1e-10)

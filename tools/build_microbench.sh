@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/.."
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --fmad=false -Xcompiler -fPIC -DEB_PHASE_TIMERS"
 mkdir -p tools/_build
-for f in abi_core k_stretch k_gauss k_swap k_swap_split k_shard k_rj host_job k_stage; do
+for f in abi_core k_stretch k_gauss k_swap k_swap_split k_shard k_rj host_job k_stage k_mt; do
   nvcc $FLAGS -c eryn_b200/csrc/$f.cu -o tools/_build/$f.o &
 done
 wait

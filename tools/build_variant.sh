@@ -7,7 +7,7 @@ NAME=$1; shift
 OUT=tools/_build/$NAME
 mkdir -p $OUT
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --fmad=false -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $@"
-for f in abi_core k_swap k_swap_split k_shard k_rj host_job k_stage; do
+for f in abi_core k_swap k_swap_split k_shard k_rj host_job k_stage k_mt; do
   nvcc $FLAGS -c eryn_b200/csrc/$f.cu -o $OUT/$f.o &
 done
 for k in 0 1 2; do
