@@ -586,6 +586,45 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   }
   EB_MARK(31);
 
+  // ---- single-GPU passes with rows in registers: the source rows of the rungs that change are requested NOW, so that
+  //      their L2 latency runs under the count publication below (two block barriers and the global reductions); the
+  //      stores follow after it (all reads of a chain before any of its writes: the block barriers order them)
+  constexpr int RRX = RR > 0 ? RR : 1;
+  double rowv[RPL][RRX], lpv[RPL], llv[RPL];
+  long long dsl[RPL];
+#pragma unroll
+  for (int m = 0; m < RPL; ++m) dsl[m] = -1;
+  if (RR > 0 && !SHARDED && !EB_DBG_SKIP(1)) {
+#pragma unroll
+    for (int m = 0; m < RPL; ++m) {
+      const int r = lane + m * CL;
+      dsl[m] = -1;
+      if (valid && r < T) {
+        const int s = swap_source(sel_lo, sel_hi, r, T);
+        if (s != r) {
+          const size_t sslot = (size_t)s * W + pos[s];
+          dsl[m] = (long long)r * W + pos[r];
+          if (EB_DBG_SKIP(32)) {
+#pragma unroll
+            for (int e = 0; e < RRX; ++e) rowv[m][e] = 1.0;
+            lpv[m] = 0.0; llv[m] = ll[s];
+          } else
+          if ((LD & 3) == 0) {
+#pragma unroll
+            for (int e = 0; e < RRX; e += 4)
+              if (e < LD) ld256(c.coords + sslot * LD + e, rowv[m][e], rowv[m][e + 1], rowv[m][e + 2], rowv[m][e + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < RRX; ++e)
+              if (e < LD) rowv[m][e] = c.coords[sslot * LD + e];
+          }
+          if (!EB_DBG_SKIP(32)) lpv[m] = c.logp[sslot];
+          llv[m] = ll[s];
+        }
+      }
+    }
+  }
+
   // ---- swap counts: swaps_accepted[r-1] counts accepted swaps at rung r (:542): ballot over the chains of the warp,
   //      shared-memory atomics over the block, global atomics over the grid
   {
@@ -631,37 +670,6 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   if (EB_DBG_SKIP(1)) return;
   if (!SHARDED) {
     if (RR > 0) {
-      constexpr int RRX = RR > 0 ? RR : 1;
-      double rowv[RPL][RRX], lpv[RPL], llv[RPL];
-      long long dsl[RPL];
-#pragma unroll
-      for (int m = 0; m < RPL; ++m) {
-        const int r = lane + m * CL;
-        dsl[m] = -1;
-        if (valid && r < T) {
-          const int s = swap_source(sel_lo, sel_hi, r, T);
-          if (s != r) {
-            const size_t sslot = (size_t)s * W + pos[s];
-            dsl[m] = (long long)r * W + pos[r];
-            if (EB_DBG_SKIP(32)) {
-#pragma unroll
-              for (int e = 0; e < RRX; ++e) rowv[m][e] = 1.0;
-              lpv[m] = 0.0; llv[m] = ll[s];
-            } else
-            if ((LD & 3) == 0) {
-#pragma unroll
-              for (int e = 0; e < RRX; e += 4)
-                if (e < LD) ld256(c.coords + sslot * LD + e, rowv[m][e], rowv[m][e + 1], rowv[m][e + 2], rowv[m][e + 3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < RRX; ++e)
-                if (e < LD) rowv[m][e] = c.coords[sslot * LD + e];
-            }
-            if (!EB_DBG_SKIP(32)) lpv[m] = c.logp[sslot];
-            llv[m] = ll[s];
-          }
-        }
-      }
       EB_MARK(24);
       if (!EB_DBG_SKIP(128)) __syncwarp();
       EB_MARK(25);
