@@ -550,8 +550,9 @@ def run_gpu(args):
         _lib.check(lib.eb_run_host(ctypes.byref(job), 1), "eb_run_host")
     e2e_s = (time.perf_counter() - t0) / ne2e
     state_bytes = h_coords.numel() * 8 + h_logl.numel() * 8 + h_logp.numel() * 8 + h_betas.numel() * 8
-    e2e = dict(value=T * W / e2e_s, unit=UNIT, h2d_bytes_per_step=int(state_bytes + par.size * 8 + 3 * d * 8 + 4120),
-               d2h_bytes_per_step=int(state_bytes + 4120), ms_per_step=e2e_s * 1e3,
+    e2e = dict(value=T * W / e2e_s, unit=UNIT,
+               h2d_bytes_per_step=int(state_bytes + par.size * 8 + 3 * d * 8 + lib.eb_ctrl_size()),
+               d2h_bytes_per_step=int(state_bytes + 16 + 4 * (T - 1)), ms_per_step=e2e_s * 1e3,
                api="eb_run_host(job, niter=1): pinned host State -> H2D -> 3 kernels -> D2H, every step")
 
     # ---- CPU baseline (oracle port), bounded sample -------------------------------------------------------------

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -30,8 +31,25 @@ struct Pool {
   }
 };
 
+// page-locked host staging for the small per-call blocks (a cudaMemcpyAsync from pageable memory is staged by the driver
+// and blocks the caller for every such copy)
+struct PinnedPool {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return 1;
+    cap = bytes;
+    return 0;
+  }
+};
+
 struct HostCtx {
-  Pool coords, logl, logp, betas, prior, like, acc, acc_cnt, ctrl, row_scratch, logp_scratch;
+  Pool coords, logl, logp, betas, small, acc, acc_cnt, row_scratch, logp_scratch;
+  PinnedPool pin_in, pin_out;
   cudaStream_t stream = nullptr;
   std::mutex mu;
 };
@@ -61,9 +79,13 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   cudaStream_t s = cx.stream;
   const size_t n = (size_t)T * W;
   const size_t bc = n * L * D * sizeof(double), bs = n * sizeof(double);
+  // the small inputs travel as ONE block: [eb_ctrl | prior lo, hi, logpdf (3 D) | likelihood parameters], built in pinned memory
+  const size_t off_prior = (sizeof(eb_ctrl) + 15) & ~(size_t)15;
+  const size_t off_like = off_prior + 3 * (size_t)D * sizeof(double);
+  const size_t small_bytes = off_like + ((size_t)job->like_nparams + 1) * sizeof(double);
   if (cx.coords.ensure(bc) || cx.logl.ensure(bs) || cx.logp.ensure(bs) || cx.betas.ensure(T * sizeof(double)) ||
-      cx.prior.ensure(3 * D * sizeof(double)) || cx.like.ensure((job->like_nparams + 1) * sizeof(double)) ||
-      cx.acc.ensure(n) || cx.acc_cnt.ensure(n * sizeof(uint32_t)) || cx.ctrl.ensure(sizeof(eb_ctrl)) ||
+      cx.small.ensure(small_bytes) || cx.acc.ensure(n) || cx.acc_cnt.ensure(n * sizeof(uint32_t)) ||
+      cx.pin_in.ensure(small_bytes) || cx.pin_out.ensure(sizeof(eb_ctrl)) ||
       (T > 32 && (cx.row_scratch.ensure(bc) || cx.logp_scratch.ensure(bs))))
     return EB_ERR_CUDA;
 
@@ -73,33 +95,37 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
   HJ_CUDA(cudaMemcpyAsync(cx.logp.p, job->logp_host, bs, cudaMemcpyHostToDevice, s));
   if (job->betas_host)
     HJ_CUDA(cudaMemcpyAsync(cx.betas.p, job->betas_host, T * sizeof(double), cudaMemcpyHostToDevice, s));
-  std::vector<double> pr(3 * D);
-  for (int d = 0; d < D; ++d) {
-    double lo = job->prior_lo_host[d], hi = job->prior_hi_host[d];
-    if (lo > hi) { double t = lo; lo = hi; hi = t; }   // prior.py:29-32
-    if (lo == hi) return EB_ERR_INVALID;               // prior.py:33-34
-    pr[d] = lo; pr[D + d] = hi; pr[2 * D + d] = std::log(1.0 / (hi - lo));  // prior.py:40-41
+  {
+    unsigned char* blk = (unsigned char*)cx.pin_in.p;
+    eb_ctrl* hc_in = (eb_ctrl*)blk;
+    std::memset(hc_in, 0, sizeof(eb_ctrl));
+    hc_in->iter = job->iter0;
+    hc_in->iter_next = job->iter0;
+    hc_in->time = job->adapt_time0;
+    double* pr = (double*)(blk + off_prior);
+    for (int d = 0; d < D; ++d) {
+      double lo = job->prior_lo_host[d], hi = job->prior_hi_host[d];
+      if (lo > hi) { double t = lo; lo = hi; hi = t; }   // prior.py:29-32
+      if (lo == hi) return EB_ERR_INVALID;               // prior.py:33-34
+      pr[d] = lo; pr[D + d] = hi; pr[2 * D + d] = std::log(1.0 / (hi - lo));  // prior.py:40-41
+    }
+    if (job->like_nparams > 0)
+      std::memcpy(blk + off_like, job->like_params_host, (size_t)job->like_nparams * sizeof(double));
+    HJ_CUDA(cudaMemcpyAsync(cx.small.p, blk, small_bytes, cudaMemcpyHostToDevice, s));
   }
-  HJ_CUDA(cudaMemcpyAsync(cx.prior.p, pr.data(), 3 * D * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (job->like_nparams > 0)
-    HJ_CUDA(cudaMemcpyAsync(cx.like.p, job->like_params_host, job->like_nparams * sizeof(double),
-                            cudaMemcpyHostToDevice, s));
-  eb_ctrl hc;
-  std::memset(&hc, 0, sizeof(hc));
-  hc.iter = job->iter0;
-  hc.iter_next = job->iter0;
-  hc.time = job->adapt_time0;
-  HJ_CUDA(cudaMemcpyAsync(cx.ctrl.p, &hc, sizeof(hc), cudaMemcpyHostToDevice, s));
   HJ_CUDA(cudaMemsetAsync(cx.acc_cnt.p, 0, n * sizeof(uint32_t), s));
+  unsigned char* dsmall = (unsigned char*)cx.small.p;
+  const double* dprior = (const double*)(dsmall + off_prior);
+  const double* dlike = (const double*)(dsmall + off_like);
 
   // ---- iterations -----------------------------------------------------------------------------
   eb_state st;
   st.ntemps = T; st.nwalkers = W; st.nleaves = L; st.ndim = D; st.temp_offset = 0; st.inds_stride = 0;
   st.coords = (double*)cx.coords.p; st.logl = (double*)cx.logl.p; st.logp = (double*)cx.logp.p;
   st.inds = nullptr; st.betas = job->betas_host ? (double*)cx.betas.p : nullptr;
-  eb_prior prior{(const double*)cx.prior.p, (const double*)cx.prior.p + D, (const double*)cx.prior.p + 2 * D, nullptr};
-  eb_like like{job->like_kind, job->like_ncomp, job->like_nparams, 0, (const double*)cx.like.p};
-  eb_ctrl* dctrl = (eb_ctrl*)cx.ctrl.p;
+  eb_prior prior{dprior, dprior + D, dprior + 2 * D, nullptr};
+  eb_like like{job->like_kind, job->like_ncomp, job->like_nparams, 0, dlike};
+  eb_ctrl* dctrl = (eb_ctrl*)dsmall;
   eb_stretch_rng srng;
   std::memset(&srng, 0, sizeof(srng));
   srng.mode = EB_RNG_PHILOX; srng.randomize_split = job->randomize_split; srng.seed = job->seed;
@@ -134,11 +160,19 @@ extern "C" int eb_run_host(eb_host_job* job, int32_t niter) {
     HJ_CUDA(cudaMemcpyAsync(job->betas_host, cx.betas.p, T * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (job->accepted_count_host)
     HJ_CUDA(cudaMemcpyAsync(job->accepted_count_host, cx.acc_cnt.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  HJ_CUDA(cudaMemcpyAsync(&hc, cx.ctrl.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  // of the control block only the head (iter, time, error) and the swap counts come back, into pinned memory
+  eb_ctrl* hc = (eb_ctrl*)cx.pin_out.p;
+  HJ_CUDA(cudaMemcpyAsync(hc, dctrl, offsetof(eb_ctrl, swaps_work), cudaMemcpyDeviceToHost, s));
+  HJ_CUDA(cudaMemcpyAsync(hc->swaps_accepted, dctrl->swaps_accepted, sizeof(int32_t) * (size_t)(T > 1 ? T - 1 : 1),
+                          cudaMemcpyDeviceToHost, s));
   HJ_CUDA(cudaStreamSynchronize(s));
+  if (hc->error) {
+    std::fprintf(stderr, "eb_run_host: device error %u (a bounded in-kernel wait ran out)\n", hc->error);
+    return EB_ERR_CUDA;
+  }
   if (job->swaps_accepted_host)
-    for (int i = 0; i + 1 < T; ++i) job->swaps_accepted_host[i] = hc.swaps_accepted[i];
-  job->iter0 = hc.iter;
-  job->adapt_time0 = hc.time;
+    for (int i = 0; i + 1 < T; ++i) job->swaps_accepted_host[i] = hc->swaps_accepted[i];
+  job->iter0 = hc->iter;
+  job->adapt_time0 = hc->time;
   return EB_OK;
 }
