@@ -31,13 +31,20 @@ def main():
     from eryn_b200.moves import StretchMove
     from eryn_b200.prior import ProbDistContainer, uniform_dist
     T, W, d = 16 * world, 4096, 8
+    shape = os.environ.get("EB_BREAKDOWN_SHAPE")   # "c4": BASELINE config 4 (32 x 16384 x 20-d mixture), strong scaling
     A = np.random.RandomState(99).randn(d, d)
     P = np.linalg.inv(A @ A.T / d + np.eye(d))
+    like = GaussianLikelihood(np.zeros(d), P)
+    if shape == "c4":
+        from eryn_b200.likelihood import GaussianMixtureLikelihood
+        T, W, d = 32, 16384, 20
+        r = np.random.RandomState(5)
+        like = GaussianMixtureLikelihood(r.uniform(-5, 5, size=(4, d)), r.uniform(0.5, 1.5, size=4), np.full(4, 0.25))
     pri = ProbDistContainer({i: uniform_dist(-10.0, 10.0) for i in range(d)})
     prof = bool(os.environ.get("ERYN_B200_LIB"))
     modes = os.environ.get("EB_BREAKDOWN_MODES", "split,fused").split(",")
     for comm in modes:
-        ctx = DeviceContext(pri, GaussianLikelihood(np.zeros(d), P), rng="philox", seed=1)
+        ctx = DeviceContext(pri, like, rng="philox", seed=1)
         run = ed.ShardedRun(ctx, T, W, comm=comm)
         tc = ed.ShardedTemperatureControl(run, d, W)
         mv = StretchMove(a=2.0)
@@ -89,6 +96,10 @@ def main():
             if hasattr(run.lib, rd + "_cta") and getattr(run.lib, rd + "_cta")(cta) == 0:
                 a = np.frombuffer(cta, dtype=np.uint64).reshape(8, 1024).astype(np.int64)
                 nreal = (W + 7) // 8 if (T > 16 or comm == "split") else (W + 15) // 16
+                if comm == "split":  # chain groups of 8 warps x (32 / nl) chains, nl = lanes per chain = pow2 >= owned rungs
+                    nown = run.t_hi - run.t_lo
+                    nl = 4 if nown <= 4 else 8 if nown <= 8 else 16 if nown <= 16 else 32
+                    nreal = min(1024, (W + 8 * (32 // nl) - 1) // (8 * (32 // nl)))
                 names = {0: "start", 1: "keys", 2: "gathered", 3: "cascade", 4: "counts", 7: "mail-pushed", 5: "rows"}
                 txt = []
                 for slot in (0, 1, 2, 3, 4, 7, 5):
