@@ -553,7 +553,21 @@ def run_gpu(args):
     e2e = dict(value=T * W / e2e_s, unit=UNIT,
                h2d_bytes_per_step=int(state_bytes + par.size * 8 + 3 * d * 8 + lib.eb_ctrl_size()),
                d2h_bytes_per_step=int(state_bytes + 16 + 4 * (T - 1)), ms_per_step=e2e_s * 1e3,
-               api="eb_run_host(job, niter=1): pinned host State -> H2D -> 3 kernels -> D2H, every step")
+               api="eb_run_host(job, niter=1), every step: pinned host State in, host State out; wavefront schedule "
+                   "(temperature groups uploaded hottest first, moved as they land, ladder resolved in rung ranges, "
+                   "finished rungs downloaded while colder groups arrive; transfers by kernels on the mapped host "
+                   "arrays, one captured CUDA graph per call)")
+    # the same call with the plain schedule (upload all -> 3 kernels -> download all through the copy engines)
+    os.environ["EB_HOST_PIPE"] = "0"
+    for i in range(3):
+        _lib.check(lib.eb_run_host(ctypes.byref(job), 1), "eb_run_host")
+    t0 = time.perf_counter()
+    for i in range(ne2e):
+        _lib.check(lib.eb_run_host(ctypes.byref(job), 1), "eb_run_host")
+    e2e_plain_s = (time.perf_counter() - t0) / ne2e
+    os.environ.pop("EB_HOST_PIPE")
+    extra["e2e_plain_schedule"] = dict(value=T * W / e2e_plain_s, ms_per_step=e2e_plain_s * 1e3,
+                                       api="EB_HOST_PIPE=0: H2D -> 3 kernels -> D2H through the copy engines")
 
     # ---- CPU baseline (oracle port), bounded sample -------------------------------------------------------------
     cpu_v, cpu_s, cpu_n = run_cpu(wl, steps=10 ** 6, warmup=1, budget_s=0.5 if args.profile else 12.0)

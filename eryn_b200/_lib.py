@@ -163,6 +163,8 @@ SYMBOLS = {
     "eb_stretch_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), C.c_double, P(eb_stretch_rng), vp, vp, vp]),
     "eb_gaussian_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), P(eb_gauss_rng), vp, vp, vp]),
     "eb_pt_swap": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
+    "eb_pt_swap_range": (C.c_int, [P(eb_state), P(eb_swap_rng), vp, C.c_int32, C.c_int32, vp]),
+    "eb_pt_swap_finish": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_pt_swap_sharded": (C.c_int, [P(eb_shard), P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_publish_logl": (C.c_int, [P(eb_publish), vp, vp]),
     "eb_pt_swap_split": (C.c_int, [P(eb_split), P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
@@ -213,7 +215,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.eb_abi_version() != 6:
+    if lib.eb_abi_version() != 7:
         raise ErynB200Error("liberyn_b200.so ABI version mismatch; rebuild")
     for i, st in enumerate(STRUCTS):
         if lib.eb_struct_size(i) != C.sizeof(st):

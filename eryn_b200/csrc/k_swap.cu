@@ -781,6 +781,144 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   EB_MARK(21);
 }
 
+// ================================================================================================
+// K3w: the ladder in rung RANGES (wavefront form of the pass, eb_pt_swap_range / eb_pt_swap_finish)
+// ================================================================================================
+// eb_run_host streams the state in hottest temperature first.  Rung i is final as soon as the swap (i, i-1) has been
+// decided (tempering.py:515 walks i = T-1 .. 1), so the ladder can be resolved a few rungs at a time while colder
+// temperatures are still on their way in and finished rungs are already on their way out.  One thread owns one chain
+// (the same chains, positions sigma_r(chain) and uniforms as pt_swap_kernel: results are bit-identical) and walks the
+// rungs r_hi .. r_lo+1 in place: the walker being carried down stays in registers, the row of the rung below is
+// requested one rung ahead, and a slot is written only when its content changes.
+struct SwapRangeArgs {
+  Common c;                     // the FULL state (all T temperatures), betas = full ladder
+  int r_hi, r_lo;               // swaps (r, r-1) for r = r_hi .. r_lo+1
+  int permute;
+  uint32_t seed_lo, seed_hi; const unsigned long long* iter_dev; unsigned long long iter;
+  eb_ctrl* ctrl;
+};
+
+constexpr int RANGE_THREADS = 128;
+
+template <int RR>
+struct CarriedRow { double v[RR]; double ll, lp; };
+
+template <int RR>
+__device__ __forceinline__ void range_load(const Common& c, size_t slot, int LD, CarriedRow<RR>& w) {
+  if ((LD & 3) == 0) {
+#pragma unroll
+    for (int e = 0; e < RR; e += 4)
+      if (e < LD) ld256(c.coords + slot * LD + e, w.v[e], w.v[e + 1], w.v[e + 2], w.v[e + 3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < RR; ++e)
+      if (e < LD) w.v[e] = c.coords[slot * LD + e];
+  }
+  w.ll = c.logl[slot];
+  w.lp = c.logp[slot];
+}
+
+template <int RR>
+__device__ __forceinline__ void range_store(const Common& c, size_t slot, int LD, const CarriedRow<RR>& w) {
+  if ((LD & 3) == 0) {
+#pragma unroll
+    for (int e = 0; e < RR; e += 4)
+      if (e < LD) st256(c.coords + slot * LD + e, w.v[e], w.v[e + 1], w.v[e + 2], w.v[e + 3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < RR; ++e)
+      if (e < LD) c.coords[slot * LD + e] = w.v[e];
+  }
+  c.logl[slot] = w.ll;
+  c.logp[slot] = w.lp;
+}
+
+template <int RR>
+__global__ void __launch_bounds__(RANGE_THREADS) pt_swap_range_kernel(const __grid_constant__ SwapRangeArgs p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const Common& c = p.c;
+  const int W = c.W, LD = c.LD, nr = p.r_hi - p.r_lo + 1, tid = threadIdx.x;
+  double* s_dts = reinterpret_cast<double*>(smraw);                                  // [nr] betas[r-1] - betas[r]
+  uint32_t* s_keys = reinterpret_cast<uint32_t*>(smraw + sizeof(double) * nr);       // [nr][FEISTEL_ROUNDS]
+  int* s_cnt = reinterpret_cast<int*>(smraw + (sizeof(double) + sizeof(uint32_t) * FEISTEL_ROUNDS) * nr);   // [nr]
+  unsigned long long it = p.iter;
+  if (p.iter_dev) it = ld_volatile_u64(p.iter_dev);
+  const RngKey key = make_rng_key(p.seed_lo, p.seed_hi, it);
+  for (int i = tid; i < nr; i += blockDim.x) {
+    const int r = p.r_lo + i;
+    s_cnt[i] = 0;
+    s_dts[i] = r >= 1 ? c.betas[r - 1] - c.betas[r] : 0.0;                           // tempering.py:518-522
+    if (p.permute) Feistel::make_keys(key, TAG_SWAP_KEY, (uint32_t)r, s_keys + FEISTEL_ROUNDS * i);
+  }
+  __syncthreads();
+  const int chain = blockIdx.x * blockDim.x + tid;
+  const bool valid = chain < W;
+  auto position = [&](int r) -> size_t {
+    int pz = chain;
+    if (p.permute) {
+      Feistel sig;
+      sig.init_from(s_keys + FEISTEL_ROUNDS * (r - p.r_lo), (uint32_t)W);
+      pz = (int)sig((uint32_t)chain);
+    }
+    return (size_t)r * W + pz;
+  };
+  CarriedRow<RR> carry, low, nxt;
+  size_t slot_r = 0, slot_low = 0, slot_nxt = 0;
+  bool dirty = false;            // the carried walker differs from what slot_r holds
+  if (valid) {
+    slot_r = position(p.r_hi);
+    range_load<RR>(c, slot_r, LD, carry);
+    slot_nxt = position(p.r_hi - 1);
+    range_load<RR>(c, slot_nxt, LD, nxt);
+  }
+  for (int r = p.r_hi; r > p.r_lo; --r) {                                             // uniform trip count: the body votes
+    bool sel = false;
+    if (valid) {
+      low = nxt;
+      slot_low = slot_nxt;
+      if (r - 1 > p.r_lo) {                                                           // the rung after this one, requested now
+        slot_nxt = position(r - 2);
+        range_load<RR>(c, slot_nxt, LD, nxt);
+      }
+      // the uniforms of pt_swap_kernel: one Philox block serves rungs r and r + 8 of a chain
+      const uint4 q = stream(key, TAG_SWAP_U, (uint32_t)chain, (uint32_t)((r & 7) | ((r >> 4) << 3)));
+      const double u = ((r >> 3) & 1) ? u01_52(q.z, q.w) : u01_52(q.x, q.y);
+      sel = s_dts[r - p.r_lo] * (carry.ll - low.ll) > log(u);                         // tempering.py:535-541
+      if (sel) {
+        range_store<RR>(c, slot_r, LD, low);       // the walker of rung r-1 moves up; the carried one goes on down
+        dirty = true;
+      } else {
+        if (dirty) range_store<RR>(c, slot_r, LD, carry);   // the carried walker settles on rung r
+        carry = low;
+        dirty = false;
+      }
+      slot_r = slot_low;
+    }
+    const int n = __popc(__ballot_sync(0xffffffffu, sel));
+    if ((tid & 31) == 0 && n) atomicAdd(&s_cnt[r - p.r_lo], n);
+  }
+  if (valid && dirty) range_store<RR>(c, slot_r, LD, carry);
+  __syncthreads();
+  for (int i = tid + 1; i < nr; i += blockDim.x)                                       // swaps_accepted[r-1] = rung r (:542)
+    if (s_cnt[i]) atomicAdd(&p.ctrl->swaps_work[blockIdx.x % swap_slots(c.T)][p.r_lo + i - 1], s_cnt[i]);
+}
+
+// the tail of a pass resolved by range kernels: fold the counts, adapt the ladder, tick the iteration counter
+__global__ void __launch_bounds__(SWAP_THREADS) pt_swap_finish_kernel(const __grid_constant__ SwapArgs p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int T = p.T, tid = threadIdx.x;
+  double* s_betas = reinterpret_cast<double*>(smraw);
+  double* s_dts = s_betas + T;
+  int* s_cnt = reinterpret_cast<int*>(s_dts + T);
+  unsigned long long it = p.iter;
+  if (p.iter_dev) it = ld_volatile_u64(p.iter_dev);
+  for (int r = tid; r < T; r += blockDim.x) s_betas[r] = p.betas[r];
+  const long long time_now = *reinterpret_cast<const volatile long long*>(&p.ctrl->time);
+  __syncthreads();
+  pt_swap_adapt(p, T, p.c.W, 0, it, time_now, s_betas, s_dts, s_cnt);
+  if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(&p.ctrl->iter_next) = it + 1ull;
+}
+
 // K3r: replay mode — turn the host permutations of every rung into a per-position pair map.
 __global__ void __launch_bounds__(BLOCK) pt_pairmap_kernel(const int32_t* __restrict__ iperm,
                                                            const int32_t* __restrict__ i1perm,
@@ -972,6 +1110,46 @@ int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rn
   }
   if (T < 2) return eb_advance_iter(ctrl, stream);
   return launch_swap<true>(args, (cudaStream_t)stream);
+}
+
+int eb_pt_swap_range(const eb_state* st, const eb_swap_rng* rng, eb_ctrl* ctrl, int32_t r_hi, int32_t r_lo, void* stream) {
+  SwapRangeArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = fill_common(a.c, st, nullptr, nullptr, false);
+  if (rc) return rc;
+  if (!rng || !ctrl) return fail(EB_ERR_INVALID, "rng/ctrl is NULL");
+  if (rng->mode != EB_RNG_PHILOX) return fail(EB_ERR_UNSUPPORTED, "rung ranges run in philox mode only");
+  if (!st->betas) return fail(EB_ERR_INVALID, "swap pass needs betas");
+  if (st->inds || a.c.LD > 32) return fail(EB_ERR_UNSUPPORTED, "rung ranges move rows of up to 32 doubles without leaf flags");
+  if (r_lo < 0 || r_hi >= a.c.T || r_hi < r_lo) return fail(EB_ERR_INVALID, "bad rung range [%d, %d] of %d", r_lo, r_hi, a.c.T);
+  if (r_hi == r_lo) return EB_OK;
+  a.r_hi = r_hi; a.r_lo = r_lo; a.permute = rng->permute;
+  a.seed_lo = (uint32_t)(rng->seed & 0xFFFFFFFFull); a.seed_hi = (uint32_t)(rng->seed >> 32);
+  a.iter_dev = (const unsigned long long*)rng->iter_dev; a.iter = rng->iter;
+  a.ctrl = ctrl;
+  const int nr = r_hi - r_lo + 1;
+  const size_t sb = (sizeof(double) + sizeof(uint32_t) * FEISTEL_ROUNDS + sizeof(int)) * (size_t)nr;
+  const unsigned grid = (unsigned)((a.c.W + RANGE_THREADS - 1) / RANGE_THREADS);
+  if (a.c.LD <= 8) pt_swap_range_kernel<8><<<grid, RANGE_THREADS, sb, (cudaStream_t)stream>>>(a);
+  else if (a.c.LD <= 20) pt_swap_range_kernel<20><<<grid, RANGE_THREADS, sb, (cudaStream_t)stream>>>(a);
+  else pt_swap_range_kernel<32><<<grid, RANGE_THREADS, sb, (cudaStream_t)stream>>>(a);
+  return check_launch("pt_swap_range");
+}
+
+int eb_pt_swap_finish(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl, void* stream) {
+  SwapArgs args;
+  memset(&args, 0, sizeof(args));
+  int rc = fill_common(args.c, st, nullptr, nullptr, false);
+  if (rc) return rc;
+  rc = fill_swap_common(args, rng, adapt, ctrl);
+  if (rc) return rc;
+  if (!st->betas) return fail(EB_ERR_INVALID, "swap pass needs betas");
+  const int T = args.c.T;
+  if (T > 128) return fail(EB_ERR_UNSUPPORTED, "swap pass supports ladders of up to 128 temperatures (got %d)", T);
+  args.T = T; args.betas = args.c.betas;
+  const size_t sb = (2 * sizeof(double) + sizeof(int)) * (size_t)T;
+  pt_swap_finish_kernel<<<1, SWAP_THREADS, sb, (cudaStream_t)stream>>>(args);
+  return check_launch("pt_swap_finish");
 }
 
 }  // extern "C"

@@ -32,7 +32,7 @@ extern "C" {
 #define EB_API
 #endif
 
-#define EB_ABI_VERSION 6
+#define EB_ABI_VERSION 7
 #define EB_MAX_TEMPS 128
 #define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
 #define EB_MAX_RANKS 16 /* GPUs of one temperature-sharded run */
@@ -232,6 +232,22 @@ EB_API int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_
  *      Increments ctrl->iter.  `adapt` may be NULL (no adaptation, rj.py:381-382). */
 EB_API int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl,
                void* stream);
+
+/* ---- the same pass a few rungs at a time (the wavefront form eb_run_host pipelines against its host copies):
+ *      tempering.py:515 walks i = T-1 .. 1, and rung i is final once the swap (i, i-1) is decided, so
+ *        eb_pt_swap_range(r_hi, r_lo)   decides and applies the swaps (r, r-1) for r = r_hi .. r_lo+1 in place
+ *                                       (tempering.py:525-559 + do_swaps_indexing :351-482; philox mode, `st` is the
+ *                                       FULL state, rows of up to 32 doubles, no leaf flags) and adds the accepted
+ *                                       counts to ctrl->swaps_work;
+ *        eb_pt_swap_finish              folds the counts into swaps_accepted / swaps_total, applies adapt_temps
+ *                                       (:563-596) and increments ctrl->iter (and iter_next).
+ *      Ranges must be issued hot -> cold, adjoining (r_lo of one = r_hi of the next), from T-1 down to 0, followed by
+ *      one finish: the result is bit-identical to one eb_pt_swap with the same eb_swap_rng (same chains, positions and
+ *      uniforms). */
+EB_API int eb_pt_swap_range(const eb_state* st, const eb_swap_rng* rng, eb_ctrl* ctrl, int32_t r_hi, int32_t r_lo,
+                     void* stream);
+EB_API int eb_pt_swap_finish(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl,
+                      void* stream);
 
 /* ---- the same pass when the ladder is sharded over GPUs by temperature (one process per GPU; rank g
  *      owns temperatures [temp_begin[g], temp_begin[g+1]) of all walkers).  The moves need
@@ -472,7 +488,12 @@ EB_API int eb_box_log_prior(const double* q, const uint8_t* inds_sub, int32_t nr
 /* ---- reference-facing entry with HOST buffers: uploads the state, runs `niter` full
  *      iterations (move + swap pass) in philox mode, downloads the state.  This is the call
  *      bench.py's `e2e` leg times.  move_schedule_host[niter]: 0 = stretch, 1 = gaussian
- *      (the reference's per-iteration `random.choice(moves)`, ensemble.py:971); NULL = stretch. */
+ *      (the reference's per-iteration `random.choice(moves)`, ensemble.py:971); NULL = stretch.
+ *      A single tempered iteration on page-locked host arrays (niter == 1, cudaHostAlloc / cudaHostRegister memory) runs
+ *      as a wavefront: temperatures are uploaded hottest first in groups, every group is moved as soon as it has landed,
+ *      the ladder is resolved a rung range at a time (eb_pt_swap_range) and finished rungs are downloaded while colder
+ *      groups are still arriving, so the two PCIe directions and the kernels overlap; results are identical to the
+ *      plain sequence.  EB_HOST_PIPE=0 selects the plain sequence, EB_HOST_GROUPS the number of groups. */
 typedef struct {
   int32_t ntemps, nwalkers, nleaves, ndim;
   double* coords_host; double* logl_host; double* logp_host; double* betas_host; /* betas NULL = untempered */
