@@ -161,6 +161,9 @@ SYMBOLS = {
     "eb_struct_size": (C.c_size_t, [C.c_int]),
     "eb_eval_state": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), vp]),
     "eb_stretch_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), C.c_double, P(eb_stretch_rng), vp, vp, vp]),
+    "eb_resident_scratch_bytes": (C.c_size_t, [P(eb_state)]),
+    "eb_resident_run": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), C.c_double, P(eb_stretch_rng), P(eb_swap_rng),
+                                  P(eb_adapt), vp, C.c_int32, vp, vp, vp, C.c_size_t, vp]),
     "eb_gaussian_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), P(eb_gauss_rng), vp, vp, vp]),
     "eb_pt_swap": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_pt_swap_range": (C.c_int, [P(eb_state), P(eb_swap_rng), vp, C.c_int32, C.c_int32, vp]),

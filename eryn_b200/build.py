@@ -24,7 +24,7 @@ SOURCES = [("abi_core.cu", [], "abi_core.o"), ("k_swap.cu", [], "k_swap.o"), ("k
 for _k in range(3):
     SOURCES.append(("k_stretch.cu", [f"-DEB_ONLY_LIKE={_k}"], f"k_stretch_{_k}.o"))
     SOURCES.append(("k_gauss.cu", [f"-DEB_ONLY_LIKE={_k}"], f"k_gauss_{_k}.o"))
-HEADERS = ["common.cuh", "likelihoods.cuh", "rng.cuh", "stretch_lanes.cuh", os.path.join("..", "..", "include", "eryn_b200.h")]
+HEADERS = ["common.cuh", "likelihoods.cuh", "rng.cuh", "stretch_lanes.cuh", "resident.cuh", os.path.join("..", "..", "include", "eryn_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

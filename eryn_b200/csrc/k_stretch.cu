@@ -404,6 +404,10 @@ EB_STRETCH_LIKE_DEF(1)
 EB_STRETCH_LIKE_DEF(2)
 #endif
 
+}  // namespace eb
+#include "resident.cuh"
+namespace eb {
+
 #if EB_ONLY_LIKE == -1 || EB_ONLY_LIKE == 0
 static int fill_stretch_args(StretchArgs& a, const eb_state* st, double stretch_a, const eb_stretch_rng* rng,
                              bool need_u_acc) {
@@ -479,6 +483,67 @@ int eb_stretch_step(const eb_state* st, const eb_prior* prior, const eb_like* li
     if (rc) return rc;
   }
   return check_launch("stretch_step");
+}
+
+size_t eb_resident_scratch_bytes(const eb_state* st) {
+  if (!st || st->ntemps < 1 || st->nwalkers < 1 || st->nleaves < 1 || st->ndim < 1) return 0;
+  const size_t n = (size_t)st->ntemps * st->nwalkers;
+  const size_t RS = ((size_t)st->nleaves * st->ndim + 2 + 1) & ~(size_t)1;
+  return RES_HEADER_BYTES + ((n * sizeof(int32_t) + 15) & ~(size_t)15) + 2 * n * RS * sizeof(double);
+}
+
+int eb_resident_run(const eb_state* st, const eb_prior* prior, const eb_like* like, double a, const eb_stretch_rng* srng,
+                    const eb_swap_rng* wrng, const eb_adapt* adapt, eb_ctrl* ctrl, int32_t niter, uint8_t* accepted,
+                    uint32_t* accepted_count, void* scratch, size_t scratch_bytes, void* stream) {
+  ResidentArgs args;
+  memset(&args, 0, sizeof(args));
+  int rc = fill_common(args.sa.c, st, prior, like, true);
+  if (rc) return rc;
+  rc = fill_stretch_args(args.sa, st, a, srng, true);
+  if (rc) return rc;
+  const Common& c = args.sa.c;
+  if (!wrng || !ctrl) return fail(EB_ERR_INVALID, "swap rng / ctrl is NULL");
+  if (niter < 0) return fail(EB_ERR_INVALID, "niter < 0");
+  // what the resident kernel covers; everything else runs as eb_stretch_step + eb_pt_swap
+  if (!args.sa.philox || wrng->mode != EB_RNG_PHILOX) return fail(EB_ERR_UNSUPPORTED, "resident kernel: philox mode only");
+  if (!st->betas) return fail(EB_ERR_UNSUPPORTED, "resident kernel: tempered samplers only");
+  if (st->inds || c.per || args.sa.gmask) return fail(EB_ERR_UNSUPPORTED, "resident kernel: no leaf flags, periodic parameters or Gibbs splits");
+  if (c.T < 2 || c.T > RES_MAX_T) return fail(EB_ERR_UNSUPPORTED, "resident kernel: 2 <= ntemps <= %d", RES_MAX_T);
+  if (c.LD > 16) return fail(EB_ERR_UNSUPPORTED, "resident kernel: rows of up to 16 doubles");
+  if (st->temp_offset != 0) return fail(EB_ERR_UNSUPPORTED, "resident kernel: single-GPU states");
+  if (srng->iter_dev != wrng->iter_dev || (!srng->iter_dev && srng->iter != wrng->iter))
+    return fail(EB_ERR_INVALID, "resident kernel: move and pass must share the iteration counter");
+  args.niter = niter;
+  args.permute = wrng->permute;
+  args.wseed_lo = (uint32_t)(wrng->seed & 0xFFFFFFFFull); args.wseed_hi = (uint32_t)(wrng->seed >> 32);
+  args.adapt_on = adapt != nullptr;
+  args.adaptive = adapt ? adapt->adaptive : 0;
+  args.stop_adaptation = adapt ? adapt->stop_adaptation : -1;
+  args.lag = adapt ? adapt->adaptation_lag : 10000.0;
+  args.t0 = adapt ? adapt->adaptation_time : 100.0;
+  args.ctrl = ctrl;
+  args.sa.accepted = accepted; args.sa.accepted_count = accepted_count;
+  const bool launch = niter > 0;
+  if (launch) {
+    if (!accepted) return fail(EB_ERR_INVALID, "accepted is NULL");
+    if (!scratch || scratch_bytes < eb_resident_scratch_bytes(st))
+      return fail(EB_ERR_INVALID, "resident kernel: scratch of %zu bytes needed", eb_resident_scratch_bytes(st));
+    unsigned char* sc = (unsigned char*)scratch;
+    const size_t n = (size_t)c.T * c.W;
+    args.g_bar = (unsigned*)sc;
+    args.g_counts = (int*)(sc + 64);
+    args.g_src = (int32_t*)(sc + RES_HEADER_BYTES);
+    args.g_rec = (double*)(sc + RES_HEADER_BYTES + ((n * sizeof(int32_t) + 15) & ~(size_t)15));
+    EB_CUDA(cudaMemsetAsync(sc, 0, RES_HEADER_BYTES, (cudaStream_t)stream));
+  }
+  ResidentPlan plan;
+  switch (like->kind) {
+    case 0: rc = resident_like<0>(args, plan, launch, (cudaStream_t)stream); break;
+    case 1: rc = resident_like<1>(args, plan, launch, (cudaStream_t)stream); break;
+    default: rc = resident_like<2>(args, plan, launch, (cudaStream_t)stream); break;
+  }
+  if (rc) return rc;
+  return launch ? check_launch("resident") : EB_OK;
 }
 
 int eb_stretch_propose(const eb_state* st, double a, int32_t split, const eb_stretch_rng* rng, const double* period,

@@ -378,6 +378,36 @@ class DeviceContext(object):
                                        _ptr(self.ctrl), self.stream()), "eb_pt_swap")
         self.launches += 1
 
+    def resident_run(self, d, a, niter, randomize_split=True, permute=True, adapt=None, accepted_count=None):
+        """`niter` whole iterations (StretchMove + temper_comps) in ONE launch with the state resident in shared memory
+        (csrc/resident.cuh; ensemble.py:965-1045).  niter = 0 only asks whether this sampler is covered: returns False
+        if not (the caller then runs stretch_step + pt_swap), else True / the accept mask of the last iteration."""
+        if not self.fused or self.rng != "philox" or d.betas is None or self.periods is not None:
+            return False
+        T, W, L, D = d.shape
+        st = d.c_struct()
+        sr = _lib.eb_stretch_rng()
+        sr.mode, sr.seed, sr.iter_dev, sr.randomize_split = _lib.EB_RNG_PHILOX, self.seed, self.iter_ptr, int(bool(randomize_split))
+        wr = _lib.eb_swap_rng()
+        wr.mode, wr.seed, wr.iter_dev, wr.permute = _lib.EB_RNG_PHILOX, self.seed, self.iter_ptr, int(bool(permute))
+        ad = None
+        if adapt is not None:
+            ad = _lib.eb_adapt(int(adapt["adaptive"]), int(adapt["stop_adaptation"]), float(adapt["adaptation_lag"]),
+                               float(adapt["adaptation_time"]))
+        nbytes = int(self.lib.eb_resident_scratch_bytes(C.byref(st)))
+        scr = self.scratch("resident", (nbytes,), torch.uint8)
+        acc = self.accepted_mask(T, W)
+        rc = self.lib.eb_resident_run(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c), float(a), C.byref(sr),
+                                      C.byref(wr), C.byref(ad) if ad is not None else None, _ptr(self.ctrl), int(niter),
+                                      _ptr(acc), _ptr(accepted_count), _ptr(scr), nbytes, self.stream())
+        if rc == 2:   # EB_ERR_UNSUPPORTED: not a shape / configuration of the resident kernel
+            return False
+        _lib.check(rc, "eb_resident_run")
+        if niter == 0:
+            return True
+        self.launches += 1
+        return acc
+
     def advance_iter(self):
         _lib.check(self.lib.eb_advance_iter(_ptr(self.ctrl), self.stream()), "eb_advance_iter")
         self.launches += 1

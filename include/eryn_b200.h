@@ -221,6 +221,24 @@ EB_API int eb_eval_state(const eb_state* st, const eb_prior* prior, const eb_lik
 EB_API int eb_stretch_step(const eb_state* st, const eb_prior* prior, const eb_like* like, double a,
                     const eb_stretch_rng* rng, uint8_t* accepted, uint32_t* accepted_count, void* stream);
 
+/* ---- `niter` whole iterations — StretchMove.propose (red_blue.py:89-333, stretch.py:74-231) followed by
+ *      TemperatureControl.temper_comps (tempering.py:598-649) — in ONE launch with the walker state resident in shared
+ *      memory (the loop of ensemble.py:965-1045 for ensembles that fit the SMs: a thread-block cluster per temperature,
+ *      half steps separated by cluster barriers, the pass through an L2-resident record buffer and two grid barriers;
+ *      csrc/resident.cuh).  Same draws and arithmetic as eb_stretch_step + eb_pt_swap: the chain is bit-identical.
+ *      Philox mode, tempered, single leaf without leaf flags / periodic parameters / Gibbs splits, 2 <= ntemps <= 32,
+ *      rows of up to 16 doubles, and the state must fit shared memory: EB_ERR_UNSUPPORTED otherwise (niter = 0 only
+ *      answers that question, nothing is launched) and the caller runs the per-launch kernels.  `scratch`: device memory
+ *      of eb_resident_scratch_bytes(st) bytes, owned by the caller; both rng structs must name the same iteration counter
+ *      (eb_ctrl.iter), which is advanced by niter; `accepted` receives the mask of the last iteration, `accepted_count`
+ *      (nullable) is incremented per accepted proposal.  The launch needs the GPU to itself (its CTAs meet at grid
+ *      barriers; a bounded wait sets eb_ctrl.error = EB_DEVERR_SWAP_TIMEOUT). */
+EB_API size_t eb_resident_scratch_bytes(const eb_state* st);
+EB_API int eb_resident_run(const eb_state* st, const eb_prior* prior, const eb_like* like, double a,
+                    const eb_stretch_rng* srng, const eb_swap_rng* wrng, const eb_adapt* adapt, eb_ctrl* ctrl,
+                    int32_t niter, uint8_t* accepted, uint32_t* accepted_count, void* scratch, size_t scratch_bytes,
+                    void* stream);
+
 /* ---- GaussianMove: one Metropolis step over all walkers = mh.py:56-193 + gaussian.py:68-195. */
 EB_API int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* like,
                      const eb_gauss_rng* rng, uint8_t* accepted, uint32_t* accepted_count,
