@@ -33,6 +33,21 @@ constexpr int RES_THREADS = 512;
 constexpr int RES_MAX_T = 32;            // one rung per lane of a chain group
 constexpr size_t RES_HEADER_BYTES = 2048;   // scratch header: grid-barrier word, error word, swap counters [2][EB_MAX_TEMPS]
 
+// -DEB_RES_MARKS (tools/build_variant.sh): thread 0 of the first and the last CTA note %globaltimer at the phase
+// boundaries of the last iteration in the scratch header (tools/res_probe.py prints them)
+#ifdef EB_RES_MARKS
+#define RES_MARK(k)                                                                                   \
+  do {                                                                                                \
+    if (tid == 0 && (cta == 0 || cta == G - 1) && i == p.niter - 1) {                                 \
+      unsigned long long gt_;                                                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                         \
+      reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(p.g_bar) + 1152)[(cta == 0 ? 0 : 16) + (k)] = gt_; \
+    }                                                                                                 \
+  } while (0)
+#else
+#define RES_MARK(k) do { } while (0)
+#endif
+
 struct ResidentArgs {
   StretchArgs sa;        // c = the full state in global memory; a, Ns, randomize, seed, iter_dev / iter
   int niter;
@@ -193,6 +208,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) resident_kernel(const __grid_c
   for (int i = 0; i < p.niter; ++i) {
     const unsigned long long it = it0 + (unsigned long long)i;
     const int par = (int)(it & 1ull);
+    RES_MARK(0);
     // ================= the move: both red/blue halves, a cluster barrier after each =================
     {
       const RngKey key = make_rng_key(sa.seed_lo, sa.seed_hi, it);
@@ -231,7 +247,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) resident_kernel(const __grid_c
           if (keep) ac[lj] += 1u;
           af[lj] = keep ? 1 : 0;
         }
+        RES_MARK(1 + 2 * s);
         cluster.sync();
+        RES_MARK(2 + 2 * s);
       }
     }
     if (T < 2) continue;   // range(ntemps-1, 0, -1) is empty: no pass (time and counts untouched, as eb_pt_swap)
@@ -252,6 +270,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) resident_kernel(const __grid_c
       const int n2 = nw * RS / 2;
       for (int e = tid; e < n2; e += NT) dst[e] = src[e];
     }
+    RES_MARK(5);
     res_gbar_arrive(p.g_bar);
     bar_target += (unsigned)G;
     // state-independent prologue of the chains this CTA resolves: chain = cta + q * G
@@ -274,7 +293,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) resident_kernel(const __grid_c
         s_lu[q * T + r] = log(u);                                               // tempering.py:535
       }
     }
+    RES_MARK(6);
     res_gbar_wait(p.g_bar, bar_target, p.ctrl, &s_dead);
+    RES_MARK(7);
     // the counters of the NEXT pass: last read after barrier 2 of the previous pass, next written after barrier 1 of
     // the next one
     if (cta == 0)
@@ -315,9 +336,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) resident_kernel(const __grid_c
     __syncthreads();
     for (int r = tid; r < T - 1; r += NT)
       if (s_swcnt[r]) atomicAdd(&g_counts[r], s_swcnt[r]);
+    RES_MARK(8);
     res_gbar_arrive(p.g_bar);
     bar_target += (unsigned)G;
     res_gbar_wait(p.g_bar, bar_target, p.ctrl, &s_dead);
+    RES_MARK(9);
     // fetch the records that moved into this CTA's slots (do_swaps_indexing, tempering.py:351-482)
     for (int j = tid; j < nw; j += NT) {
       const int o = __ldcg(p.g_src + (size_t)t * W + w0 + j);
@@ -327,6 +350,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) resident_kernel(const __grid_c
         for (int e = 0; e < RS / 2; ++e) dst[e] = __ldcg(src + e);
       }
     }
+    RES_MARK(10);
     // counts and ladder adaptation (adapt_temps, tempering.py:563-596), redundantly in every CTA
     for (int r = tid; r < T - 1; r += NT) s_cnt2[r] = __ldcg(g_counts + r);
     __syncthreads();
@@ -362,7 +386,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) resident_kernel(const __grid_c
       }
       time_now += 1;                                                             // :596
     }
+    RES_MARK(11);
     cluster.sync();     // fetched records and the new ladder are in place before the next half step reads them
+    RES_MARK(12);
   }
 
   // ---- store: the state slice, the accept mask of the last iteration, the counters; CTA 0: ladder and control block

@@ -5,6 +5,7 @@ store — and the walkers live on the GPU between yields: `thin_by` iterations r
 no host synchronisation, and a host `State` is materialised only at yield/store points
 (ensemble.py:1013, :1045)."""
 import gc
+import os
 import warnings
 import weakref
 from collections.abc import Iterable
@@ -355,7 +356,7 @@ class EnsembleSampler(object):
         br = state.branches[self.branch_names[0]]
         if (self._mb or d is None or d.shape != tuple(br.coords.shape) or (d.inds is None) != bool(np.all(br.inds))
                 or d.betas is not betas_dev):
-            self._graphs, self._warm, self._ring = {}, set(), None
+            self._graphs, self._warm, self._ring, self._k12_ok = {}, set(), None, None
             return self.ctx.upload(state, betas=betas_dev)
         d.coords.copy_(torch.from_numpy(np.ascontiguousarray(br.coords, dtype=np.float64)))
         if d.inds is not None:
@@ -523,6 +524,22 @@ class EnsembleSampler(object):
         g[0].replay()
         self.ctx.launches += g[1]
 
+    _K12_MIN_ITERS = 8       # below this a block runs as replayed per-launch kernels (K12 pays ~25 us per launch)
+    _K12_MAX_WALKERS = 16384  # ntemps * nwalkers up to which K12 beats the per-launch kernels (profiles/r02_res_probe_small.txt)
+
+    def _k12_applies(self, mv, d):
+        """a plain StretchMove of a tempered single-leaf sampler on an ensemble small enough for the resident kernel"""
+        ok = getattr(self, "_k12_ok", None)
+        if ok is None:
+            from .moves.stretch import StretchMove
+            T, W, L, D = d.shape
+            limit = int(os.environ.get("EB_RESIDENT_MAX_WALKERS", self._K12_MAX_WALKERS))
+            ok = (type(mv) is StretchMove and mv.temperature_control is not None and T >= 2 and T * W <= limit
+                  and d.inds is None and mv._single_branch_splits(d.branch_name, L, D) == [(0, 0, L * D)]
+                  and self.ctx.resident_run(d, mv.a, 0) is True)
+            self._k12_ok = ok
+        return ok
+
     def _advance_resident(self, model, d, n):
         """n inner iterations, device resident, no host synchronisation"""
         R = self.num_repeats_in_model
@@ -534,6 +551,19 @@ class EnsembleSampler(object):
                 mv.propose(model, d)
                 self._warm.add(0)
                 todo -= 1
+            if todo >= self._K12_MIN_ITERS and self._k12_applies(mv, d):
+                # small ensembles: the whole block in ONE launch with the state resident in shared memory (K12,
+                # csrc/resident.cuh) — same chain bit for bit, no kernel boundaries between iterations
+                tc = mv.temperature_control
+                ad = None
+                if tc.adaptive:
+                    ad = dict(adaptive=True, stop_adaptation=tc.stop_adaptation, adaptation_lag=tc.adaptation_lag,
+                              adaptation_time=tc.adaptation_time)
+                T, W = d.shape[0], d.shape[1]
+                self.ctx.resident_run(d, mv.a, todo, randomize_split=mv.randomize_split, permute=tc.permute, adapt=ad,
+                                      accepted_count=mv._count_buffer(self.ctx, T, W))
+                mv._host_tick(todo)
+                return
             while todo > 0:
                 k = min(todo, self._CHUNK)
 

@@ -88,3 +88,24 @@ def test_resident_declines_what_it_does_not_cover():
     T, W = 32, 16384           # config 4: 92 MB of state
     ds = ctx.upload(State({"model_0": r.uniform(-3, 3, size=(T, W, 1, d))}), betas=torch.from_numpy(np.geomspace(1, 1e-3, T)).to(ctx.device))
     assert ctx.resident_run(ds, 2.0, 0) is False
+
+
+def test_sampler_uses_the_resident_kernel_for_small_ensembles(monkeypatch):
+    """run_mcmc(thin_by=20) on 8 x 256 walkers: blocks of >= 8 iterations go through K12 (one launch per block); the chain
+    equals the eager path and the replayed per-launch kernels bit for bit"""
+    from tests.test_gpu_api import make_sampler, same_backend, stretch_only
+    x0 = np.random.RandomState(3).uniform(-3, 3, size=(8, 256, 8))
+    runs = {}
+    for mode in ("eager", "graphs", "k12"):
+        monkeypatch.setenv("EB_RESIDENT_MAX_WALKERS", "0" if mode == "graphs" else "16384")
+        smp, _ = make_sampler(8, 256, 8, stretch_only)
+        smp.force_eager = mode == "eager"
+        last = smp.run_mcmc(x0, 5, thin_by=20, burn=30)
+        runs[mode] = (smp, last, smp.ctx.launches)
+    for mode in ("graphs", "k12"):
+        same_backend(runs["eager"][0], runs[mode][0])
+        for n in ("log_like", "log_prior", "betas"):
+            np.testing.assert_array_equal(getattr(runs["eager"][1], n), getattr(runs[mode][1], n))
+        np.testing.assert_array_equal(runs["eager"][1].branches_coords["model_0"], runs[mode][1].branches_coords["model_0"])
+    assert runs["k12"][0]._k12_ok is True and runs["graphs"][0]._k12_ok in (False, None)
+    assert runs["k12"][2] < runs["graphs"][2] / 4      # one launch per block instead of three per iteration
