@@ -525,7 +525,11 @@ class EnsembleSampler(object):
         self.ctx.launches += g[1]
 
     _K12_MIN_ITERS = 8       # below this a block runs as replayed per-launch kernels (K12 pays ~25 us per launch)
-    _K12_MAX_WALKERS = 16384  # ntemps * nwalkers up to which K12 beats the per-launch kernels (profiles/r02_res_probe_small.txt)
+    # ntemps * nwalkers up to which blocks go through K12.  0 = never (the default): measured against a replayed graph
+    # of the SAME block, whose launches are chained by programmatic dependent launch, K12 does not win at any size
+    # (8 x 256: 12.2 vs 11.7 us per iteration, config 2: 32.4 vs 19.5; bench.py extra.resident_kernel).
+    # EB_RESIDENT_MAX_WALKERS opts in.
+    _K12_MAX_WALKERS = 0
 
     def _k12_applies(self, mv, d):
         """a plain StretchMove of a tempered single-leaf sampler on an ensemble small enough for the resident kernel"""

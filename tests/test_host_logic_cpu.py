@@ -209,3 +209,31 @@ def test_swap_and_split_bijections_have_uniform_pair_frequencies():
         exp0 = nit * n0 / W
         z = (in0 - exp0) / np.sqrt(nit * (n0 / W) * (1 - n0 / W))
         assert np.abs(z).max() < 5.0, (W, z)
+
+
+def test_backend_grow_prefaults_without_touching_stored_samples():
+    """Backend.grow populates new chain pages from a helper thread (MADV_POPULATE_WRITE): stores that race with it keep
+    their contents, and the helper is optional (errors are swallowed)"""
+    import threading
+    from eryn_b200 import backend as bk
+    from eryn_b200.backend import Backend
+    T, W, D, n = 4, 4096, 8, 40          # 1 MB per sample, 40 MB of chain: above the prefault threshold
+    b = Backend()
+    b.reset(W, D, ntemps=T, branch_names=["model_0"])
+    b.grow(n)
+    r = np.random.RandomState(0)
+    samples = []
+    for it in range(n):
+        c = r.randn(T, W, 1, D)
+        samples.append(c)
+        b.save_arrays({"model_0": c}, None, c[..., 0, 0], c[..., 0, 1], np.ones(T), np.zeros((T, W)))
+    for t in threading.enumerate():
+        if t.name == "eryn_b200-prefault":
+            t.join(10.0)
+    chain = b.get_chain()["model_0"]
+    for it in range(n):
+        assert np.array_equal(chain[it], samples[it])
+    # growing again keeps what is stored
+    b.grow(n)
+    assert np.array_equal(b.get_chain()["model_0"][n - 1], samples[-1])
+    assert bk._prefault_async(np.empty((3, 4)), 0) is None      # small arrays: nothing to do
