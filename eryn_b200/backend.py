@@ -2,6 +2,7 @@
 (backend.py:616-1091).  HDF5 storage is host I/O outside this build's scope."""
 import ctypes
 import mmap
+import os
 import threading
 
 import numpy as np
@@ -18,11 +19,37 @@ __all__ = ["Backend"]
 # changed) and the call runs without the GIL.  Transparent huge pages are requested first where the system allows them.
 _MADV_HUGEPAGE, _MADV_POPULATE_WRITE = 14, 23
 _PREFAULT_MIN_BYTES = 8 << 20
-_PREFAULT_CHUNK = 16 << 20
+_PREFAULT_CHUNK = 4 << 20
+_PREFAULT_THREADS = 4     # page zeroing is per-core work: one thread populates ~4-5 GB/s
+
+
+# ---- the copy of a stored sample into the chain, split over a few threads (one host thread copies ~4 GB/s here) ------
+_COPY_MIN_BYTES = 2 << 20
+_COPY_THREADS = 4
+_copy_pool = None
+
+
+def _store_copy(dst, src):
+    """dst[...] = src for one sample; large samples are split along the first axis over a small thread pool (NumPy copies
+    release the GIL)"""
+    global _copy_pool
+    src = np.asarray(src)
+    if dst.nbytes < _COPY_MIN_BYTES or src.shape != dst.shape or dst.shape[0] < 2:
+        dst[...] = src
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _copy_pool = ThreadPoolExecutor(max_workers=_COPY_THREADS, thread_name_prefix="eryn_b200-store")
+    n = min(_COPY_THREADS, dst.shape[0])
+    edges = [dst.shape[0] * k // n for k in range(n + 1)]
+    futs = [_copy_pool.submit(np.copyto, dst[a:b], src[a:b]) for a, b in zip(edges[1:-1], edges[2:])]
+    np.copyto(dst[edges[0]:edges[1]], src[edges[0]:edges[1]])     # this thread takes the first part
+    for f in futs:
+        f.result()
 
 
 def _prefault_async(arr, first_row):
-    """populate the pages of arr[first_row:] in the background; returns the thread (or None if there is nothing to do)"""
+    """populate the pages of arr[first_row:] in the background; returns the threads (or None if there is nothing to do)"""
     if arr.size == 0 or first_row >= len(arr) or not arr.flags.c_contiguous:
         return None
     row_bytes = arr.strides[0]
@@ -40,17 +67,21 @@ def _prefault_async(arr, first_row):
     madvise.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
     madvise.restype = ctypes.c_int
 
-    def work(keep=arr):   # `keep` pins the array: its memory cannot be unmapped while the thread runs
-        madvise(lo, hi - lo, _MADV_HUGEPAGE)                       # advisory; ignored where THP is off
-        at = lo
+    madvise(lo, hi - lo, _MADV_HUGEPAGE)                           # advisory; ignored where THP is off
+    nthreads = max(1, min(_PREFAULT_THREADS, (os.cpu_count() or 2) // 2))
+
+    def work(j, keep=arr):   # `keep` pins the array: its memory cannot be unmapped while the thread runs
+        # thread j takes chunks j, j + nthreads, ...: all of them advance from the front, where the next store lands
+        at = lo + j * _PREFAULT_CHUNK
         while at < hi:
             n = min(_PREFAULT_CHUNK, hi - at)
             if madvise(at, n, _MADV_POPULATE_WRITE) != 0:          # old kernel / no memory: first touch will do it
                 break
-            at += n
-    th = threading.Thread(target=work, name="eryn_b200-prefault", daemon=True)
-    th.start()
-    return th
+            at += nthreads * _PREFAULT_CHUNK
+    threads = [threading.Thread(target=work, args=(j,), name="eryn_b200-prefault", daemon=True) for j in range(nthreads)]
+    for th in threads:
+        th.start()
+    return threads
 
 
 class Backend(object):
@@ -144,7 +175,7 @@ class Backend(object):
         if it >= len(self.log_like):
             raise ValueError("backend is full: call grow() first")
         for n in self.branch_names:
-            self.chain[n][it] = coords[n]
+            _store_copy(self.chain[n][it], coords[n])
             self.inds[n][it] = True if inds is None else inds[n]
         self.log_like[it] = log_like
         self.log_prior[it] = log_prior

@@ -221,7 +221,8 @@ bool is_pinned(const void* p) {
     cudaGetLastError();
     return false;
   }
-  return a.type == cudaMemoryTypeHost;
+  // page-locked (cudaHostAlloc / cudaHostRegister) AND addressable by the kernels under the same pointer
+  return a.type == cudaMemoryTypeHost && a.devicePointer == p;
 }
 
 int ensure_pipe_objects(HostCtx& cx) {
