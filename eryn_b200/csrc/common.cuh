@@ -78,7 +78,17 @@ static __device__ unsigned long long eb_dbg_cta[8][1024];                // mark
       if ((i) >= 16 && blockIdx.x < 1024) eb_dbg_cta[(i) & 7][blockIdx.x] = gt_;       \
     }                                                                                  \
   } while (0)
+// the same from whichever CTA gets there (e.g. the CTA that adapts the ladder): recorded as the "last CTA" value
+#define EB_MARK_ANY(i)                                                                 \
+  do {                                                                                 \
+    if ((threadIdx.x & 31) == 0) {                                                     \
+      unsigned long long gt_;                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                          \
+      eb_dbg_gmax[i] = gt_;                                                            \
+    }                                                                                  \
+  } while (0)
 #else
+#define EB_MARK_ANY(i) do { } while (0)
 #define EB_MARK(i) do { } while (0)
 #define EB_DEFINE_MARK_READER(NAME)
 #define EB_DBG_SKIP(bit) false

@@ -157,7 +157,7 @@ __device__ __forceinline__ void publish_ll(const SwapArgs& p, unsigned long long
 
 // slots the CTAs spread their partial swap counts and arrivals over (same-address atomics serialise in L2, but the
 // adapt CTA reads slots x (T-1) words): fewer slots for long ladders
-__device__ __forceinline__ int swap_slots(int T) { return T > 16 ? 8 : EB_SWAP_SLOTS; }
+__device__ __forceinline__ int swap_slots(int T) { return 8; }
 
 // The adapt CTA of the swap pass: wait for the counts of all `nreal` chain CTAs, fold them into swaps_accepted and
 // apply adapt_temps (tempering.py:563-596); ticks the iteration counter.
@@ -247,6 +247,75 @@ __device__ __forceinline__ void pt_swap_adapt(const SwapArgs& p, int T, int W, i
   if (tid == 0) ctrl->iter = it + 1ull;
 }
 
+// The same fold + adapt_temps done by ONE WARP: the warp of the chain CTA that published its counts last (ticket
+// election) runs it straight away — no extra CTA polling arrival words, no block barriers — while the other warps of that
+// CTA and all other CTAs go on moving rows.  Every operand and every operation is the one of pt_swap_adapt, so the ladder
+// is bit-identical.  `s_betas` / `s_dts` / `s_cnt` are the CTA's shared arrays; no other warp touches them after the
+// block barrier that precedes the count publication.
+__device__ __forceinline__ void pt_swap_adapt_warp(const SwapArgs& p, int T, int W, unsigned long long it, double* s_betas,
+                                                   double* s_dts, int* s_cnt) {
+  eb_ctrl* ctrl = p.ctrl;
+  const int lane = threadIdx.x & 31;
+  const int NS = swap_slots(T);
+  // fold the slot counts: all loads of a lane in flight together, then the sums; the slots are zeroed for the next pass
+  const long long time_now = *reinterpret_cast<const volatile long long*>(&ctrl->time);
+  for (int r = lane; r < T - 1; r += 32) {
+    int w8[8];
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) w8[sl] = sl < NS ? *reinterpret_cast<volatile int*>(&ctrl->swaps_work[sl][r]) : 0;
+    int v = 0;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) v += w8[sl];
+    s_cnt[r] = v;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl)
+      if (sl < NS) ctrl->swaps_work[sl][r] = 0;
+  }
+  __syncwarp();
+  if (p.adapt_on && p.adaptive && T > 1) {                                     // tempering.py:632-633
+    if (p.stop_adaptation < 0 || time_now < (long long)p.stop_adaptation) {   // :590
+      const double decay = p.lag / ((double)time_now + p.lag);                 // :571
+      const double kappa = decay / p.t0;                                       // :572
+      const double nw = (double)W;
+      for (int j = lane; j + 2 < T; j += 32) {
+        const double r0 = (double)s_cnt[j] / nw, r1 = (double)s_cnt[j + 1] / nw;   // :587
+        const double dS = kappa * (r0 - r1);                                   // :575
+        const double dT = 1.0 / s_betas[j + 1] - 1.0 / s_betas[j];             // :578
+        s_dts[j] = dT * exp(dS);                                               // :579
+      }
+      __syncwarp();
+      if (lane == 0) {                                                         // np.cumsum: sequential adds, in order
+        double cum = 0.0;
+        for (int j0 = 0; j0 + 2 < T; j0 += 8) {                                // operands loaded ahead of the dependent adds
+          double v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = j0 + k + 2 < T ? s_dts[j0 + k] : 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (j0 + k + 2 < T) { cum = cum + v[k]; s_dts[j0 + k] = cum; }
+        }
+      }
+      __syncwarp();
+      const double inv_b0 = 1.0 / s_betas[0];
+      for (int j = lane; j + 2 < T; j += 32) {
+        const double bold = s_betas[j + 1];
+        const double bnew = 1.0 / (s_dts[j] + inv_b0);                         // :580
+        p.betas[j + 1] = bold + (bnew - bold);                                 // :583, :593
+      }
+    }
+    if (lane == 0) ctrl->time = time_now + 1;                                  // :596
+  }
+  for (int r = lane; r < T - 1; r += 32) {
+    const int v = s_cnt[r];
+    ctrl->swaps_accepted[r] = v;
+    atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->swaps_total[r]), (unsigned long long)v);   // no round trip
+  }
+  if (lane == 0) {
+    ctrl->ticket = 0u;
+    ctrl->iter = it + 1ull;
+  }
+}
+
 constexpr int SWAP_THREADS = 256;
 constexpr int SWAP_AGES = 8;      // tests per walker evaluated ahead of the cascade walk (bits of one band byte)
 
@@ -271,10 +340,8 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   const int tid = threadIdx.x;
   const int g = tid / CL, lane = tid % CL;
   const int chain = blockIdx.x * cpb + g;
-  const bool valid = !adapt_cta && g < cpb && chain < W;
+  bool valid = !adapt_cta && g < cpb && chain < W;
   eb_ctrl* ctrl = p.ctrl;
-  long long time_now = 0;
-  if (adapt_cta && tid == 0) time_now = *reinterpret_cast<const volatile long long*>(&ctrl->time);
   // ---- prologue: nothing here reads the walker state, so under programmatic dependent launch it overlaps the move
   //      kernel that precedes this pass.  ctrl->iter is written only by this kernel's own tail.
   if (p.pdl == 2) pdl_wait();
@@ -348,7 +415,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
       s_ok = ok;
     }
     __syncthreads();
-    if (!s_ok) return;
+    if (!s_ok) valid = false;   // the error is sticky; the CTA still draws its ticket so that the pass ends consistently
   }
   EB_MARK(26);
   for (int r = tid; r < T; r += blockDim.x) {   // the ladder is adapted by the previous pass: read after the wait
@@ -644,24 +711,24 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     }
   }
 
-  // the counts are published here, before the rows move (fire-and-forget reductions + one arrival per CTA, all spread
-  // over EB_SWAP_SLOTS addresses: same-address atomics serialise in L2)
+  // the counts are published here, before the rows move: fire-and-forget reductions by warp 0, spread over EB_SWAP_SLOTS
+  // addresses (same-address atomics serialise in L2), then ONE ticket per CTA with release / acquire semantics.  The CTA
+  // that draws the last ticket has every count in sight: its warp 0 folds them and adapts the ladder at once
+  // (pt_swap_adapt_warp) while everybody else — its own other warps included — moves rows.
   __syncthreads();
-  if (EB_DBG_SKIP(2)) {
-    if (adapt_cta) return;
-  } else if (!adapt_cta) {
-    for (int r = tid; r < T - 1; r += blockDim.x)
+  if (adapt_cta) return;        // the extra CTA only published iter_next
+  if (!EB_DBG_SKIP(2) && tid < 32) {
+    for (int r = tid; r < T - 1; r += 32)
       if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[blockIdx.x % swap_slots(T)][r], s_cnt[r]);
-    __syncthreads();
-    if (tid == 0) {        // block barrier + one device-scope release by the signalling thread (cumulative)
-      fence_acq_rel_gpu();
-      atomicAdd(&ctrl->arrive[blockIdx.x % swap_slots(T)], 1u);
+    __syncwarp();
+    unsigned prev = 0u;
+    if (tid == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&ctrl->ticket) : "memory");
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev == (unsigned)(nreal - 1) && !EB_DBG_SKIP(4)) {
+      EB_MARK_ANY(28);
+      pt_swap_adapt_warp(p, T, W, it, s_betas, s_dts, s_cnt);
+      EB_MARK_ANY(23);
     }
-  } else {
-    if (EB_DBG_SKIP(4)) { if (tid < EB_SWAP_SLOTS) ctrl->arrive[tid] = 0u; return; }
-    pt_swap_adapt(p, T, W, nreal, it, time_now, s_betas, s_dts, s_cnt);
-    EB_MARK(23);
-    return;
   }
 
   EB_MARK(20);

@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 1700 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r02_pytest_gpu.log; cat gpurun_out/r02_pytest_gpu.log
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 | tee gpurun_out/r02_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3

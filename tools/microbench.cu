@@ -22,6 +22,7 @@ extern "C" int eb_debug_marks_stretch(long long* out_host);
 extern "C" int eb_debug_marks_swap(long long* out_host);
 extern "C" int eb_debug_marks_swap_global(unsigned long long* mn, unsigned long long* mx, int reset);
 extern "C" int eb_debug_marks_stretch_global(unsigned long long* mn, unsigned long long* mx, int reset);
+extern "C" int eb_debug_marks_swap_cta(unsigned long long* out8x1024);
 #endif
 
 #define CK(x)                                                                         \
@@ -207,7 +208,15 @@ int main(int argc, char** argv) {
     if (eb_debug_marks_swap_global(mn, mx, 0) == 0) {
       std::printf("swap marks, ns since CTA 0 start [CTA 0 .. adapt CTA]:");
       for (int i = 16; i <= 25; ++i) if (i != 22) std::printf(" m%d=%llu", i, mn[i] - mn[16]);
-      std::printf(" adapt-CTA-end=%llu", mx[23] - mn[16]);
+      std::printf(" | adapting warp: start=%llu end=%llu", mx[28] - mn[16], mx[23] - mn[16]);
+      std::printf(" | CTA 0: counts=%llu rows=%llu", mn[20] - mn[16], mn[21] - mn[16]);
+      static unsigned long long cta[8 * 1024];
+      if (eb_debug_marks_swap_cta(cta) == 0) {
+        const int nreal = (W + 15) / 16 < 1024 ? (W + 15) / 16 : 1024;   // chain CTAs of the 16-rung shape (16 chains per CTA)
+        unsigned long long c4 = 0, c5 = 0;
+        for (int b = 0; b < nreal; ++b) { if (cta[4 * 1024 + b] > c4) c4 = cta[4 * 1024 + b]; if (cta[5 * 1024 + b] > c5) c5 = cta[5 * 1024 + b]; }
+        std::printf(" | latest over the first %d CTAs: counts=%llu rows=%llu", nreal, c4 - mn[16], c5 - mn[16]);
+      }
       std::printf("\n");
     }
     eb_debug_marks_stretch_global(mn, mx, 1);
