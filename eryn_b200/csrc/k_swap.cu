@@ -711,23 +711,46 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     }
   }
 
-  // the counts are published here, before the rows move: fire-and-forget reductions by warp 0, spread over EB_SWAP_SLOTS
-  // addresses (same-address atomics serialise in L2), then ONE ticket per CTA with release / acquire semantics.  The CTA
-  // that draws the last ticket has every count in sight: its warp 0 folds them and adapts the ladder at once
-  // (pt_swap_adapt_warp) while everybody else — its own other warps included — moves rows.
+  // The counts are published here, before the rows move: fire-and-forget reductions spread over swap_slots() addresses
+  // (same-address atomics serialise in L2).
   __syncthreads();
-  if (adapt_cta) return;        // the extra CTA only published iter_next
-  if (!EB_DBG_SKIP(2) && tid < 32) {
-    for (int r = tid; r < T - 1; r += 32)
-      if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[blockIdx.x % swap_slots(T)][r], s_cnt[r]);
-    __syncwarp();
-    unsigned prev = 0u;
-    if (tid == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&ctrl->ticket) : "memory");
-    prev = __shfl_sync(0xffffffffu, prev, 0);
-    if (prev == (unsigned)(nreal - 1) && !EB_DBG_SKIP(4)) {
-      EB_MARK_ANY(28);
-      pt_swap_adapt_warp(p, T, W, it, s_betas, s_dts, s_cnt);
-      EB_MARK_ANY(23);
+  if (!SHARDED) {
+    // Single-GPU pass: warp 0 publishes and draws ONE ticket per CTA with release / acquire semantics.  The CTA that draws
+    // the last ticket has every count in sight: its warp 0 folds them and adapts the ladder at once (pt_swap_adapt_warp)
+    // while everybody else — its own other warps included — moves rows.  No CTA polls, no block barrier in the tail.
+    if (adapt_cta) return;        // the extra CTA only published iter_next
+    if (!EB_DBG_SKIP(2) && tid < 32) {
+      for (int r = tid; r < T - 1; r += 32)
+        if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[blockIdx.x % swap_slots(T)][r], s_cnt[r]);
+      __syncwarp();
+      unsigned prev = 0u;
+      if (tid == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&ctrl->ticket) : "memory");
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev == (unsigned)(nreal - 1) && !EB_DBG_SKIP(4)) {
+        EB_MARK_ANY(28);
+        pt_swap_adapt_warp(p, T, W, it, s_betas, s_dts, s_cnt);
+        EB_MARK_ANY(23);
+      }
+    }
+  } else {
+    // Sharded pass: the rows of a chain wait for mail from the peers, so no chain warp can spare the time: an extra CTA
+    // (the last block) spins on the arrival slots, folds the counts and adapts the ladder WHILE the others move rows.
+    if (EB_DBG_SKIP(2)) {
+      if (adapt_cta) return;
+    } else if (!adapt_cta) {
+      for (int r = tid; r < T - 1; r += blockDim.x)
+        if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[blockIdx.x % swap_slots(T)][r], s_cnt[r]);
+      __syncthreads();
+      if (tid == 0) {        // block barrier + one device-scope release by the signalling thread (cumulative)
+        fence_acq_rel_gpu();
+        atomicAdd(&ctrl->arrive[blockIdx.x % swap_slots(T)], 1u);
+      }
+    } else {
+      if (EB_DBG_SKIP(4)) { if (tid < EB_SWAP_SLOTS) ctrl->arrive[tid] = 0u; return; }
+      const long long time_now = *reinterpret_cast<const volatile long long*>(&ctrl->time);
+      pt_swap_adapt(p, T, W, nreal, it, time_now, s_betas, s_dts, s_cnt);
+      EB_MARK(23);
+      return;
     }
   }
 
