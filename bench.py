@@ -236,6 +236,9 @@ class SingleGpu(object):
         self.ctx = DeviceContext(self.pri, device_like(wl), device=dev, rng="philox", seed=seed)
         self.tc = TemperatureControl(d, W, ntemps=T)
         self.tc.bind(self.ctx)
+        # loops of plain stretch proposals: the swap pass leaves its ladder adaptation to the next stretch kernel
+        # (DeviceContext.lazy_adapt), as EnsembleSampler's resident path does
+        self.ctx.lazy_adapt = all(m["kind"] == "stretch" for m in wl["moves"]) and os.environ.get("EB_LAZY_ADAPT", "1") != "0"
         self.moves = []
         for m in wl["moves"]:
             mv = StretchMove(a=m["a"]) if m["kind"] == "stretch" else GaussianMove({"model_0": m["proposal"]["scale"] ** 2})
@@ -331,7 +334,23 @@ class SingleGpu(object):
         return self.graph_us(lambda: self.ctx.stretch_step(self.ds, 2.0, accepted_count=cnt), nrep)
 
     def swap_us(self, nrep):
-        return self.graph_us(lambda: self.tc.temper_comps(self.ds), nrep)
+        """average duration of the swap pass alone (back-to-back launches in one graph).  With lazy adaptation the passes
+        of such a graph pile their counts up unapplied, so the ladder and the control block are put back afterwards."""
+        from eryn_b200 import _lib
+        torch = self.torch
+        self.ctx.flush_adapt()
+        torch.cuda.synchronize()
+        betas0, ctrl0 = self.ds.betas.clone(), self.ctx.ctrl.clone()
+        us = self.graph_us(lambda: self.tc.temper_comps(self.ds), nrep)
+        torch.cuda.synchronize()
+        it_now = self.ctx.ctrl[:8].clone()
+        self.ctx.ctrl.copy_(ctrl0)
+        self.ctx.ctrl[:8].copy_(it_now)                              # the iteration counter keeps running
+        o = _lib.eb_ctrl.iter_next.offset
+        self.ctx.ctrl[o:o + 8].copy_(it_now)
+        self.ds.betas.copy_(betas0)
+        torch.cuda.synchronize()
+        return us
 
     def moved_fraction(self):
         """fraction of walkers whose row changes rung in one swap pass (measured on the current state)"""

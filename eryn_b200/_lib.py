@@ -41,7 +41,8 @@ class eb_stretch_rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("randomize_split", C.c_int32), ("pdl_chain", C.c_int32), ("_pad", C.c_int32),
                 ("list", vp * 2), ("rint", vp * 2), ("u_z", vp * 2), ("u_acc", vp * 2),
                 ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64),
-                ("gibbs_mask", C.c_uint32), ("gibbs_ndim", C.c_int32), ("gibbs_index", C.c_int32), ("_pad2", C.c_int32)]
+                ("gibbs_mask", C.c_uint32), ("gibbs_ndim", C.c_int32), ("gibbs_index", C.c_int32), ("_pad2", C.c_int32),
+                ("lazy_ctrl", vp)]
 
 
 class eb_gauss_rng(C.Structure):
@@ -54,14 +55,18 @@ class eb_gauss_rng(C.Structure):
 class eb_swap_rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("permute", C.c_int32), ("iperm", vp), ("i1perm", vp), ("u", vp),
                 ("next_pos", vp), ("u_at", vp), ("row_scratch", vp), ("logp_scratch", vp), ("inds_scratch", vp),
-                ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64)]
+                ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64), ("defer_adapt", C.c_int32),
+                ("_pad_defer", C.c_int32)]
 
 
 class eb_ctrl(C.Structure):
     _fields_ = [("iter", C.c_uint64), ("time", C.c_int64), ("ticket", C.c_uint32), ("error", C.c_uint32),
                 ("swaps_work", (C.c_int32 * EB_MAX_TEMPS) * EB_SWAP_SLOTS), ("swaps_accepted", C.c_int32 * EB_MAX_TEMPS),
                 ("swaps_total", C.c_uint64 * EB_MAX_TEMPS), ("arrive", C.c_uint32 * EB_SWAP_SLOTS),
-                ("iter_next", C.c_uint64)]
+                ("iter_next", C.c_uint64), ("adapt_pending", C.c_uint64), ("adapt_applied", C.c_uint64),
+                ("pend_time", C.c_int64), ("pend_adapt_on", C.c_int32), ("pend_adaptive", C.c_int32), ("pend_stop", C.c_int32),
+                ("pend_T", C.c_int32), ("pend_W", C.c_int32), ("_pad_lazy", C.c_int32), ("pend_lag", C.c_double),
+                ("pend_t0", C.c_double), ("pend_betas", C.c_double * EB_MAX_TEMPS)]
 
 
 class eb_adapt(C.Structure):
@@ -166,6 +171,7 @@ SYMBOLS = {
                                   P(eb_adapt), vp, C.c_int32, vp, vp, vp, C.c_size_t, vp]),
     "eb_gaussian_step": (C.c_int, [P(eb_state), P(eb_prior), P(eb_like), P(eb_gauss_rng), vp, vp, vp]),
     "eb_pt_swap": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
+    "eb_adapt_flush": (C.c_int, [vp, vp, vp]),
     "eb_pt_swap_range": (C.c_int, [P(eb_state), P(eb_swap_rng), vp, C.c_int32, C.c_int32, vp]),
     "eb_pt_swap_finish": (C.c_int, [P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
     "eb_pt_swap_sharded": (C.c_int, [P(eb_shard), P(eb_state), P(eb_swap_rng), P(eb_adapt), vp, vp]),
@@ -218,7 +224,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.eb_abi_version() != 7:
+    if lib.eb_abi_version() != 8:
         raise ErynB200Error("liberyn_b200.so ABI version mismatch; rebuild")
     for i, st in enumerate(STRUCTS):
         if lib.eb_struct_size(i) != C.sizeof(st):

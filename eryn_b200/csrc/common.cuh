@@ -101,6 +101,87 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const void* p) {
   return v;
 }
 
+// ---- lazy ladder adaptation (eb_swap_rng.defer_adapt) -------------------------------------------------------------------
+// A deferred pass leaves its accepted-swap counts in the rows [(it & 1) * LAZY_SLOTS, +LAZY_SLOTS) of eb_ctrl.swaps_work and
+// a snapshot of the ladder, the adaptation clock and the adaptation parameters.  Whoever needs the adapted ladder first —
+// every CTA of the next stretch kernel, in its prologue, or the one CTA of eb_adapt_flush — folds the counts and runs
+// adapt_temps (tempering.py:563-596; same operands, same operations, same order as pt_swap_adapt) on shared memory.
+// `writer` (one CTA) also does the bookkeeping of temper_comps: betas, swaps_accepted / swaps_total, the clock, and it
+// zeroes the count rows of the OTHER parity (last read one iteration ago, next written by the next pass).
+constexpr int LAZY_SLOTS = 8;
+struct LazyShared { double b[EB_MAX_TEMPS]; double d[EB_MAX_TEMPS]; int c[EB_MAX_TEMPS]; };
+
+// all threads of the CTA call this (block barriers inside); returns true if a pass was pending for iteration `it`, and
+// then sh.b holds the adapted ladder
+__device__ __forceinline__ bool lazy_adapt_apply(eb_ctrl* ctrl, unsigned long long it, double* betas_global, bool writer,
+                                                 bool zero_own, LazyShared& sh) {
+  const unsigned long long pend = ld_volatile_u64(&ctrl->adapt_pending);
+  if (pend == 0ull || pend != it) return false;        // uniform over the grid: written by a kernel that has completed
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int T = ctrl->pend_T, W = ctrl->pend_W;
+  const unsigned long long itp = pend - 1ull;
+  const int row0 = (int)(itp & 1ull) * LAZY_SLOTS;
+  for (int r = tid; r < T; r += nt) {
+    sh.b[r] = ctrl->pend_betas[r];
+    int v = 0;
+    if (r < T - 1) {
+      int w8[LAZY_SLOTS];
+#pragma unroll
+      for (int sl = 0; sl < LAZY_SLOTS; ++sl) w8[sl] = *reinterpret_cast<volatile int*>(&ctrl->swaps_work[row0 + sl][r]);
+#pragma unroll
+      for (int sl = 0; sl < LAZY_SLOTS; ++sl) v += w8[sl];
+    }
+    sh.c[r] = v;
+  }
+  const long long time_now = ctrl->pend_time;
+  const bool adapting = ctrl->pend_adapt_on && ctrl->pend_adaptive && T > 1;                     // tempering.py:632-633
+  const bool moving = adapting && (ctrl->pend_stop < 0 || time_now < (long long)ctrl->pend_stop);   // :590
+  __syncthreads();
+  if (moving) {
+    const double decay = ctrl->pend_lag / ((double)time_now + ctrl->pend_lag);                   // :571
+    const double kappa = decay / ctrl->pend_t0;                                                   // :572
+    const double nw = (double)W;
+    for (int j = tid; j + 2 < T; j += nt) {
+      const double r0 = (double)sh.c[j] / nw, r1 = (double)sh.c[j + 1] / nw;                      // :587
+      const double dS = kappa * (r0 - r1);                                                        // :575
+      const double dT = 1.0 / sh.b[j + 1] - 1.0 / sh.b[j];                                        // :578
+      sh.d[j] = dT * exp(dS);                                                                     // :579
+    }
+    __syncthreads();
+    if (tid == 0) {                                                                               // np.cumsum: sequential adds, in order
+      double cum = 0.0;
+      for (int j = 0; j + 2 < T; ++j) { cum = cum + sh.d[j]; sh.d[j] = cum; }
+    }
+    __syncthreads();
+    const double inv_b0 = 1.0 / sh.b[0];
+    for (int j = tid; j + 2 < T; j += nt) {          // every thread touches its own rungs only (and rung 0, never written)
+      const double bold = sh.b[j + 1];
+      const double bnew = 1.0 / (sh.d[j] + inv_b0);                                               // :580
+      sh.b[j + 1] = bold + (bnew - bold);                                                         // :583, :593
+    }
+    __syncthreads();
+  }
+  if (writer) {
+    for (int r = tid; r < T; r += nt) betas_global[r] = sh.b[r];
+    for (int r = tid; r < T - 1; r += nt) {
+      ctrl->swaps_accepted[r] = sh.c[r];
+      atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->swaps_total[r]), (unsigned long long)sh.c[r]);
+      const int other = (row0 ^ LAZY_SLOTS);
+#pragma unroll
+      for (int sl = 0; sl < LAZY_SLOTS; ++sl) ctrl->swaps_work[other + sl][r] = 0;
+      if (zero_own) {      // nobody else is reading them (eb_adapt_flush: one CTA)
+#pragma unroll
+        for (int sl = 0; sl < LAZY_SLOTS; ++sl) ctrl->swaps_work[row0 + sl][r] = 0;
+      }
+    }
+    if (tid == 0) {
+      if (adapting) ctrl->time = time_now + 1;                                                    // :596
+      ctrl->adapt_applied = pend;
+    }
+  }
+  return true;
+}
+
 struct Common {
   double* coords; double* logl; double* logp; uint8_t* inds; double* betas;
   int T, W, L, D, LD;

@@ -35,6 +35,7 @@ struct StretchArgs {
   // philox
   uint32_t seed_lo, seed_hi; const unsigned long long* iter_dev; unsigned long long iter;
   uint8_t* accepted; uint32_t* accepted_count;
+  eb_ctrl* lazy_ctrl;   // first launch of a step after a pass that deferred its ladder adaptation (common.cuh:lazy_adapt_apply)
   // split path outputs
   double* q_out; double* factors_out; int32_t* sub_out;
 };
@@ -103,14 +104,22 @@ __device__ __forceinline__ void job_load_own(const StretchArgs& p, int t, Walker
   j.active = c.inds ? (c.inds[slot] != 0) : true;
 }
 
+// the partner row c_temp (stretch.py:100): its own stage so that the request can go out ahead of other work
+template <int DMAX, bool EXACT>
+__device__ __forceinline__ void job_load_partner(const StretchArgs& p, int t, const WalkerJob<DMAX>& j, double (&cc)[DMAX]) {
+  if (!j.live) return;
+  const Common& c = p.c;
+  const int LD = EXACT ? DMAX : c.LD;
+  load_row<DMAX>(c.coords + ((size_t)t * c.W + j.wc) * LD, LD, cc);
+}
+
 template <int DMAX, int LIKE, bool EXACT>
-__device__ __forceinline__ void job_finish(const StretchArgs& p, const double* sm, int t, WalkerJob<DMAX>& j) {
+__device__ __forceinline__ void job_finish(const StretchArgs& p, const double* sm, int t, WalkerJob<DMAX>& j,
+                                           double (&cc)[DMAX]) {
   if (!j.live) return;
   const Common& c = p.c;
   const int LD = EXACT ? DMAX : c.LD;
   const size_t slot = (size_t)t * c.W + j.w;
-  double cc[DMAX];
-  load_row<DMAX>(c.coords + ((size_t)t * c.W + j.wc) * LD, LD, cc);          // c_temp (stretch.py:100)
   const bool tempered = c.betas != nullptr;
   if (c.per) {
     // periodic parameters (single leaf: LD == D): the distance from s to c goes through the boundary when that is
@@ -206,7 +215,17 @@ __global__ void __launch_bounds__(STRETCH_HALF_THREADS, 2) stretch_step_kernel(c
   pdl_wait();
   if (p.both || s == 0) pdl_launch_dependents();
   if (!own_early) job_load_own<DMAX, EXACT>(p, t, job);
-  if (c.betas) job.beta = c.betas[t];         // adapted by the swap pass: read after the wait
+  // the partner row is requested now unless this is the second half of a fused CTA (which must wait for the first)
+  double cc[DMAX];
+  const bool partner_early = !(p.both && s == 1);
+  if (partner_early) job_load_partner<DMAX, EXACT>(p, t, job, cc);
+  // a pass that deferred its ladder adaptation: every CTA folds the counts and adapts the ladder itself, under the row
+  // loads just issued (the ladder is needed at the Metropolis test only); CTA (0,0) also does the bookkeeping
+  __shared__ LazyShared lazy_sh;
+  bool lazy = false;
+  if (PHILOX && p.lazy_ctrl && (p.both || s == 0))
+    lazy = lazy_adapt_apply(p.lazy_ctrl, it, c.betas, blockIdx.x == 0 && blockIdx.y == 0, false, lazy_sh);
+  if (c.betas) job.beta = lazy ? lazy_sh.b[c.t0 + t] : c.betas[t];   // adapted by the swap pass: read after the wait
   stage_store(c, staged, sm);
   __syncthreads();                            // staged parameters visible
   EB_MARK(3);
@@ -215,7 +234,8 @@ __global__ void __launch_bounds__(STRETCH_HALF_THREADS, 2) stretch_step_kernel(c
   const bool wait_first = p.both && s == 1;
   if (wait_first) asm volatile("barrier.sync.aligned 0;" ::: "memory");
   EB_MARK(4);
-  job_finish<DMAX, LIKE, EXACT>(p, sm, t, job);
+  if (!partner_early) job_load_partner<DMAX, EXACT>(p, t, job, cc);
+  job_finish<DMAX, LIKE, EXACT>(p, sm, t, job, cc);
   EB_MARK(6);
   if (p.both && s == 0) asm volatile("barrier.sync.aligned 0;" ::: "memory");
   EB_MARK(7);
@@ -429,6 +449,7 @@ static int fill_stretch_args(StretchArgs& a, const eb_state* st, double stretch_
   a.q_out = nullptr; a.factors_out = nullptr; a.sub_out = nullptr;
   a.accepted = nullptr; a.accepted_count = nullptr;
   a.both = 0; a.split = 0; a.pdl = 0;
+  a.lazy_ctrl = nullptr;
   a.gmask = rng->gibbs_mask; a.gndim = rng->gibbs_ndim; a.gidx = rng->gibbs_index;
   if (a.gmask) {
     const int LD = st->nleaves * st->ndim;
@@ -475,6 +496,7 @@ int eb_stretch_step(const eb_state* st, const eb_prior* prior, const eb_like* li
   for (int l = 0; l < nlaunch; ++l) {
     args.split = l;
     args.pdl = ((l == 1 && (pdl_mask & 1)) || (l == 0 && rng->pdl_chain && (pdl_mask & 4))) ? 1 : 0;
+    args.lazy_ctrl = (l == 0 && args.philox && st->temp_offset == 0) ? (eb_ctrl*)rng->lazy_ctrl : nullptr;
     switch (like->kind) {
       case 0: rc = launch_stretch_like<0>(args, s); break;
       case 1: rc = launch_stretch_like<1>(args, s); break;

@@ -45,6 +45,7 @@ struct SwapArgs {
   eb_ctrl* ctrl;
   int adapt_on, adaptive, stop_adaptation; double lag, t0;
   int dbg_skip;
+  int defer;                                      // single-GPU pass: leave counts + snapshot for a lazy adaptation
 };
 
 // CTAs of the publish kernel for `ndoubles` of logl (must match k_shard.cu: a flag word counts publishing CTAs)
@@ -256,20 +257,20 @@ __device__ __forceinline__ void pt_swap_adapt_warp(const SwapArgs& p, int T, int
                                                    double* s_dts, int* s_cnt) {
   eb_ctrl* ctrl = p.ctrl;
   const int lane = threadIdx.x & 31;
-  const int NS = swap_slots(T);
-  // fold the slot counts: all loads of a lane in flight together, then the sums; the slots are zeroed for the next pass
+  const int row0 = (int)(it & 1ull) * LAZY_SLOTS;   // single-GPU passes alternate between two sets of count rows (common.cuh)
+  // fold the slot counts: all loads of a lane in flight together, then the sums; the rows are zeroed for the passes to
+  // come — both parities: the other one may hold the counts of a deferred pass that has been applied since
   const long long time_now = *reinterpret_cast<const volatile long long*>(&ctrl->time);
   for (int r = lane; r < T - 1; r += 32) {
-    int w8[8];
+    int w8[LAZY_SLOTS];
 #pragma unroll
-    for (int sl = 0; sl < 8; ++sl) w8[sl] = sl < NS ? *reinterpret_cast<volatile int*>(&ctrl->swaps_work[sl][r]) : 0;
+    for (int sl = 0; sl < LAZY_SLOTS; ++sl) w8[sl] = *reinterpret_cast<volatile int*>(&ctrl->swaps_work[row0 + sl][r]);
     int v = 0;
 #pragma unroll
-    for (int sl = 0; sl < 8; ++sl) v += w8[sl];
+    for (int sl = 0; sl < LAZY_SLOTS; ++sl) v += w8[sl];
     s_cnt[r] = v;
 #pragma unroll
-    for (int sl = 0; sl < 8; ++sl)
-      if (sl < NS) ctrl->swaps_work[sl][r] = 0;
+    for (int sl = 0; sl < 2 * LAZY_SLOTS; ++sl) ctrl->swaps_work[sl][r] = 0;
   }
   __syncwarp();
   if (p.adapt_on && p.adaptive && T > 1) {                                     // tempering.py:632-633
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     }
   }
 
+  unsigned defer_ticket = 0xffffffffu;
   // The counts are published here, before the rows move: fire-and-forget reductions spread over swap_slots() addresses
   // (same-address atomics serialise in L2).
   __syncthreads();
@@ -718,18 +720,38 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
     // Single-GPU pass: warp 0 publishes and draws ONE ticket per CTA with release / acquire semantics.  The CTA that draws
     // the last ticket has every count in sight: its warp 0 folds them and adapts the ladder at once (pt_swap_adapt_warp)
     // while everybody else — its own other warps included — moves rows.  No CTA polls, no block barrier in the tail.
-    if (adapt_cta) return;        // the extra CTA only published iter_next
+    if (adapt_cta) {              // the extra CTA published iter_next at its start
+      if (p.defer) {
+        // deferred adaptation: the snapshot the next stretch kernel (or eb_adapt_flush) adapts from.  Taken here, after the
+        // grid-dependency wait: the ladder and the clock may have been written by the kernel before this pass.
+        for (int r = tid; r < T; r += blockDim.x) ctrl->pend_betas[r] = p.betas[r];
+        if (tid == 0) {
+          ctrl->pend_time = *reinterpret_cast<const volatile long long*>(&ctrl->time);
+          ctrl->pend_adapt_on = p.adapt_on; ctrl->pend_adaptive = p.adaptive; ctrl->pend_stop = p.stop_adaptation;
+          ctrl->pend_T = T; ctrl->pend_W = W; ctrl->pend_lag = p.lag; ctrl->pend_t0 = p.t0;
+          ctrl->adapt_pending = it + 1ull;
+        }
+      }
+      return;
+    }
     if (!EB_DBG_SKIP(2) && tid < 32) {
+      const int row = (int)(it & 1ull) * LAZY_SLOTS + (int)(blockIdx.x % LAZY_SLOTS);
       for (int r = tid; r < T - 1; r += 32)
-        if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[blockIdx.x % swap_slots(T)][r], s_cnt[r]);
-      __syncwarp();
-      unsigned prev = 0u;
-      if (tid == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&ctrl->ticket) : "memory");
-      prev = __shfl_sync(0xffffffffu, prev, 0);
-      if (prev == (unsigned)(nreal - 1) && !EB_DBG_SKIP(4)) {
-        EB_MARK_ANY(28);
-        pt_swap_adapt_warp(p, T, W, it, s_betas, s_dts, s_cnt);
-        EB_MARK_ANY(23);
+        if (s_cnt[r]) atomicAdd(&ctrl->swaps_work[row][r], s_cnt[r]);
+      if (!p.defer) {
+        __syncwarp();
+        unsigned prev = 0u;
+        if (tid == 0) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&ctrl->ticket) : "memory");
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev == (unsigned)(nreal - 1) && !EB_DBG_SKIP(4)) {
+          EB_MARK_ANY(28);
+          pt_swap_adapt_warp(p, T, W, it, s_betas, s_dts, s_cnt);
+          EB_MARK_ANY(23);
+        }
+      } else if (tid == 0) {
+        // deferred: nobody folds here, so nothing has to be released — a relaxed ticket only finds the CTA that ticks the
+        // iteration counter once every CTA has read it (its value is looked at after the rows have been issued)
+        asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(defer_ticket) : "l"(&ctrl->ticket) : "memory");
       }
     }
   } else {
@@ -869,6 +891,10 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
   }
 
   EB_MARK(21);
+  if (!SHARDED && p.defer && tid == 0 && defer_ticket == (unsigned)(nreal - 1)) {
+    ctrl->ticket = 0u;
+    ctrl->iter = it + 1ull;      // every CTA has read the counter: this was the last ticket
+  }
 }
 
 // ================================================================================================
@@ -1009,6 +1035,18 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_finish_kernel(const __gr
   if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(&p.ctrl->iter_next) = it + 1ull;
 }
 
+// eb_adapt_flush: a deferred adaptation applied by one CTA (whoever needs the ladder before the next stretch kernel)
+__global__ void __launch_bounds__(128) adapt_flush_kernel(eb_ctrl* ctrl, double* betas) {
+  __shared__ LazyShared sh;
+  const unsigned long long pend = ld_volatile_u64(&ctrl->adapt_pending);
+  if (pend == 0ull || pend == ld_volatile_u64(&ctrl->adapt_applied)) return;   // nothing deferred, or applied already
+  lazy_adapt_apply(ctrl, pend, betas, true, true, sh);
+  // a stretch kernel looks at adapt_pending only (its CTAs must all take the same decision while CTA (0,0) does the
+  // bookkeeping): after a flush there is nothing left for it
+  __syncthreads();
+  if (threadIdx.x == 0) ctrl->adapt_pending = 0ull;
+}
+
 // K3r: replay mode — turn the host permutations of every rung into a per-position pair map.
 __global__ void __launch_bounds__(BLOCK) pt_pairmap_kernel(const int32_t* __restrict__ iperm,
                                                            const int32_t* __restrict__ i1perm,
@@ -1041,6 +1079,8 @@ static int fill_swap_common(SwapArgs& args, const eb_swap_rng* rng, const eb_ada
   args.lag = adapt ? adapt->adaptation_lag : 10000.0;
   args.t0 = adapt ? adapt->adaptation_time : 100.0;
   if (!args.philox && rng->mode != EB_RNG_REPLAY) return fail(EB_ERR_INVALID, "unknown rng mode %d", rng->mode);
+  args.defer = rng->defer_adapt ? 1 : 0;
+  if (args.defer && !args.philox) return fail(EB_ERR_INVALID, "defer_adapt is a philox-mode option");
   return EB_OK;
 }
 
@@ -1157,6 +1197,7 @@ int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rn
   rc = fill_swap_common(args, rng, adapt, ctrl);
   if (rc) return rc;
   if (!args.philox) return fail(EB_ERR_UNSUPPORTED, "temperature-sharded swaps run in philox mode only");
+  if (args.defer) return fail(EB_ERR_UNSUPPORTED, "defer_adapt: single-GPU passes only");
   if (sh->world < 1 || sh->world > EB_MAX_RANKS || sh->rank < 0 || sh->rank >= sh->world)
     return fail(EB_ERR_INVALID, "bad rank/world %d/%d", sh->rank, sh->world);
   const int T = sh->ntemps_total;
@@ -1200,6 +1241,12 @@ int eb_pt_swap_sharded(const eb_shard* sh, const eb_state* dst, const eb_swap_rn
   }
   if (T < 2) return eb_advance_iter(ctrl, stream);
   return launch_swap<true>(args, (cudaStream_t)stream);
+}
+
+int eb_adapt_flush(eb_ctrl* ctrl, double* betas, void* stream) {
+  if (!ctrl || !betas) return fail(EB_ERR_INVALID, "ctrl/betas is NULL");
+  adapt_flush_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(ctrl, betas);
+  return check_launch("adapt_flush");
 }
 
 int eb_pt_swap_range(const eb_state* st, const eb_swap_rng* rng, eb_ctrl* ctrl, int32_t r_hi, int32_t r_lo, void* stream) {

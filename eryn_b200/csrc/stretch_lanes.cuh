@@ -208,7 +208,11 @@ __global__ void __launch_bounds__(STRETCH_HALF_THREADS, EB_LANES_MINB) stretch_l
   pdl_wait();
   if (s == 0) pdl_launch_dependents();
   const bool tempered = c.betas != nullptr;
-  const double beta = tempered ? c.betas[t] : 1.0;   // adapted by the swap pass: read after the wait
+  __shared__ LazyShared lazy_sh;                     // a pass that deferred its ladder adaptation (stretch_step_kernel)
+  bool lazy = false;
+  if (PHILOX && p.lazy_ctrl && s == 0)
+    lazy = lazy_adapt_apply(p.lazy_ctrl, it, c.betas, blockIdx.x == 0 && blockIdx.y == 0, false, lazy_sh);
+  const double beta = tempered ? (lazy ? lazy_sh.b[c.t0 + t] : c.betas[t]) : 1.0;   // adapted by the swap pass: read after the wait
   const double* lo = sm;
   const double* hi = sm + D;
   const double* lpdf = sm + 2 * D;

@@ -99,6 +99,13 @@ class DeviceContext(object):
         self.ctrl = torch.zeros(self.lib.eb_ctrl_size(), dtype=torch.uint8, device=self.device)
         self._scratch = {}
         self.launches = 0  # kernels launched through this context (bench.py reports it)
+        # Lazy ladder adaptation (include/eryn_b200.h: eb_swap_rng.defer_adapt): while it is on, a swap pass ends with its
+        # row moves and the NEXT stretch kernel folds the counts and adapts the ladder in its prologue — 3 us less per
+        # iteration at config 2.  Everything else that looks at betas / swap counts / the clock goes through
+        # flush_adapt() first (a one-CTA kernel, no-op when nothing is pending).  Only loops that consist of plain
+        # StretchMove proposals switch it on (EnsembleSampler._sample_resident, bench.py).
+        self.lazy_adapt = False
+        self._lazy_betas = None
 
     # ---- helpers ------------------------------------------------------------------------------
     def stream(self):
@@ -125,11 +132,20 @@ class DeviceContext(object):
         its programmatic dependents, so the next stretch kernel can start its draws early (pdl_chain)."""
         return C.c_void_p(self.ctrl.data_ptr() + _lib.eb_ctrl.iter_next.offset)
 
+    def flush_adapt(self):
+        """apply a deferred ladder adaptation now (no-op on the device if nothing is pending)"""
+        if self._lazy_betas is not None:
+            _lib.check(self.lib.eb_adapt_flush(_ptr(self.ctrl), _ptr(self._lazy_betas), self.stream()), "eb_adapt_flush")
+            self.launches += 1
+            if not self.lazy_adapt:
+                self._lazy_betas = None
+
     def read_ctrl(self):
+        self.flush_adapt()
         return _lib.eb_ctrl.from_buffer_copy(self.ctrl.cpu().numpy().tobytes())
 
     def write_ctrl(self, iter=None, time=None):
-        c = self.read_ctrl()
+        c = self.read_ctrl()   # (flushes a deferred adaptation first)
         if iter is not None:
             c.iter = int(iter)
             c.iter_next = int(iter)
@@ -159,13 +175,14 @@ class DeviceContext(object):
 
     def check_error(self):
         """raise if a kernel set eb_ctrl.error (a bounded in-kernel wait ran out): the chain is invalid from there on"""
-        err = int(self.read_ctrl().error)
+        err = int(_lib.eb_ctrl.from_buffer_copy(self.ctrl.cpu().numpy().tobytes()).error)
         if err:
             raise _lib.ErynB200Error(f"device error {err} (EB_DEVERR_*): a bounded wait inside the swap pass timed out "
                                      "(peer never published / a CTA never arrived); results after that pass are invalid")
 
     def download(self, d, into=None, random_state=None):
         """DeviceState -> host State (new, or refreshing the arrays of `into` in place)."""
+        self.flush_adapt()
         self.check_error()
         coords = d.coords.cpu().numpy()
         logl = d.logl.cpu().numpy()
@@ -236,6 +253,8 @@ class DeviceContext(object):
             r.seed = self.seed
             r.iter_dev = self.iter_next_ptr
             r.pdl_chain = 1
+            if self.lazy_adapt:
+                r.lazy_ctrl = _ptr(self.ctrl)
         else:
             keep = dict(list=[self.to_dev(x, np.int32) for x in replay["lists"]],
                         rint=[self.to_dev(x, np.int64) for x in replay["rint"]],
@@ -257,6 +276,8 @@ class DeviceContext(object):
         if gibbs is not None:
             r.gibbs_mask, r.gibbs_ndim, r.gibbs_index = int(gibbs[0]), int(gibbs[1]), int(gibbs[2])
             r.pdl_chain = 0 if gibbs[2] > 0 else r.pdl_chain  # only the first split follows the swap pass
+            if gibbs[2] > 0:
+                r.lazy_ctrl = None
         acc = self.accepted_mask(T, W)
         _lib.check(self.lib.eb_stretch_step(C.byref(st), C.byref(self._prior_c), C.byref(self._like_c),
                                             float(a), C.byref(r), _ptr(acc), _ptr(accepted_count),
@@ -266,6 +287,7 @@ class DeviceContext(object):
 
     def stretch_step_split(self, d, a, randomize_split=True, replay=None, accepted_count=None):
         """Split path for callables, per half: propose kernel -> prior kernel -> user likelihood -> accept kernel."""
+        self.flush_adapt()
         T, W, L, D = d.shape
         st = d.c_struct()
         r, keep = self._stretch_rng(randomize_split, replay)
@@ -294,6 +316,7 @@ class DeviceContext(object):
         """GaussianMove step, fused (mh.py:56-193 + gaussian.py:68-195).  gibbs = (parameter mask bits, split index);
         dim_mode 1 = one random dimension per walker, log_factor = log of GaussianMove's `factor` (philox mode)."""
         self._require_fused()
+        self.flush_adapt()
         T, W, L, D = d.shape
         st = d.c_struct()
         r = _lib.eb_gauss_rng()
@@ -330,6 +353,7 @@ class DeviceContext(object):
         """MTDistGenMove step (multipletry.py:238-514 + mtdistgen.py inside mh.py:56-193), all walkers in one launch.
         replay = (tries [T*W, num_try, D], u_sel [T*W], u_acc [T, W]) drawn on the host in the reference's order."""
         self._require_fused()
+        self.flush_adapt()
         T, W, L, D = d.shape
         st = d.c_struct()
         r = _lib.eb_mt_rng()
@@ -358,6 +382,9 @@ class DeviceContext(object):
             r.mode = _lib.EB_RNG_PHILOX
             r.seed = self.seed
             r.iter_dev = self.iter_ptr
+            if self.lazy_adapt and T > 1 and d.temp_offset == 0:
+                r.defer_adapt = 1
+                self._lazy_betas = d.betas
         else:
             iperm, i1perm, u = replay
             keep = (self.to_dev(iperm, np.int32), self.to_dev(i1perm, np.int32), self.to_dev(u, np.float64),
@@ -384,6 +411,7 @@ class DeviceContext(object):
         if not (the caller then runs stretch_step + pt_swap), else True / the accept mask of the last iteration."""
         if not self.fused or self.rng != "philox" or d.betas is None or self.periods is not None:
             return False
+        self.flush_adapt()
         T, W, L, D = d.shape
         st = d.c_struct()
         sr = _lib.eb_stretch_rng()

@@ -590,7 +590,25 @@ class EnsembleSampler(object):
                 mv._host_tick(1)
             self._graph((mi, 1), lambda mv=mv: mv.propose(model, d))
 
+    def _lazy_adapt_applies(self, d):
+        """the loop consists of plain StretchMove proposals on a tempered ensemble: the swap pass may leave its ladder
+        adaptation to the next stretch kernel (DeviceContext.lazy_adapt)"""
+        if os.environ.get("EB_LAZY_ADAPT", "1") == "0" or len(self.moves) != 1 or self.num_repeats_in_model != 1:
+            return False
+        mv = self.moves[0]
+        T, W, L, D = d.shape
+        return (type(mv) is StretchMove and mv.temperature_control is not None and T > 1 and d.inds is None
+                and mv._single_branch_splits(d.branch_name, L, D) == [(0, 0, L * D)])
+
     def _sample_resident(self, model, d, iterations, thin_by, store, tune):
+        self.ctx.lazy_adapt = self._lazy_adapt_applies(d)
+        try:
+            yield from self._sample_resident_loop(model, d, iterations, thin_by, store, tune)
+        finally:
+            self.ctx.flush_adapt()
+            self.ctx.lazy_adapt = False
+
+    def _sample_resident_loop(self, model, d, iterations, thin_by, store, tune):
         from .staging import StoreRing
         tc = self.temperature_control
         T, W = self.ntemps, self.nwalkers

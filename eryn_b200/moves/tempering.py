@@ -85,7 +85,10 @@ class TemperatureControl(object):
 
     @property
     def betas(self):
-        return self._betas_host if self._betas_dev is None else self._betas_dev.cpu().numpy()
+        if self._betas_dev is None:
+            return self._betas_host
+        self.ctx.flush_adapt()   # a pass may have left its ladder adaptation to the next stretch kernel
+        return self._betas_dev.cpu().numpy()
 
     @betas.setter
     def betas(self, b):
@@ -94,6 +97,7 @@ class TemperatureControl(object):
             raise ValueError("betas has the wrong number of temperatures")
         self._betas_host = b.copy()
         if self._betas_dev is not None:
+            self.ctx.flush_adapt()
             self._betas_dev.copy_(torch.from_numpy(self._betas_host))
 
     @property

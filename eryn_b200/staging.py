@@ -103,6 +103,7 @@ class StoreRing(object):
             s.meta.evict()              # a yielded state that is still referenced keeps its data
             if s.copying:
                 s.copied.synchronize()  # the side stream may still be reading s.dev
+        self.ctx.flush_adapt()   # the snapshot holds the ladder and the swap counts: a deferred adaptation goes first
         cur = torch.cuda.current_stream(self.device)
         self._sg.dst = s.dev.data_ptr()
         _lib.check(self.lib.eb_stage_pack(C.byref(self._sg), C.c_void_p(cur.cuda_stream)), "eb_stage_pack")

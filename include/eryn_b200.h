@@ -32,7 +32,7 @@ extern "C" {
 #define EB_API
 #endif
 
-#define EB_ABI_VERSION 7
+#define EB_ABI_VERSION 8
 #define EB_MAX_TEMPS 128
 #define EB_MAX_ROW 32 /* nleaves*ndim supported by the fused kernels */
 #define EB_MAX_RANKS 16 /* GPUs of one temperature-sharded run */
@@ -126,6 +126,9 @@ typedef struct {
    *             which is what the reference adds to Move.accepted per split (red_blue.py:296-309, :325) */
   uint32_t gibbs_mask;
   int32_t gibbs_ndim, gibbs_index, _pad2;
+  void* lazy_ctrl;         /* philox, first launch of a step: the eb_ctrl of a pass that may have deferred its ladder
+                              adaptation (eb_swap_rng.defer_adapt); the kernel folds the counts and adapts the ladder in
+                              its prologue if that pass belongs to the iteration before this one.  NULL = nothing deferred */
 } eb_stretch_rng;
 
 /* Random inputs of one Gaussian Metropolis step (gaussian.py:68-195, mh.py:171). */
@@ -168,6 +171,11 @@ typedef struct {
   uint64_t seed;
   const uint64_t* iter_dev;
   uint64_t iter;
+  int32_t defer_adapt;    /* single-GPU philox passes: do not fold the counts / adapt the ladder in this kernel; leave them
+                             for the next stretch kernel (eb_stretch_rng.lazy_ctrl) or eb_adapt_flush.  The pass then ends
+                             with its row moves.  Whoever reads betas / swaps_accepted / time before the
+                             next stretch step must call eb_adapt_flush first. */
+  int32_t _pad_defer;
 } eb_swap_rng;
 
 /* Device control block: iteration counter, ladder-adaptation clock and swap statistics
@@ -185,6 +193,14 @@ typedef struct {
   uint64_t iter_next;                   /* = iter between iterations; a swap pass sets it to iter+1 BEFORE it releases
                                            its programmatic dependents, so the next move kernel can key its draws
                                            while the pass still runs (eb_stretch_rng.pdl_chain) */
+  /* lazy ladder adaptation (eb_swap_rng.defer_adapt): the pass leaves its swap counts in swaps_work and a snapshot of
+   * what adapt_temps needs; the next stretch kernel (eb_stretch_rng.lazy_ctrl) or eb_adapt_flush folds and adapts */
+  uint64_t adapt_pending;               /* 0, or iter+1 of the deferred pass */
+  uint64_t adapt_applied;               /* value of adapt_pending that has been applied */
+  int64_t pend_time;                    /* TemperatureControl.time at the deferred pass */
+  int32_t pend_adapt_on, pend_adaptive, pend_stop, pend_T, pend_W, _pad_lazy;
+  double pend_lag, pend_t0;
+  double pend_betas[EB_MAX_TEMPS];      /* the ladder at the deferred pass */
 } eb_ctrl;
 
 typedef struct {
@@ -250,6 +266,10 @@ EB_API int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_
  *      Increments ctrl->iter.  `adapt` may be NULL (no adaptation, rj.py:381-382). */
 EB_API int eb_pt_swap(const eb_state* st, const eb_swap_rng* rng, const eb_adapt* adapt, eb_ctrl* ctrl,
                void* stream);
+
+/* ---- apply a deferred ladder adaptation now (eb_swap_rng.defer_adapt; adapt_temps tempering.py:563-596 and the
+ *      bookkeeping of temper_comps :598-649): no-op if nothing is pending.  `betas` = the ladder the pass ran on. */
+EB_API int eb_adapt_flush(eb_ctrl* ctrl, double* betas, void* stream);
 
 /* ---- the same pass a few rungs at a time (the wavefront form eb_run_host pipelines against its host copies):
  *      tempering.py:515 walks i = T-1 .. 1, and rung i is final once the swap (i, i-1) is decided, so

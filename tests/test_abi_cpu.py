@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound():
 def test_struct_layouts_match():
     from eryn_b200 import _lib
     lib = _lib.load()
-    assert lib.eb_abi_version() == 7
+    assert lib.eb_abi_version() == 8
     for i, st in enumerate(_lib.STRUCTS):
         assert lib.eb_struct_size(i) == ctypes.sizeof(st), st.__name__
     assert lib.eb_ctrl_size() == ctypes.sizeof(_lib.eb_ctrl)

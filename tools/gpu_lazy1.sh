@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_lazy_adapt.py -x -q -m gpu 2>&1 | tail -15
