@@ -238,7 +238,8 @@ class SingleGpu(object):
         self.tc.bind(self.ctx)
         # loops of plain stretch proposals: the swap pass leaves its ladder adaptation to the next stretch kernel
         # (DeviceContext.lazy_adapt), as EnsembleSampler's resident path does
-        self.ctx.lazy_adapt = all(m["kind"] == "stretch" for m in wl["moves"]) and os.environ.get("EB_LAZY_ADAPT", "1") != "0"
+        self.ctx.lazy_adapt = (all(m["kind"] == "stretch" for m in wl["moves"]) and T * W <= 131072
+                               and os.environ.get("EB_LAZY_ADAPT", "1") != "0")
         self.moves = []
         for m in wl["moves"]:
             mv = StretchMove(a=m["a"]) if m["kind"] == "stretch" else GaussianMove({"model_0": m["proposal"]["scale"] ** 2})
@@ -330,6 +331,7 @@ class SingleGpu(object):
         return k0.elapsed_time(k1) * 1e3 / nrep
 
     def stretch_us(self, nrep):
+        self.ctx.flush_adapt()   # back-to-back stretch steps without a pass in between: nothing may be pending
         cnt = self.stretch[0]._count_buffer(self.ctx, self.wl["T"], self.wl["W"])
         return self.graph_us(lambda: self.ctx.stretch_step(self.ds, 2.0, accepted_count=cnt), nrep)
 
@@ -537,7 +539,9 @@ def run_gpu(args):
         mf = sg.moved_fraction()
         s_us = sg.swap_us(100)
         sb = (12 + (16 * d + 34) * mf) * T * W
-        roofline_swap = roofline_entry("pt_swap_kernel (ladder + row moves + adaptation, one launch)", sb, s_us, peak, peak_src,
+        roofline_swap = roofline_entry("pt_swap_kernel (ladder + row moves, one launch; the ladder adaptation is left to the next "
+                                       "stretch kernel)" if sg.ctx.lazy_adapt else
+                                       "pt_swap_kernel (ladder + row moves + adaptation, one launch)", sb, s_us, peak, peak_src,
                                        moved_fraction=round(mf, 4),
                                        note="algorithmic bytes = 12 + (16 D + 34) x moved_fraction per walker; latency-bound at "
                                             "this size (the ladder is a dependent chain over the rungs)")
@@ -645,7 +649,8 @@ def run_gpu(args):
                  notes=dict(rng="philox (counter-based, in-kernel)",
                             l2="flushed between timed steps (256 MiB fill outside the per-step CUDA-event pairs)",
                             step="one iteration = stretch step (red launch + blue launch chained by programmatic dependent "
-                                 "launch) + 1 swap/adapt kernel (CUDA graph replay)"))
+                                 "launch) + 1 swap kernel (CUDA graph replay); the swap kernel leaves the ladder adaptation "
+                                 "of its pass to the prologue of the next stretch kernel (lazy adaptation)"))
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f64", data="synthetic", config=config_of(wl),

@@ -113,10 +113,9 @@ struct LazyShared { double b[EB_MAX_TEMPS]; double d[EB_MAX_TEMPS]; int c[EB_MAX
 
 // all threads of the CTA call this (block barriers inside); returns true if a pass was pending for iteration `it`, and
 // then sh.b holds the adapted ladder
-__device__ __forceinline__ bool lazy_adapt_apply(eb_ctrl* ctrl, unsigned long long it, double* betas_global, bool writer,
-                                                 bool zero_own, LazyShared& sh) {
-  const unsigned long long pend = ld_volatile_u64(&ctrl->adapt_pending);
-  if (pend == 0ull || pend != it) return false;        // uniform over the grid: written by a kernel that has completed
+// (the work itself is kept out of line: the stretch kernels run at their register limit and only look at the flag)
+static __device__ __noinline__ void lazy_adapt_work(eb_ctrl* ctrl, unsigned long long pend, double* betas_global, bool writer,
+                                                    bool zero_own, LazyShared& sh) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int T = ctrl->pend_T, W = ctrl->pend_W;
   const unsigned long long itp = pend - 1ull;
@@ -161,7 +160,10 @@ __device__ __forceinline__ bool lazy_adapt_apply(eb_ctrl* ctrl, unsigned long lo
     }
     __syncthreads();
   }
-  if (writer) {
+  // the bookkeeping happens once per deferred pass: a second stretch kernel of the same iteration (no pass in between)
+  // recomputes the same ladder from the snapshot and leaves the counters alone.  Only writer CTAs read or write
+  // adapt_applied, and they run in stream order.
+  if (writer && ld_volatile_u64(&ctrl->adapt_applied) != pend) {
     for (int r = tid; r < T; r += nt) betas_global[r] = sh.b[r];
     for (int r = tid; r < T - 1; r += nt) {
       ctrl->swaps_accepted[r] = sh.c[r];
@@ -174,11 +176,19 @@ __device__ __forceinline__ bool lazy_adapt_apply(eb_ctrl* ctrl, unsigned long lo
         for (int sl = 0; sl < LAZY_SLOTS; ++sl) ctrl->swaps_work[row0 + sl][r] = 0;
       }
     }
+    __syncthreads();   // every thread of the writer has read adapt_applied
     if (tid == 0) {
       if (adapting) ctrl->time = time_now + 1;                                                    // :596
       ctrl->adapt_applied = pend;
     }
   }
+}
+
+__device__ __forceinline__ bool lazy_adapt_apply(eb_ctrl* ctrl, unsigned long long it, double* betas_global, bool writer,
+                                                 bool zero_own, LazyShared& sh) {
+  const unsigned long long pend = ld_volatile_u64(&ctrl->adapt_pending);
+  if (pend == 0ull || pend != it) return false;        // uniform over the grid: written by a kernel that has completed
+  lazy_adapt_work(ctrl, pend, betas_global, writer, zero_own, sh);
   return true;
 }
 

@@ -597,8 +597,12 @@ class EnsembleSampler(object):
             return False
         mv = self.moves[0]
         T, W, L, D = d.shape
+        # worth it while the pass is latency-bound (config 2: 10.2 -> 7.6 us); on grids of thousands of CTAs (config 4) the
+        # per-CTA fold in the stretch kernel costs more than the pass saves
         return (type(mv) is StretchMove and mv.temperature_control is not None and T > 1 and d.inds is None
-                and mv._single_branch_splits(d.branch_name, L, D) == [(0, 0, L * D)])
+                and T * W <= self._LAZY_MAX_WALKERS and mv._single_branch_splits(d.branch_name, L, D) == [(0, 0, L * D)])
+
+    _LAZY_MAX_WALKERS = 131072
 
     def _sample_resident(self, model, d, iterations, thin_by, store, tune):
         self.ctx.lazy_adapt = self._lazy_adapt_applies(d)
