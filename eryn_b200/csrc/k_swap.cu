@@ -317,6 +317,48 @@ __device__ __forceinline__ void pt_swap_adapt_warp(const SwapArgs& p, int T, int
   }
 }
 
+// One row copied by a whole warp: coalesced 16 / 8-byte (doubles) or 4 / 1-byte (payload) accesses, every load of the row
+// in flight before the first store.  Rows of the staging path are long (config 5: 60 doubles + 1.3 KB of leaf flags and
+// friend table per walker); one lane per rung copying them element by element was 228 us per pass there.
+__device__ __forceinline__ void warp_copy_doubles(double* __restrict__ dst, const double* __restrict__ src, int n, int wl) {
+  if ((n & 1) == 0 && ((reinterpret_cast<size_t>(dst) | reinterpret_cast<size_t>(src)) & 15) == 0) {
+    const int n2 = n >> 1;
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int i0 = 0; i0 < n2; i0 += 4 * 32) {
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + wl; if (i < n2) v[u] = s2[i]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + wl; if (i < n2) d2[i] = v[u]; }
+    }
+  } else {
+    for (int i0 = 0; i0 < n; i0 += 4 * 32) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + wl; if (i < n) v[u] = src[i]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + wl; if (i < n) dst[i] = v[u]; }
+    }
+  }
+}
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int n, int wl) {
+  if (((n | (int)(reinterpret_cast<size_t>(dst) | reinterpret_cast<size_t>(src))) & 3) == 0) {
+    const int n4 = n >> 2;
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+    for (int i0 = 0; i0 < n4; i0 += 12 * 32) {
+      uint32_t v[12];
+#pragma unroll
+      for (int u = 0; u < 12; ++u) { const int i = i0 + u * 32 + wl; if (i < n4) v[u] = s4[i]; }
+#pragma unroll
+      for (int u = 0; u < 12; ++u) { const int i = i0 + u * 32 + wl; if (i < n4) d4[i] = v[u]; }
+    }
+  } else {
+    for (int i = wl; i < n; i += 32) dst[i] = src[i];
+  }
+}
+
 constexpr int SWAP_THREADS = 256;
 constexpr int SWAP_AGES = 8;      // tests per walker evaluated ahead of the cascade walk (bits of one band byte)
 
@@ -816,24 +858,64 @@ __global__ void __launch_bounds__(SWAP_THREADS) pt_swap_kernel(const __grid_cons
         }
     } else {
       // long rows / leaf flags / long ladders: the moved rows rest in the global staging buffers between the gather
-      // and the scatter (indexed by destination slot, so chains never collide)
-      for (int r = lane; valid && r < T; r += CL) {
-        const int s = swap_source(sel_lo, sel_hi, r, T);
-        if (s == r) continue;
-        const size_t sslot = (size_t)s * W + pos[s], dslot = (size_t)r * W + pos[r];
-        copy_row(p.scratch_coords + dslot * LD, c.coords + sslot * LD, LD);
-        p.scratch_logp[dslot] = c.logp[sslot];
-        if (c.inds) copy_bytes(p.scratch_inds + dslot * L, c.inds + sslot * L, L);
-      }
-      __syncwarp();
-      for (int r = lane; valid && r < T; r += CL) {
-        const int s = swap_source(sel_lo, sel_hi, r, T);
-        if (s == r) continue;
-        const size_t dslot = (size_t)r * W + pos[r];
-        copy_row(c.coords + dslot * LD, p.scratch_coords + dslot * LD, LD);
-        c.logp[dslot] = p.scratch_logp[dslot];
-        c.logl[dslot] = ll[s];
-        if (c.inds) copy_bytes(c.inds + dslot * L, p.scratch_inds + dslot * L, L);
+      // and the scatter (indexed by destination slot, so chains never collide).  The WARP walks over the chains of its
+      // lane groups and copies every moved row cooperatively (warp_copy_*); the source rung of every rung comes out of
+      // one downward pass over the accept bits.
+      constexpr int CPW = 32 / CL;
+      const int wl = tid & 31, warp = tid >> 5;
+      const bool long_rows = LD * (int)sizeof(double) + (c.inds ? L : 0) >= 256;
+      if (!long_rows) {
+        // short rows on a long ladder: one lane per rung keeps 32 rows of the warp in flight at once
+        for (int r = lane; valid && r < T; r += CL) {
+          const int sr = swap_source(sel_lo, sel_hi, r, T);
+          if (sr == r) continue;
+          const size_t sslot = (size_t)sr * W + pos[sr], dslot = (size_t)r * W + pos[r];
+          copy_row(p.scratch_coords + dslot * LD, c.coords + sslot * LD, LD);
+          p.scratch_logp[dslot] = c.logp[sslot];
+          if (c.inds) copy_bytes(p.scratch_inds + dslot * L, c.inds + sslot * L, L);
+        }
+        __syncwarp();
+        for (int r = lane; valid && r < T; r += CL) {
+          const int sr = swap_source(sel_lo, sel_hi, r, T);
+          if (sr == r) continue;
+          const size_t dslot = (size_t)r * W + pos[r];
+          copy_row(c.coords + dslot * LD, p.scratch_coords + dslot * LD, LD);
+          c.logp[dslot] = p.scratch_logp[dslot];
+          c.logl[dslot] = ll[sr];
+          if (c.inds) copy_bytes(c.inds + dslot * L, p.scratch_inds + dslot * L, L);
+        }
+      } else
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+        for (int q = 0; q < CPW; ++q) {
+          const int gl = q * CL;                                   // first lane of the chain group
+          const unsigned long long qlo = __shfl_sync(0xffffffffu, sel_lo, gl), qhi = __shfl_sync(0xffffffffu, sel_hi, gl);
+          if (!__shfl_sync(0xffffffffu, (int)valid, gl)) continue; // uniform over the warp
+          const int gq = warp * CPW + q;                           // the group's index within the CTA
+          const int* qpos = reinterpret_cast<const int*>(smraw + lay.pos) + (size_t)gq * T;
+          const double* qll = reinterpret_cast<const double*>(smraw + lay.ll) + (size_t)gq * T;
+          int top = T - 1;                                         // rung the walker carried past rung r started on
+          for (int r = T - 1; r >= 0; --r) {
+            if (!(r + 1 < T && sel_bit(qlo, qhi, r + 1))) top = r;
+            const int sr = (r >= 1 && sel_bit(qlo, qhi, r)) ? r - 1 : top;   // = swap_source(qlo, qhi, r, T)
+            if (sr == r) continue;
+            const size_t sslot = (size_t)sr * W + qpos[sr], dslot = (size_t)r * W + qpos[r];
+            if (phase == 0) {
+              warp_copy_doubles(p.scratch_coords + dslot * LD, c.coords + sslot * LD, LD, wl);
+              if (wl == 0) p.scratch_logp[dslot] = c.logp[sslot];
+              if (c.inds) warp_copy_bytes(p.scratch_inds + dslot * L, c.inds + sslot * L, L, wl);
+            } else {
+              warp_copy_doubles(c.coords + dslot * LD, p.scratch_coords + dslot * LD, LD, wl);
+              if (wl == 0) {
+                c.logp[dslot] = p.scratch_logp[dslot];
+                c.logl[dslot] = qll[sr];
+              }
+              if (c.inds) warp_copy_bytes(c.inds + dslot * L, p.scratch_inds + dslot * L, L, wl);
+            }
+          }
+        }
+        __syncwarp();      // every gather of the warp's chains before any scatter (chains never leave their warp)
       }
     }
   } else if (valid) {
