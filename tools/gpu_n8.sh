@@ -1,3 +1,7 @@
 mkdir -p gpurun_out
-bash tools/gpu_breakdown8.sh 8
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 200 --warmup 10 > gpurun_out/r02_bench_n8_auto.json 2> gpurun_out/r02_bench_n8_auto.err; echo "n8 rc=$?"
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 200 --warmup 10 > gpurun_out/r02_bench_n8_auto.json 2> gpurun_out/r02_bench_n8_auto.err; echo "n8 rc=$?"; tail -1 gpurun_out/r02_bench_n8_auto.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r02_bench_n8_auto.json").read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","ms_per_step")}, d.get("parity",{}).get("ok"), d["extra"].get("c4_strong",{}).get("speedup_vs_1gpu"), d["extra"].get("c4_strong",{}).get("ms_per_step"))
+PY
