@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(STRETCH_HALF_THREADS, 2) stretch_step_kernel(c
   EB_MARK(2);
   const bool own_early = !p.both && s == 1;   // split-1 rows are not touched by half 0
   if (own_early) job_load_own<DMAX, EXACT>(p, t, job);
+  stage_store(c, staged, sm);                 // constant parameters (no kernel writes them): in place before the wait, so that
+  __syncthreads();                            // the block barrier is not on the path behind it
   pdl_wait();
   if (p.both || s == 0) pdl_launch_dependents();
   if (!own_early) job_load_own<DMAX, EXACT>(p, t, job);
@@ -226,8 +228,6 @@ __global__ void __launch_bounds__(STRETCH_HALF_THREADS, 2) stretch_step_kernel(c
   if (PHILOX && p.lazy_ctrl && (p.both || s == 0))
     lazy = lazy_adapt_apply(p.lazy_ctrl, it, c.betas, blockIdx.x == 0 && blockIdx.y == 0, false, lazy_sh);
   if (c.betas) job.beta = lazy ? lazy_sh.b[c.t0 + t] : c.betas[t];   // adapted by the swap pass: read after the wait
-  stage_store(c, staged, sm);
-  __syncthreads();                            // staged parameters visible
   EB_MARK(3);
   // Half 1 gathers what half 0 wrote, inside this temperature only.  In a fused CTA the split-1 warps arrive at the
   // barrier first and wait there for the split-0 warps, which arrive after their `finish`.
