@@ -19,6 +19,7 @@ __all__ = ["Backend"]
 # changed) and the call runs without the GIL.  Transparent huge pages are requested first where the system allows them.
 _MADV_HUGEPAGE, _MADV_POPULATE_WRITE = 14, 23
 _PREFAULT_MIN_BYTES = 8 << 20
+_PREFAULT_MAX_BYTES = 1 << 30
 _PREFAULT_CHUNK = 4 << 20
 _PREFAULT_THREADS = 4     # page zeroing is per-core work: one thread populates ~4-5 GB/s
 
@@ -60,6 +61,7 @@ def _prefault_async(arr, first_row):
     hi = hi // page * page
     if hi - lo < _PREFAULT_MIN_BYTES:
         return None
+    hi = min(hi, lo + _PREFAULT_MAX_BYTES)   # a long run reserves far more than it may ever touch: populate the head only
     try:
         madvise = ctypes.CDLL(None, use_errno=True).madvise
     except (OSError, AttributeError):

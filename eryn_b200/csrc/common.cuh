@@ -115,12 +115,13 @@ struct LazyShared { double b[EB_MAX_TEMPS]; double d[EB_MAX_TEMPS]; int c[EB_MAX
 // then sh.b holds the adapted ladder
 // (the work itself is kept out of line: the stretch kernels run at their register limit and only look at the flag)
 static __device__ __noinline__ void lazy_adapt_work(eb_ctrl* ctrl, unsigned long long pend, double* betas_global, bool writer,
-                                                    bool zero_own, LazyShared& sh) {
+                                                    bool zero_own, LazyShared& sh, int cnt_mine, double beta_mine) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int T = ctrl->pend_T, W = ctrl->pend_W;
   const unsigned long long itp = pend - 1ull;
   const int row0 = (int)(itp & 1ull) * LAZY_SLOTS;
-  for (int r = tid; r < T; r += nt) {
+  if (tid < T) { sh.b[tid] = beta_mine; sh.c[tid] = tid < T - 1 ? cnt_mine : 0; }   // requested ahead of the flag
+  for (int r = tid + nt; r < T; r += nt) {                                          // CTAs narrower than the ladder
     sh.b[r] = ctrl->pend_betas[r];
     int v = 0;
     if (r < T - 1) {
@@ -186,9 +187,23 @@ static __device__ __noinline__ void lazy_adapt_work(eb_ctrl* ctrl, unsigned long
 
 __device__ __forceinline__ bool lazy_adapt_apply(eb_ctrl* ctrl, unsigned long long it, double* betas_global, bool writer,
                                                  bool zero_own, LazyShared& sh) {
+  // the counts and the snapshot ladder of this thread's rung are requested together with the flag (their addresses do not
+  // depend on it: a pass pending for iteration `it` has iteration number it - 1), so the fold costs one round trip, not two
+  const int tid = threadIdx.x;
+  int cnt_mine = 0;
+  double beta_mine = 0.0;
+  if (tid < EB_MAX_TEMPS) {
+    const int row0 = (int)((it - 1ull) & 1ull) * LAZY_SLOTS;
+    int w8[LAZY_SLOTS];
+#pragma unroll
+    for (int sl = 0; sl < LAZY_SLOTS; ++sl) w8[sl] = *reinterpret_cast<volatile int*>(&ctrl->swaps_work[row0 + sl][tid]);
+    beta_mine = *reinterpret_cast<volatile double*>(&ctrl->pend_betas[tid]);
+#pragma unroll
+    for (int sl = 0; sl < LAZY_SLOTS; ++sl) cnt_mine += w8[sl];
+  }
   const unsigned long long pend = ld_volatile_u64(&ctrl->adapt_pending);
   if (pend == 0ull || pend != it) return false;        // uniform over the grid: written by a kernel that has completed
-  lazy_adapt_work(ctrl, pend, betas_global, writer, zero_own, sh);
+  lazy_adapt_work(ctrl, pend, betas_global, writer, zero_own, sh, cnt_mine, beta_mine);
   return true;
 }
 
