@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 4 --steps 200 --warmup 10 > gpurun_out/r02_bench_n4_auto.json 2> gpurun_out/r02_bench_n4_auto.err; echo "n4 rc=$?"; tail -1 gpurun_out/r02_bench_n4_auto.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r02_bench_n4_auto.json").read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","ms_per_step")}, d.get("parity",{}).get("ok"), d["extra"].get("c4_strong",{}).get("speedup_vs_1gpu"), d["e2e"]["value"])
+PY
