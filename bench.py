@@ -238,7 +238,7 @@ class SingleGpu(object):
         self.tc.bind(self.ctx)
         # loops of plain stretch proposals: the swap pass leaves its ladder adaptation to the next stretch kernel
         # (DeviceContext.lazy_adapt), as EnsembleSampler's resident path does
-        self.ctx.lazy_adapt = (all(m["kind"] == "stretch" for m in wl["moves"]) and T * W <= 131072
+        self.ctx.lazy_adapt = (all(m["kind"] in ("stretch", "gaussian") for m in wl["moves"]) and T * W <= 131072
                                and os.environ.get("EB_LAZY_ADAPT", "1") != "0")
         self.moves = []
         for m in wl["moves"]:

@@ -49,7 +49,7 @@ class eb_gauss_rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("cov_kind", C.c_int32), ("scale", C.c_double), ("chol", vp), ("delta", vp),
                 ("u_acc", vp), ("seed", C.c_uint64), ("iter_dev", vp), ("iter", C.c_uint64),
                 ("gibbs_mask", C.c_uint32), ("gibbs_index", C.c_int32), ("dim_mode", C.c_int32), ("_pad3", C.c_int32),
-                ("log_factor", C.c_double)]
+                ("log_factor", C.c_double), ("lazy_ctrl", vp)]
 
 
 class eb_swap_rng(C.Structure):

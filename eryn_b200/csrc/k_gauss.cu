@@ -14,6 +14,7 @@ struct GaussArgs {
   uint8_t* accepted; uint32_t* accepted_count;
   uint32_t gmask; int gidx;   // Gibbs split (mh.py:77-183): parameters that change (0 = all), index of the split
   int dim_mode; double log_factor;   // gaussian.py:134-181: 1 = one random dimension per walker; scale factor exp(U(-lf, lf))
+  eb_ctrl* lazy_ctrl;   // a pass that deferred its ladder adaptation (common.cuh:lazy_adapt_apply)
 };
 
 template <int DMAX, int LIKE, bool PHILOX, bool EXACT>
@@ -27,6 +28,12 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) s_chol[i] = p.chol[i];
     __syncthreads();
   }
+  // a pass that deferred its ladder adaptation: every CTA folds the counts and adapts the ladder itself, CTA 0 does the
+  // bookkeeping (all threads take part: block barriers inside)
+  __shared__ LazyShared lazy_sh;
+  bool lazy = false;
+  if (PHILOX && p.lazy_ctrl)
+    lazy = lazy_adapt_apply(p.lazy_ctrl, p.iter_dev ? ld_volatile_u64(p.iter_dev) : p.iter, c.betas, blockIdx.x == 0, false, lazy_sh);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= c.T * c.W) return;
   const int t = tid / c.W;
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(BLOCK) gaussian_step_kernel(const GaussArgs p)
   }
   const double ll0 = c.logl[tid], lp0 = c.logp[tid];
   const bool tempered = c.betas != nullptr;
-  const double beta = tempered ? c.betas[t] : 1.0;
+  const double beta = tempered ? (lazy ? lazy_sh.b[c.t0 + t] : c.betas[t]) : 1.0;
   double lp, ll;
   eval_point<DMAX, LIKE, EXACT>(q, c, sm, active, lp, ll);                          // mh.py:134-148
   const double logP = log_posterior(ll, lp, beta, tempered);
@@ -198,6 +205,7 @@ int eb_gaussian_step(const eb_state* st, const eb_prior* prior, const eb_like* l
   args.accepted = accepted; args.accepted_count = accepted_count;
   args.gmask = rng->gibbs_mask; args.gidx = rng->gibbs_index;
   args.dim_mode = rng->dim_mode; args.log_factor = rng->log_factor;
+  args.lazy_ctrl = (args.philox && st->temp_offset == 0 && st->betas) ? (eb_ctrl*)rng->lazy_ctrl : nullptr;
   if (args.dim_mode != 0 && (args.dim_mode != 1 || rng->cov_kind != 0))
     return fail(EB_ERR_INVALID, "dim_mode must be 0 (vector) or, for scalar proposals, 1 (random)");
   if (args.log_factor < 0.0) return fail(EB_ERR_INVALID, "'factor' must be >= 1.0");

@@ -132,13 +132,23 @@ class DeviceContext(object):
         its programmatic dependents, so the next stretch kernel can start its draws early (pdl_chain)."""
         return C.c_void_p(self.ctrl.data_ptr() + _lib.eb_ctrl.iter_next.offset)
 
+    def lazy_begin(self, betas):
+        """switch lazy ladder adaptation on for a loop of stretch / Gaussian proposals on the ladder `betas` (device tensor)"""
+        self.lazy_adapt = True
+        self._lazy_betas = betas
+
+    def lazy_end(self):
+        """apply what is pending and go back to passes that adapt in their own kernel"""
+        self.flush_adapt()
+        self.lazy_adapt = False
+        self._lazy_betas = None
+
     def flush_adapt(self):
-        """apply a deferred ladder adaptation now (no-op on the device if nothing is pending)"""
+        """apply a deferred ladder adaptation now (no-op on the device if nothing is pending).  The ladder tensor is
+        remembered from lazy_begin / the first deferred pass: replayed graphs defer without passing through pt_swap()."""
         if self._lazy_betas is not None:
             _lib.check(self.lib.eb_adapt_flush(_ptr(self.ctrl), _ptr(self._lazy_betas), self.stream()), "eb_adapt_flush")
             self.launches += 1
-            if not self.lazy_adapt:
-                self._lazy_betas = None
 
     def read_ctrl(self):
         self.flush_adapt()
@@ -316,10 +326,14 @@ class DeviceContext(object):
         """GaussianMove step, fused (mh.py:56-193 + gaussian.py:68-195).  gibbs = (parameter mask bits, split index);
         dim_mode 1 = one random dimension per walker, log_factor = log of GaussianMove's `factor` (philox mode)."""
         self._require_fused()
-        self.flush_adapt()
+        lazy = self.lazy_adapt and replay is None and (gibbs is None or gibbs[1] == 0)
+        if not lazy:
+            self.flush_adapt()
         T, W, L, D = d.shape
         st = d.c_struct()
         r = _lib.eb_gauss_rng()
+        if lazy:
+            r.lazy_ctrl = _ptr(self.ctrl)   # the kernel applies a deferred ladder adaptation in its prologue
         r.dim_mode, r.log_factor = int(dim_mode), float(log_factor)
         if gibbs is not None:
             r.gibbs_mask, r.gibbs_index = int(gibbs[0]), int(gibbs[1])

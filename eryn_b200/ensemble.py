@@ -591,26 +591,32 @@ class EnsembleSampler(object):
             self._graph((mi, 1), lambda mv=mv: mv.propose(model, d))
 
     def _lazy_adapt_applies(self, d):
-        """the loop consists of plain StretchMove proposals on a tempered ensemble: the swap pass may leave its ladder
-        adaptation to the next stretch kernel (DeviceContext.lazy_adapt)"""
-        if os.environ.get("EB_LAZY_ADAPT", "1") == "0" or len(self.moves) != 1 or self.num_repeats_in_model != 1:
+        """the loop consists of plain StretchMove / GaussianMove proposals on a tempered ensemble: the swap pass may leave its
+        ladder adaptation to the next move kernel (DeviceContext.lazy_adapt)"""
+        if os.environ.get("EB_LAZY_ADAPT", "1") == "0" or self.num_repeats_in_model != 1:
             return False
-        mv = self.moves[0]
+        from .moves import GaussianMove
         T, W, L, D = d.shape
         # worth it while the pass is latency-bound (config 2: 10.2 -> 7.6 us); on grids of thousands of CTAs (config 4) the
-        # per-CTA fold in the stretch kernel costs more than the pass saves
-        return (type(mv) is StretchMove and mv.temperature_control is not None and T > 1 and d.inds is None
-                and T * W <= self._LAZY_MAX_WALKERS and mv._single_branch_splits(d.branch_name, L, D) == [(0, 0, L * D)])
+        # per-CTA fold in the move kernel costs more than the pass saves
+        if T <= 1 or d.inds is not None or T * W > self._LAZY_MAX_WALKERS:
+            return False
+        for mv in self.moves:   # the kernels that apply a deferred adaptation themselves: stretch and Gaussian steps
+            if type(mv) not in (StretchMove, GaussianMove) or mv.temperature_control is None:
+                return False
+            if mv._single_branch_splits(d.branch_name, L, D) != [(0, 0, L * D)]:
+                return False
+        return True
 
     _LAZY_MAX_WALKERS = 131072
 
     def _sample_resident(self, model, d, iterations, thin_by, store, tune):
-        self.ctx.lazy_adapt = self._lazy_adapt_applies(d)
+        if self._lazy_adapt_applies(d):
+            self.ctx.lazy_begin(d.betas)
         try:
             yield from self._sample_resident_loop(model, d, iterations, thin_by, store, tune)
         finally:
-            self.ctx.flush_adapt()
-            self.ctx.lazy_adapt = False
+            self.ctx.lazy_end()
 
     def _sample_resident_loop(self, model, d, iterations, thin_by, store, tune):
         from .staging import StoreRing

@@ -153,6 +153,7 @@ typedef struct {
    * log_factor > 0: the scale is multiplied by exp(U(-log_factor, log_factor)), one draw per call (get_factor). */
   int32_t dim_mode, _pad3;
   double log_factor;
+  void* lazy_ctrl;        /* philox: as eb_stretch_rng.lazy_ctrl (a pass that deferred its ladder adaptation) */
 } eb_gauss_rng;
 
 /* Random inputs of one swap pass (tempering.py:525-535). */

@@ -105,3 +105,25 @@ def test_sampler_takes_lazy_adaptation_and_matches_eager(monkeypatch):
         same_backend(runs["eager"][0], runs[mode][0])
         for a, b in zip(runs["eager"][1], runs[mode][1]):
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+
+
+@pytest.mark.parametrize("moves_name", ["stretch_only", "mix"])
+def test_lazy_adaptation_across_calls_that_only_replay_graphs(moves_name, monkeypatch):
+    """a second sample() call whose iterations are all graph replays (no pass goes through DeviceContext.pt_swap) still
+    flushes at every yield: stored ladders, clocks and swap counts equal the eager path"""
+    from tests import test_gpu_api as api
+    moves_f = getattr(api, moves_name)
+    x0 = np.random.RandomState(3).uniform(-3, 3, size=(4, 128, 8))
+    runs = {}
+    for mode in ("eager", "lazy"):
+        monkeypatch.setenv("EB_LAZY_ADAPT", "1" if mode == "lazy" else "0")
+        smp, _ = api.make_sampler(4, 128, 8, moves_f)
+        smp.force_eager = mode == "eager"
+        smp.run_mcmc(x0, 4, thin_by=3, burn=3)
+        seen = []
+        for st in smp.sample(smp.get_last_sample(), iterations=5, thin_by=3):       # graphs of this block size exist already
+            seen.append((st.betas.copy(), smp.temperature_control.time, smp.temperature_control.swaps_accepted.copy()))
+        runs[mode] = (smp, seen)
+    api.same_backend(runs["eager"][0], runs["lazy"][0])
+    for a, b in zip(runs["eager"][1], runs["lazy"][1]):
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2])
