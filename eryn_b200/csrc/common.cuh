@@ -8,13 +8,19 @@
 //       stretch_lanes_kernel      the same step with a walker spread over 2 / 4 lanes (HBM-sized shapes, stretch_lanes.cuh)
 //   K2  gaussian_step_kernel      fused Gaussian Metropolis step over all walkers    (k_gauss.cu)
 //   K3  pt_swap_kernel            chain-parallel swap ladder (decide on logl, then move only the rows
-//                                 that changed rung, in place) + last-block ladder adaptation (k_swap.cu)
+//                                 that changed rung, in place) + ladder adaptation: by the warp that draws the last
+//                                 ticket, by an extra CTA (sharded passes), or deferred to the next move kernel
+//                                 (lazy_adapt_apply below / adapt_flush_kernel)                      (k_swap.cu)
+//   K3w pt_swap_range_kernel /    the ladder a few rungs at a time + its tail: what the wavefront schedule of
+//       pt_swap_finish_kernel     eb_run_host (host_job.cu, with the zero-copy transfer kernel zc_copy_kernel) runs
 //   K3r pt_pairmap_kernel         replay mode: host permutations -> per-position pair map
 //   K4  stretch_propose_kernel / accept_update_kernel / box_prior_kernel   (split path)
 //   K3s pt_swap_split_kernel      the swap pass of a temperature-sharded run, chains split over the ranks (k_swap_split.cu)
 //   K6-K9 multi-branch kernels    reversible jump + group stretch (k_rj.cu)
 //   K10 stage_pack_kernel         snapshot of a stored sample for the staged Backend.save_step (k_stage.cu)
 //   K11 mt_distgen_kernel         multiple-try Metropolis with an independent proposal (k_mt.cu)
+//   K12 resident_kernel           whole iterations in one launch, state resident in shared memory, a cluster per
+//                                 temperature (resident.cuh; measured slower than K1 + K3 chained by PDL: opt-in)
 //
 // Built with --fmad=false so that +,-,*,/ round exactly like the NumPy reference.
 #pragma once

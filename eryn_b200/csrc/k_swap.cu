@@ -21,7 +21,9 @@ namespace eb {
 //      leaving the accept bits in registers; src[r] = rung whose walker ends on rung r follows from the bits;
 //   3. only the rows with src[r] != r move, in place: every lane gathers the source rows of its rungs into
 //      registers, one warp-level sync, then writes (long rows / leaf flags: through a global staging buffer).
-// The last block to finish folds the per-rung swap counts and adapts the ladder (tempering.py:563-596).
+// The per-rung swap counts are folded and the ladder adapted (tempering.py:563-596) by the warp that draws the last
+// ticket, by an extra CTA (sharded passes) or by the next move kernel (deferred adaptation): see the count publication
+// below and common.cuh:lazy_adapt_apply.
 struct SwapArgs {
   Common c;                                       // local state (sharded: the DESTINATION buffers of this rank)
   int T;                                          // rungs of the full ladder
