@@ -237,3 +237,97 @@ def test_backend_grow_prefaults_without_touching_stored_samples():
     b.grow(n)
     assert np.array_equal(b.get_chain()["model_0"][n - 1], samples[-1])
     assert bk._prefault_async(np.empty((3, 4)), 0) is None      # small arrays: nothing to do
+
+
+def test_lazy_adaptation_protocol_model():
+    """NumPy model of the deferred ladder adaptation (csrc/k_swap.cu count publication, common.cuh:lazy_adapt_apply,
+    adapt_flush_kernel, DeviceContext.flush_adapt): two sets of count rows alternating with the iteration parity, a
+    snapshot of ladder and clock, the pending / applied markers and the writer guard.  Random schedules of deferred and
+    self-adapting passes, move kernels that apply (possibly twice per iteration), kernels that need a host flush, and host
+    reads must (a) give the ladder, clock and totals of a pass that adapts every time (tempering.py:563-596) and (b) find
+    the count rows of every pass zero when it starts."""
+    T, W, lag, t0 = 6, 64, 50.0, 10.0
+
+    def adapt(betas, counts, time):   # adapt_temps, the arithmetic of pt_swap_adapt
+        b = betas.copy()
+        kappa = (lag / (time + lag)) / t0
+        ratios = counts / float(W)
+        dS = kappa * (ratios[:-1] - ratios[1:])
+        dT = np.diff(1.0 / b[:-1]) * np.exp(dS)
+        b[1:-1] = b[1:-1] + (1.0 / (np.cumsum(dT) + 1.0 / b[0]) - b[1:-1])
+        return b
+
+    class Dev(object):
+        def __init__(self, betas):
+            self.betas, self.time, self.iter = betas.copy(), 0, 0
+            self.work = np.zeros((2, T - 1), dtype=np.int64)
+            self.total = np.zeros(T - 1, dtype=np.int64)
+            self.last = np.zeros(T - 1, dtype=np.int64)
+            self.pending = self.applied = 0
+            self.snap = None
+
+        def swap_pass(self, counts, defer):
+            it = self.iter
+            assert not self.work[it & 1].any(), "count rows of this parity must be zero when a pass starts"
+            self.work[it & 1] += counts
+            if defer:
+                self.snap = (self.betas.copy(), self.time)
+                self.pending = it + 1
+            else:
+                assert self.pending in (0, self.applied), "the host flushes before a pass that adapts itself"
+                c = self.work[it & 1].copy()
+                self.betas = adapt(self.betas, c, self.time)
+                self.work[:] = 0
+                self.last, self.total, self.time = c, self.total + c, self.time + 1
+            self.iter = it + 1
+
+        def apply(self, it, writer_zero_own=False):
+            """what every CTA of a move kernel of iteration `it` (or the flush kernel) computes; returns the ladder it uses"""
+            if self.pending == 0 or self.pending != it:
+                return self.betas
+            row = (it - 1) & 1
+            c = self.work[row].copy()
+            ladder = adapt(self.snap[0], c, self.snap[1])
+            if self.applied != self.pending:            # the writer CTA, once per deferred pass
+                self.betas = ladder.copy()
+                self.last, self.total, self.time = c, self.total + c, self.snap[1] + 1
+                self.work[row ^ 1] = 0
+                if writer_zero_own:
+                    self.work[row] = 0
+                self.applied = self.pending
+            return ladder
+
+        def flush(self):
+            if self.pending and self.pending != self.applied:
+                self.apply(self.pending, writer_zero_own=True)
+                self.pending = 0
+
+    rs = np.random.RandomState(11)
+    for trial in range(200):
+        betas0 = np.geomspace(1.0, 1e-2, T)
+        dev = Dev(betas0)
+        ref_b, ref_time, ref_total = betas0.copy(), 0, np.zeros(T - 1, dtype=np.int64)
+        lazy = bool(rs.randint(2))
+        for it in range(rs.randint(1, 30)):
+            if rs.rand() < 0.15:                          # the loop changes character: lazy_begin / lazy_end
+                if lazy:
+                    dev.flush()
+                lazy = not lazy
+            kind = rs.randint(3)                          # 0 / 1: kernels that apply themselves, 2: needs the host flush
+            if kind == 2 or not lazy:
+                dev.flush()
+                used = dev.betas
+            else:
+                used = dev.apply(dev.iter)
+                if rs.rand() < 0.3:
+                    assert np.array_equal(dev.apply(dev.iter), used)   # a second kernel of the same iteration: same ladder
+            assert np.array_equal(used, ref_b), "a move kernel must see the ladder adapted by every earlier pass"
+            counts = rs.randint(0, W + 1, size=T - 1)
+            dev.swap_pass(counts, defer=lazy)
+            ref_b, ref_time, ref_total = adapt(ref_b, counts, ref_time), ref_time + 1, ref_total + counts
+            if rs.rand() < 0.3:                           # a host read: download / read_ctrl / staging snapshot
+                dev.flush()
+                assert np.array_equal(dev.betas, ref_b) and dev.time == ref_time and np.array_equal(dev.total, ref_total)
+                assert np.array_equal(dev.last, counts)
+        dev.flush()
+        assert np.array_equal(dev.betas, ref_b) and dev.time == ref_time and np.array_equal(dev.total, ref_total)
