@@ -331,3 +331,28 @@ def test_lazy_adaptation_protocol_model():
                 assert np.array_equal(dev.last, counts)
         dev.flush()
         assert np.array_equal(dev.betas, ref_b) and dev.time == ref_time and np.array_equal(dev.total, ref_total)
+
+
+def test_wavefront_groups_cover_every_rung_once():
+    """the group arithmetic of eb_run_host's wavefront schedule (csrc/host_job.cu:issue_wavefront): temperatures are
+    uploaded in G groups hottest first, the rung ranges adjoin from T-1 down to 0, and every rung is downloaded exactly
+    once, never before the range that makes it final (tempering.py:515: rung i is final after the swap (i, i-1))"""
+    for T in range(2, 40):
+        for G in range(1, min(T, 16) + 1):
+            b = [T - (T * g) // G for g in range(G + 1)]          # group g = temperatures [b[g+1], b[g])
+            assert b[0] == T and b[-1] == 0 and all(b[g] > b[g + 1] for g in range(G))
+            uploaded, downloaded, resolved = set(), [], set()
+            prev_lo = None
+            for g in range(G):
+                t_lo, t_hi = b[g + 1], b[g]
+                uploaded |= set(range(t_lo, t_hi))
+                r_hi, r_lo = (T - 1 if g == 0 else t_hi), t_lo
+                assert prev_lo is None or r_hi == prev_lo          # ranges adjoin
+                prev_lo = r_lo
+                assert set(range(r_lo, r_hi + 1)) <= uploaded      # a range only touches temperatures that have landed
+                resolved |= set(range(r_lo + 1, r_hi + 1))         # swaps (r, r-1) for r = r_hi .. r_lo+1
+                f_lo = 0 if g == G - 1 else r_lo + 1
+                final = list(range(f_lo, r_hi + 1))
+                assert all(r in resolved or r == 0 for r in final)
+                downloaded += final
+            assert sorted(downloaded) == list(range(T)) and resolved == set(range(1, T))

@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_mgpu.py -m gpu -q -x 2>&1 | tail -6 | tee gpurun_out/r02_mgpu_n2.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 200 --warmup 10 > gpurun_out/r02_bench_n2_auto.json 2> gpurun_out/r02_bench_n2_auto.err; echo "n2 rc=$?"; tail -1 gpurun_out/r02_bench_n2_auto.err
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 200 --warmup 10 > gpurun_out/r02_bench_n2_auto.json 2> gpurun_out/r02_bench_n2_auto.err; echo "n2 rc=$?"; tail -1 gpurun_out/r02_bench_n2_auto.err
 python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/r02_bench_n2_auto.json").read().strip().splitlines()[-1])
-print({k:d[k] for k in ("value","ms_per_step")}, d.get("parity",{}).get("ok"), d["extra"].get("c4_strong",{}).get("speedup_vs_1gpu"))
+print({k:d[k] for k in ("value","ms_per_step")}, d.get("parity"), d["extra"].get("c4_strong",{}).get("speedup_vs_1gpu"))
 PY
