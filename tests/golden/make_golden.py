@@ -16,6 +16,7 @@ The cases mirror BASELINE.json's configs at sizes small enough to commit (<300 K
   gauss_matrix   3 temps x 24 walkers x 3-d, GaussianMove(full covariance) + PT
   odd_walkers    1 temp x 99 walkers x 5-d (tests/test_eryn.py:96 test_base shape), a=1.5
   noadapt_noperm 4 temps x 32 walkers, adaptive=False, permute=False
+  stop_adapt     5 temps x 40 walkers, adaptation_lag=30, adaptation_time=4, stop_adaptation=6   (argv: stop_adapt)
   gauss_modes    (`gauss_modes`) GaussianMove modes random / sequential / vector and `factor`
   mt_mix         (`mt`) 3 temps x 16 walkers x 3-d, MTDistGenMove(num_try=6, independent) mixed with StretchMove
   gibbs_mix      (`gibbs`) 3 temps x 24 walkers x 4-d, Stretch and Gaussian moves with parameter-level Gibbs splits
@@ -153,6 +154,12 @@ if __name__ == "__main__":
         # walkers start uniform over [0, 2 pi): the periodic distance (|c - s| > pi) and the wrap are exercised constantly
         run_case("periodic_mix", 21, 3, 24, 3, 40, ll_gauss_vec, [mu3, np.eye(3) / 0.49], True, 0.0, 2 * np.pi,
                  moves_factory=lambda: [(StretchMove(), 0.5), (GaussianMove({"model_0": 0.25}), 0.5)], periodic=per)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "stop_adapt":
+        # a fast-moving ladder (adaptation_lag = 30, adaptation_time = 4) that freezes once the adaptation clock reaches
+        # stop_adaptation = 6 (tempering.py:571-572, :590)
+        run_case("stop_adapt", 19, 3, 40, 5, 15, ll_gauss_vec, [np.zeros(3), np.eye(3)], True, -5.0, 5.0,
+                 tempering_kwargs=dict(stop_adaptation=6, adaptation_lag=30, adaptation_time=4))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "distgen":
         # prior-draw Metropolis move (distgen.py) mixed with the stretch move; narrow box so that prior draws get accepted

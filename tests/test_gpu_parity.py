@@ -80,6 +80,7 @@ def test_replay_matches_reference_golden(name):
     tk = {}
     if bool(g["tempered"]):
         tk = dict(ntemps=T, adaptive=c.get("adaptive", True), permute=c.get("permute", True))
+        tk.update(c.get("tempering", {}))
     moves = dev_moves(c["moves"], priors)
     w = c.get("weights", [1.0] * len(moves))
     periodic = None

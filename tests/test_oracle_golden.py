@@ -20,7 +20,7 @@ def make_oracle(name, g, streams):
         betas = orc.make_ladder_default(d, T) if T > 1 else np.array([1.0])
     return orc.OracleSampler(prior, c["like"](d), c["moves"], c.get("weights", [1.0]), streams, betas=betas,
                              adaptive=c.get("adaptive", True), permute=c.get("permute", True),
-                             periods=c.get("periods")), prior
+                             periods=c.get("periods"), **c.get("tempering", {})), prior
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
