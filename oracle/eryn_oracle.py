@@ -424,10 +424,11 @@ class NumpyStreams:
     def move_choice(self, it, weights):
         return int(self.private.choice(len(weights), p=weights))  # ensemble.py:971
 
-    def split_lists(self, it, T, W):
+    def split_lists(self, it, T, W, randomize=True):
         labels = np.tile(np.arange(W), (T, 1)) % 2  # red_blue.py:121-122
-        for row in labels:
-            self.glob.shuffle(row)  # :124
+        if randomize:  # red_blue.py:123 (StretchMove(randomize_split=...))
+            for row in labels:
+                self.glob.shuffle(row)  # :124
         ids = np.tile(np.arange(W), (T, 1))
         return [ids[labels == s].reshape(T, -1) for s in (0, 1)]  # :150-154 ascending ids
 
@@ -504,13 +505,14 @@ class PhiloxStreams:
     def move_choice(self, it, weights):
         return int(self.sched.choice(len(weights), p=weights))  # host-side schedule, as the reference
 
-    def split_lists(self, it, T, W):
+    def split_lists(self, it, T, W, randomize=True):
         n0 = (W + 1) // 2
         n1 = W // 2
         subs0 = np.empty((T, n0), dtype=np.int64)
         subs1 = np.empty((T, n1), dtype=np.int64)
         for t in range(T):
-            sig = px.split_perm(it, self.seed, self.t0 + t, W)
+            # randomize_split=False: the identity instead of the keyed bijection (csrc/k_stretch.cu:stretch_draw)
+            sig = px.split_perm(it, self.seed, self.t0 + t, W) if randomize else np.arange(W)
             subs0[t] = sig[0::2][:n0]
             subs1[t] = sig[1::2][:n1]
         return [subs0, subs1]
@@ -660,7 +662,8 @@ class OracleSampler:
         self.last_nsplits = len(gibbs)
         self.last_accept_sum = np.zeros((T, W), dtype=np.int64)  # what the reference adds to move.accepted in this call
         if move["kind"] == "stretch":
-            lists = st.split_lists(it, T, W)  # red_blue.py:118-124: one red/blue labelling for all Gibbs splits
+            # red_blue.py:118-124: one red/blue labelling for all Gibbs splits
+            lists = st.split_lists(it, T, W, randomize=move.get("randomize_split", True))
             for gi, gmask in enumerate(gibbs):
                 if gmask is not None and not np.any(state.inds[:, :, gmask.any(axis=-1)]):
                     continue  # setup_proposals: no leaf to propose for (red_blue.py:142-143)

@@ -58,6 +58,8 @@ CASES = {
                         weights=[0.5, 0.3, 0.2]),
     "mt_mix": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d) / 0.25),
                    moves=[dict(kind="stretch", a=2.0), dict(kind="mt", num_try=6)], weights=[0.4, 0.6]),
+    "nosplit": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                    moves=[dict(kind="stretch", a=2.0, randomize_split=False)]),
     "stop_adapt": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), moves=[dict(kind="stretch", a=2.0)],
                        tempering=dict(stop_adaptation=6, adaptation_lag=30, adaptation_time=4)),
     "noadapt_noperm": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),

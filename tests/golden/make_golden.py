@@ -16,6 +16,7 @@ The cases mirror BASELINE.json's configs at sizes small enough to commit (<300 K
   gauss_matrix   3 temps x 24 walkers x 3-d, GaussianMove(full covariance) + PT
   odd_walkers    1 temp x 99 walkers x 5-d (tests/test_eryn.py:96 test_base shape), a=1.5
   noadapt_noperm 4 temps x 32 walkers, adaptive=False, permute=False
+  nosplit        3 temps x 30 walkers, StretchMove(randomize_split=False)   (argv: nosplit)
   stop_adapt     5 temps x 40 walkers, adaptation_lag=30, adaptation_time=4, stop_adaptation=6   (argv: stop_adapt)
   gauss_modes    (`gauss_modes`) GaussianMove modes random / sequential / vector and `factor`
   mt_mix         (`mt`) 3 temps x 16 walkers x 3-d, MTDistGenMove(num_try=6, independent) mixed with StretchMove
@@ -160,6 +161,11 @@ if __name__ == "__main__":
         # stop_adaptation = 6 (tempering.py:571-572, :590)
         run_case("stop_adapt", 19, 3, 40, 5, 15, ll_gauss_vec, [np.zeros(3), np.eye(3)], True, -5.0, 5.0,
                  tempering_kwargs=dict(stop_adaptation=6, adaptation_lag=30, adaptation_time=4))
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "nosplit":
+        # StretchMove(randomize_split=False) (red_blue.py:123): even / odd walkers, no shuffle drawn from the global stream
+        run_case("nosplit", 23, 4, 30, 3, 20, ll_gauss_vec, [np.zeros(4), np.eye(4)], True, -5.0, 5.0,
+                 moves_factory=lambda: StretchMove(randomize_split=False))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "distgen":
         # prior-draw Metropolis move (distgen.py) mixed with the stretch move; narrow box so that prior draws get accepted

@@ -46,7 +46,7 @@ def dev_moves(moves, priors=None):
         if m["kind"] == "combine":
             out.append(CombineMove(dev_moves(m["moves"], priors)))
         elif m["kind"] == "stretch":
-            out.append(StretchMove(a=m.get("a", 2.0), **kw))
+            out.append(StretchMove(a=m.get("a", 2.0), randomize_split=m.get("randomize_split", True), **kw))
         elif m["kind"] == "distgen":
             out.append(DistributionGenerate({"model_0": priors}))
         elif m["kind"] == "mt":  # generate_dist as a bare ProbDistContainer, as the reference's test passes it
@@ -167,6 +167,8 @@ PHILOX_CASES = {
                 [dict(kind="combine", moves=[dict(kind="stretch", a=2.0),
                                              dict(kind="gaussian", proposal=dict(kind="scalar", scale=0.4))])], [1.0], 10, -5, 5),
     "distgen_d8": (2, 128, 8, c2_like, [dict(kind="distgen")], [1.0], 6, -1, 1),
+    "nosplit": (3, 99, 5, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                [dict(kind="stretch", a=2.0, randomize_split=False)], [1.0], 10, -5, 5),
     "d13": (2, 64, 13, lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), [dict(kind="stretch", a=2.0)], [1.0], 8, -5, 5),
     "d18": (2, 64, 18, lambda d: orc.RosenbrockLike(), [dict(kind="stretch", a=2.0)], [1.0], 8, -5, 5),
     "d30": (2, 128, 30, gmix_like, [dict(kind="stretch", a=2.0)], [1.0], 6, -10, 10),
