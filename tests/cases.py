@@ -58,6 +58,9 @@ CASES = {
                         weights=[0.5, 0.3, 0.2]),
     "mt_mix": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d) / 0.25),
                    moves=[dict(kind="stretch", a=2.0), dict(kind="mt", num_try=6)], weights=[0.4, 0.6]),
+    "tiny_live": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
+                      moves=[dict(kind="stretch", a=2.0, live_dangerously=True)]),
+    "one_temp": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), moves=[dict(kind="stretch", a=2.0)]),
     "nosplit": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)),
                     moves=[dict(kind="stretch", a=2.0, randomize_split=False)]),
     "stop_adapt": dict(like=lambda d: orc.GaussianLike(np.zeros(d), np.eye(d)), moves=[dict(kind="stretch", a=2.0)],

@@ -16,6 +16,8 @@ The cases mirror BASELINE.json's configs at sizes small enough to commit (<300 K
   gauss_matrix   3 temps x 24 walkers x 3-d, GaussianMove(full covariance) + PT
   odd_walkers    1 temp x 99 walkers x 5-d (tests/test_eryn.py:96 test_base shape), a=1.5
   noadapt_noperm 4 temps x 32 walkers, adaptive=False, permute=False
+  tiny_live      3 temps x 6 walkers x 5-d, StretchMove(live_dangerously=True)   (argv: tiny)
+  one_temp       tempering_kwargs=dict(ntemps=1): 1 temp x 20 walkers              (argv: tiny)
   nosplit        3 temps x 30 walkers, StretchMove(randomize_split=False)   (argv: nosplit)
   stop_adapt     5 temps x 40 walkers, adaptation_lag=30, adaptation_time=4, stop_adaptation=6   (argv: stop_adapt)
   gauss_modes    (`gauss_modes`) GaussianMove modes random / sequential / vector and `factor`
@@ -166,6 +168,13 @@ if __name__ == "__main__":
         # StretchMove(randomize_split=False) (red_blue.py:123): even / odd walkers, no shuffle drawn from the global stream
         run_case("nosplit", 23, 4, 30, 3, 20, ll_gauss_vec, [np.zeros(4), np.eye(4)], True, -5.0, 5.0,
                  moves_factory=lambda: StretchMove(randomize_split=False))
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tiny":
+        # edge cases of the shapes: fewer walkers than 2 ndim (live_dangerously=True, red_blue.py:103-114), 3 walkers per
+        # half; and a tempered sampler with ONE temperature (no swap, no adaptation: tempering.py:515, :632)
+        run_case("tiny_live", 31, 5, 6, 3, 25, ll_gauss_vec, [np.zeros(5), np.eye(5)], True, -5.0, 5.0,
+                 moves_factory=lambda: StretchMove(live_dangerously=True))
+        run_case("one_temp", 37, 4, 20, 1, 20, ll_gauss_vec, [np.zeros(4), np.eye(4)], True, -5.0, 5.0)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "distgen":
         # prior-draw Metropolis move (distgen.py) mixed with the stretch move; narrow box so that prior draws get accepted

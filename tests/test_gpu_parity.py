@@ -46,7 +46,8 @@ def dev_moves(moves, priors=None):
         if m["kind"] == "combine":
             out.append(CombineMove(dev_moves(m["moves"], priors)))
         elif m["kind"] == "stretch":
-            out.append(StretchMove(a=m.get("a", 2.0), randomize_split=m.get("randomize_split", True), **kw))
+            out.append(StretchMove(a=m.get("a", 2.0), randomize_split=m.get("randomize_split", True),
+                                   live_dangerously=m.get("live_dangerously", False), **kw))
         elif m["kind"] == "distgen":
             out.append(DistributionGenerate({"model_0": priors}))
         elif m["kind"] == "mt":  # generate_dist as a bare ProbDistContainer, as the reference's test passes it
